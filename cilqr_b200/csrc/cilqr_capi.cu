@@ -1,0 +1,541 @@
+// cilqr_capi.cu -- extern "C" shim (include/cilqr_b200.h) over the sm_100a solve kernel.
+//
+// Replaces, for the host program, IlqrOptimizer's constructor/Init (ilqr_optimizer.cc:13-51) with
+// cilqr_create and IlqrOptimizer::Plan (ilqr_optimizer.cc:53-95) with cilqr_plan_batch.  There is
+// no CPU path in this library: without a CUDA device every entry point fails with
+// CILQR_E_NO_DEVICE / CILQR_E_CUDA.
+#include "cilqr_kernel.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "../../include/cilqr_b200.h"
+
+using cilqr::DevParams;
+using cilqr::KernelArgs;
+using cilqr::SmemLayout;
+
+namespace {
+
+constexpr int kSlots = 2;           // double buffering of the host path
+constexpr int kDefaultChunk = 8192; // scenarios per pipelined chunk on the host path
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  unsigned int* ticket = nullptr;
+  double* ws = nullptr;
+  size_t ws_bytes = 0;
+  // device staging for the host API
+  char* in_buf = nullptr;
+  char* out_buf = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace
+
+struct cilqr_handle {
+  int device = 0;
+  int num_sms = 0;
+  int smem_optin = 0;
+  CilqrParams params;
+  DevParams dev;
+  int N_max = 0, M_max = 0, S_max = 0, B_max = 0;
+  int chunk = kDefaultChunk;
+  Slot slots[kSlots];
+  int64_t launches = 0;
+  int last_slot = 0;
+  bool timed = false;
+  std::string cuda_err;
+};
+
+namespace {
+
+int fail_cuda(cilqr_handle* h, cudaError_t e, const char* where) {
+  if (h) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", where, cudaGetErrorString(e));
+    h->cuda_err = buf;
+  }
+  return CILQR_E_CUDA;
+}
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return fail_cuda(h, e_, #call);  \
+  } while (0)
+
+void make_dev_params(const CilqrParams& p, DevParams* d) {
+  d->dt = p.delta_t;
+  d->L = p.wheel_base;
+  d->rt = 1.0 / p.barrier_t;
+  d->eps = p.barrier_eps;
+  d->inv_eps = 1.0 / p.barrier_eps;
+  d->inv_eps2 = 1.0 / (p.barrier_eps * p.barrier_eps);
+  d->relax_c = -0.5 * d->rt - d->rt * log(p.barrier_eps);
+  d->vmax = p.max_velocity;
+  d->amin = p.min_acceleration;
+  d->amax = p.max_acceleration;
+  d->dmin = p.delta_min;
+  d->dmax = p.delta_max;
+  d->jmin = p.jerk_min;
+  d->jmax = p.jerk_max;
+  d->drmin = p.delta_rate_min;
+  d->drmax = p.delta_rate_max;
+  d->wx = p.w_x_target;
+  d->wy = p.w_y_target;
+  d->wth = p.w_theta;
+  d->wv = p.w_v;
+  d->wa = p.w_a;
+  d->wd = p.w_delta;
+  d->wj = p.w_jerk;
+  d->wdr = p.w_delta_rate;
+  d->abs_tol = p.abs_cost_tol;
+  d->rel_tol = p.rel_cost_tol;
+  // disc centres, ilqr_optimizer.cc:556-565
+  const double Ld = (p.rear_hang_length + p.wheel_base + p.front_hang_length) / p.num_of_disc;
+  for (int j = 0; j < cilqr::kDisc; ++j) d->off[j] = (Ld * (j - 0.5) - p.rear_hang_length);
+  // CalculateDiscRadius, ilqr_optimizer.cc:97-104
+  const double length = p.front_hang_length + p.wheel_base + p.rear_hang_length;
+  const double r = hypot(p.width / 2.0, length / 2.0 / p.num_of_disc);
+  d->shrink_corr = r + p.safe_margin;
+  d->shrink_lane = r;
+  d->max_iter = p.max_iter_num;
+}
+
+SmemLayout make_layout(int N, int S_left, int S_right) {
+  SmemLayout L;
+  const int K = N + 1;
+  int o = 0;
+  L.X = o; o += K * 6;
+  L.U = o; o += N * 2;
+  L.Xc = o; o += K * 6;
+  L.Uc = o; o += N * 2;
+  L.Kg = o; o += N * 12;
+  L.kg = o; o += N * 2;
+  L.lin = o; o += 32 * cilqr::kLinStride;
+  o += (o & 1);
+  L.seg = o; o += (S_left + S_right) * cilqr::kSegStride;
+  L.scr = o; o += cilqr::kScratch;
+  L.nidx = o;
+  L.nidx_bytes = (K * 10 + 7) / 8 * 8;
+  L.total_bytes = o * 8 + 2 * L.nidx_bytes;
+  return L;
+}
+
+struct Launch {
+  SmemLayout sm;
+  int blocks_per_sm = 0;
+  int grid = 0;
+  int Kp = 0;
+};
+
+int plan_launch(cilqr_handle* h, int B, int N, int S_left, int S_right, Launch* out) {
+  Launch L;
+  L.sm = make_layout(N, S_left, S_right);
+  L.Kp = (N + 1 + 31) / 32 * 32;
+  if (L.sm.total_bytes > h->smem_optin) return CILQR_E_SMEM;
+  CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, cilqr::cilqr_solve_kernel, 32, L.sm.total_bytes));
+  if (L.blocks_per_sm < 1) return CILQR_E_SMEM;
+  // persistent grid: one CTA (= one warp) per resident slot of every SM
+  L.grid = std::min(B, h->num_sms * L.blocks_per_sm);
+  if (L.grid < 1) L.grid = 1;
+  *out = L;
+  return CILQR_OK;
+}
+
+int ensure_ws(cilqr_handle* h, Slot* s, size_t bytes) {
+  if (s->ws_bytes >= bytes) return CILQR_OK;
+  CK(cudaStreamSynchronize(s->stream));
+  if (s->ws) CK(cudaFree(s->ws));
+  s->ws = nullptr;
+  s->ws_bytes = 0;
+  CK(cudaMalloc(&s->ws, bytes));
+  s->ws_bytes = bytes;
+  return CILQR_OK;
+}
+
+int validate(const cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out) {
+  if (!h || !in || !out) return CILQR_E_INVALID;
+  // guards of IlqrOptimizer::Plan, ilqr_optimizer.cc:64-78
+  if (!out->states || !out->controls || !out->status) return CILQR_E_INVALID;
+  if (!in->start || !in->coarse || !in->corridor || !in->corridor_cnt || !in->lane_left || !in->lane_right)
+    return CILQR_E_INVALID;
+  if (in->B < 0 || in->N < 1 || in->M_max < 1 || in->S_left < 1 || in->S_right < 1) return CILQR_E_INVALID;
+  if (in->S_left > 255 || in->S_right > 255) return CILQR_E_CAPACITY;  // nearest index is cached as a byte
+  if (in->N > h->N_max || in->M_max > h->M_max || in->S_left > h->S_max || in->S_right > h->S_max)
+    return CILQR_E_CAPACITY;
+  if ((out->iter_states || out->cost_hist) && out->hist_cap < 1) return CILQR_E_INVALID;
+  return CILQR_OK;
+}
+
+int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatchIn* in, const CilqrBatchOut* out,
+                 const CilqrDebugOut* dbg) {
+  if (in->B == 0) return CILQR_OK;
+  Launch L;
+  int rc = plan_launch(h, in->B, in->N, in->S_left, in->S_right, &L);
+  if (rc != CILQR_OK) return rc;
+  rc = ensure_ws(h, s, (size_t)L.grid * in->M_max * 3 * L.Kp * sizeof(double));
+  if (rc != CILQR_OK) return rc;
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = h->dev;
+  a.sm = L.sm;
+  a.B = in->B;
+  a.N = in->N;
+  a.M_max = in->M_max;
+  a.S_left = in->S_left;
+  a.S_right = in->S_right;
+  a.Kp = L.Kp;
+  a.start = in->start;
+  a.coarse = in->coarse;
+  a.corridor = in->corridor;
+  a.corridor_cnt = in->corridor_cnt;
+  a.lane_left = in->lane_left;
+  a.lane_right = in->lane_right;
+  a.states = out->states;
+  a.controls = out->controls;
+  a.status = out->status;
+  a.trajectory = out->trajectory;
+  a.init_states = out->init_states;
+  a.init_controls = out->init_controls;
+  a.cost_hist = out->cost_hist;
+  a.iter_states = out->iter_states;
+  a.iter_controls = out->iter_controls;
+  a.hist_len = out->hist_len;
+  a.hist_cap = out->hist_cap;
+  a.ws = s->ws;
+  a.ticket = s->ticket;
+  a.debug = 0;
+  if (dbg) {
+    a.debug = 1;
+    a.dbg.corridor = dbg->corridor;
+    a.dbg.lanes = dbg->lanes;
+    a.dbg.X0 = dbg->X0;
+    a.dbg.U0 = dbg->U0;
+    a.dbg.cost0 = dbg->cost0;
+    a.dbg.A11 = dbg->A11;
+    a.dbg.Jx = dbg->Jx;
+    a.dbg.Ju = dbg->Ju;
+    a.dbg.Hx = dbg->Hx;
+    a.dbg.Hu = dbg->Hu;
+    a.dbg.Kg = dbg->Kg;
+    a.dbg.kg = dbg->kg;
+    a.dbg.dV = dbg->dV;
+    a.dbg.Xn = dbg->Xn;
+    a.dbg.Un = dbg->Un;
+    a.dbg.costn = dbg->costn;
+    a.dbg.nearest = dbg->nearest;
+  }
+  CK(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), stream));
+  CK(cudaEventRecord(s->ev0, stream));
+  cilqr::cilqr_solve_kernel<<<L.grid, 32, L.sm.total_bytes, stream>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s->ev1, stream));
+  h->launches += 1;
+  h->last_slot = (int)(s - h->slots);
+  h->timed = true;
+  return CILQR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cilqr_abi_version(void) { return CILQR_ABI_VERSION; }
+
+void cilqr_default_params(CilqrParams* p) {
+  if (!p) return;
+  // vehicle_param.h:26-64
+  p->front_hang_length = 0.96;
+  p->wheel_base = 1.0;
+  p->rear_hang_length = 0.929;
+  p->width = 1.942;
+  p->max_velocity = 20.0;
+  p->min_acceleration = -5.0;
+  p->max_acceleration = 5.0;
+  p->jerk_min = -10.0;
+  p->jerk_max = 10.0;
+  p->delta_min = -40.0 / 180 * M_PI;
+  p->delta_max = 40.0 / 180 * M_PI;
+  p->delta_rate_min = p->delta_min / 3.0;
+  p->delta_rate_max = p->delta_max / 3.0;
+  // planner_config.h:45-66
+  p->safe_margin = 0.2;
+  p->w_jerk = 1;
+  p->w_delta_rate = 1;
+  p->w_x_target = 0.5;
+  p->w_y_target = 0.5;
+  p->w_theta = 1e-3;
+  p->w_v = 0.0;
+  p->w_a = 0.0;
+  p->w_delta = 0.0;
+  p->abs_cost_tol = 1e-2;
+  p->rel_cost_tol = 1e-2;
+  // barrier_function.h:143-146
+  p->barrier_t = 5.0;
+  p->barrier_eps = 0.01;
+  p->delta_t = 0.1;  // planner_config.h:94
+  p->num_of_disc = 5;
+  p->max_iter_num = 200;
+}
+
+const char* cilqr_strerror(int code) {
+  switch (code) {
+    case CILQR_OK: return "ok";
+    case CILQR_E_INVALID: return "invalid argument (null pointer, empty constraint set or bad size)";
+    case CILQR_E_CUDA: return "CUDA runtime error";
+    case CILQR_E_NO_DEVICE: return "no CUDA device of compute capability 10.x (this library has no CPU fallback)";
+    case CILQR_E_CAPACITY: return "request exceeds the capacity the handle was created with";
+    case CILQR_E_SMEM: return "horizon does not fit the per-warp shared-memory stage";
+    default: return "unknown error";
+  }
+}
+
+const char* cilqr_last_cuda_error(const cilqr_handle* h) { return h ? h->cuda_err.c_str() : ""; }
+
+int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, int S_max, int B_max,
+                 cilqr_handle** out) {
+  if (!out) return CILQR_E_INVALID;
+  *out = nullptr;
+  if (!params || N_max < 1 || M_max < 1 || S_max < 1 || B_max < 1) return CILQR_E_INVALID;
+  if (params->num_of_disc != cilqr::kDisc) return CILQR_E_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return CILQR_E_NO_DEVICE;
+  }
+  cilqr_handle* h = new (std::nothrow) cilqr_handle();
+  if (!h) return CILQR_E_INVALID;
+  h->device = device;
+  h->params = *params;
+  make_dev_params(*params, &h->dev);
+  h->N_max = N_max;
+  h->M_max = M_max;
+  h->S_max = S_max;
+  h->B_max = B_max;
+  const char* env_chunk = getenv("CILQR_CHUNK");
+  if (env_chunk && atoi(env_chunk) > 0) h->chunk = atoi(env_chunk);
+  auto bail = [&](int rc) {
+    cilqr_destroy(h);
+    return rc;
+  };
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    return bail(CILQR_E_CUDA);
+  }
+  if (prop.major != 10) return bail(CILQR_E_NO_DEVICE);
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (make_layout(N_max, S_max, S_max).total_bytes > h->smem_optin) return bail(CILQR_E_SMEM);
+  for (int i = 0; i < kSlots; ++i) {
+    Slot* s = &h->slots[i];
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->ticket, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
+  }
+  *out = h;
+  return CILQR_OK;
+}
+
+void cilqr_destroy(cilqr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < kSlots; ++i) {
+    Slot* s = &h->slots[i];
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->ticket) cudaFree(s->ticket);
+    if (s->ws) cudaFree(s->ws);
+    if (s->in_buf) cudaFree(s->in_buf);
+    if (s->out_buf) cudaFree(s->out_buf);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+  }
+  delete h;
+}
+
+int cilqr_plan_batch_device(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out, void* cuda_stream) {
+  int rc = validate(h, in, out);
+  if (rc != CILQR_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  Slot* s = &h->slots[0];
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+  return launch_solve(h, s, st, in, out, nullptr);
+}
+
+int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in, const CilqrDebugOut* dbg) {
+  if (!h || !in || !dbg) return CILQR_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  // the regular outputs are still produced; park them in scratch device memory
+  const size_t K = in->N + 1;
+  double* tmp = nullptr;
+  const size_t n = (size_t)in->B * (K * 6 + (size_t)in->N * 2 + 8);
+  CK(cudaMalloc(&tmp, n * sizeof(double)));
+  CilqrBatchOut out;
+  memset(&out, 0, sizeof(out));
+  out.states = tmp;
+  out.controls = tmp + (size_t)in->B * K * 6;
+  out.status = out.controls + (size_t)in->B * in->N * 2;
+  int rc = validate(h, in, &out);
+  if (rc == CILQR_OK) rc = launch_solve(h, &h->slots[0], h->slots[0].stream, in, &out, dbg);
+  cudaError_t e = cudaStreamSynchronize(h->slots[0].stream);
+  cudaFree(tmp);
+  if (rc != CILQR_OK) return rc;
+  if (e != cudaSuccess) return fail_cuda(h, e, "debug kernel");
+  return CILQR_OK;
+}
+
+int cilqr_synchronize(cilqr_handle* h) {
+  if (!h) return CILQR_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  for (int i = 0; i < kSlots; ++i) CK(cudaStreamSynchronize(h->slots[i].stream));
+  return CILQR_OK;
+}
+
+// Host path: chunks of `chunk` scenarios are pipelined over two streams, each doing
+// H2D(inputs) -> solve -> D2H(outputs); copies of one chunk overlap the solve of the other.
+int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out) {
+  int rc = validate(h, in, out);
+  if (rc != CILQR_OK) return rc;
+  if (in->B > h->B_max) return CILQR_E_CAPACITY;
+  CK(cudaSetDevice(h->device));
+  const size_t K = in->N + 1, N = in->N, M = in->M_max;
+  const int chunk = std::max(1, std::min(h->chunk, in->B));
+  const int H = out->hist_cap;
+  // per-scenario byte counts
+  const size_t b_start = 4 * 8, b_coarse = K * 6 * 8, b_corr = K * M * 3 * 8, b_cnt = K * 4;
+  const size_t b_ll = (size_t)in->S_left * 7 * 8, b_lr = (size_t)in->S_right * 7 * 8;
+  const size_t b_st = K * 6 * 8, b_ct = N * 2 * 8, b_status = 8 * 8, b_traj = K * 13 * 8;
+  const size_t b_ch = (size_t)H * 5 * 8, b_is = (size_t)H * K * 6 * 8, b_ic = (size_t)H * N * 2 * 8, b_hl = 2 * 4;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t in_need = up(b_start * chunk) + up(b_coarse * chunk) + up(b_corr * chunk) + up(b_cnt * chunk) +
+                         up(b_ll * chunk) + up(b_lr * chunk);
+  size_t out_need = up(b_st * chunk) + up(b_ct * chunk) + up(b_status * chunk);
+  if (out->trajectory) out_need += up(b_traj * chunk);
+  if (out->init_states) out_need += up(b_st * chunk);
+  if (out->init_controls) out_need += up(b_ct * chunk);
+  if (out->cost_hist) out_need += up(b_ch * chunk);
+  if (out->iter_states) out_need += up(b_is * chunk);
+  if (out->iter_controls) out_need += up(b_ic * chunk);
+  if (out->hist_len) out_need += up(b_hl * chunk);
+  for (int i = 0; i < kSlots; ++i) {
+    Slot* s = &h->slots[i];
+    if (s->in_bytes < in_need) {
+      CK(cudaStreamSynchronize(s->stream));
+      if (s->in_buf) CK(cudaFree(s->in_buf));
+      s->in_buf = nullptr;
+      s->in_bytes = 0;
+      CK(cudaMalloc(&s->in_buf, in_need));
+      s->in_bytes = in_need;
+    }
+    if (s->out_bytes < out_need) {
+      CK(cudaStreamSynchronize(s->stream));
+      if (s->out_buf) CK(cudaFree(s->out_buf));
+      s->out_buf = nullptr;
+      s->out_bytes = 0;
+      CK(cudaMalloc(&s->out_buf, out_need));
+      s->out_bytes = out_need;
+    }
+  }
+  int ci = 0;
+  for (int b0 = 0; b0 < in->B; b0 += chunk, ++ci) {
+    const int nb = std::min(chunk, in->B - b0);
+    Slot* s = &h->slots[ci % kSlots];
+    char* p = s->in_buf;
+    auto h2d = [&](const void* src, size_t per, char** dev) -> cudaError_t {
+      *dev = p;
+      p += up(per * chunk);
+      return cudaMemcpyAsync(*dev, (const char*)src + per * b0, per * nb, cudaMemcpyHostToDevice, s->stream);
+    };
+    char *d_start, *d_coarse, *d_corr, *d_cnt, *d_ll, *d_lr;
+    CK(h2d(in->start, b_start, &d_start));
+    CK(h2d(in->coarse, b_coarse, &d_coarse));
+    CK(h2d(in->corridor, b_corr, &d_corr));
+    CK(h2d(in->corridor_cnt, b_cnt, &d_cnt));
+    CK(h2d(in->lane_left, b_ll, &d_ll));
+    CK(h2d(in->lane_right, b_lr, &d_lr));
+    CilqrBatchIn din = *in;
+    din.B = nb;
+    din.start = (const double*)d_start;
+    din.coarse = (const double*)d_coarse;
+    din.corridor = (const double*)d_corr;
+    din.corridor_cnt = (const int32_t*)d_cnt;
+    din.lane_left = (const double*)d_ll;
+    din.lane_right = (const double*)d_lr;
+    char* q = s->out_buf;
+    auto carve = [&](bool want, size_t per) -> char* {
+      if (!want) return nullptr;
+      char* r = q;
+      q += up(per * chunk);
+      return r;
+    };
+    CilqrBatchOut dout;
+    memset(&dout, 0, sizeof(dout));
+    dout.hist_cap = H;
+    dout.states = (double*)carve(true, b_st);
+    dout.controls = (double*)carve(true, b_ct);
+    dout.status = (double*)carve(true, b_status);
+    dout.trajectory = (double*)carve(out->trajectory != nullptr, b_traj);
+    dout.init_states = (double*)carve(out->init_states != nullptr, b_st);
+    dout.init_controls = (double*)carve(out->init_controls != nullptr, b_ct);
+    dout.cost_hist = (double*)carve(out->cost_hist != nullptr, b_ch);
+    dout.iter_states = (double*)carve(out->iter_states != nullptr, b_is);
+    dout.iter_controls = (double*)carve(out->iter_controls != nullptr, b_ic);
+    dout.hist_len = (int32_t*)carve(out->hist_len != nullptr, b_hl);
+    if (dout.cost_hist) CK(cudaMemsetAsync(dout.cost_hist, 0, b_ch * nb, s->stream));
+    rc = launch_solve(h, s, s->stream, &din, &dout, nullptr);
+    if (rc != CILQR_OK) return rc;
+    auto d2h = [&](void* dst, const void* dev, size_t per) -> cudaError_t {
+      if (!dst) return cudaSuccess;
+      return cudaMemcpyAsync((char*)dst + per * b0, dev, per * nb, cudaMemcpyDeviceToHost, s->stream);
+    };
+    CK(d2h(out->states, dout.states, b_st));
+    CK(d2h(out->controls, dout.controls, b_ct));
+    CK(d2h(out->status, dout.status, b_status));
+    CK(d2h(out->trajectory, dout.trajectory, b_traj));
+    CK(d2h(out->init_states, dout.init_states, b_st));
+    CK(d2h(out->init_controls, dout.init_controls, b_ct));
+    CK(d2h(out->cost_hist, dout.cost_hist, b_ch));
+    CK(d2h(out->iter_states, dout.iter_states, b_is));
+    CK(d2h(out->iter_controls, dout.iter_controls, b_ic));
+    CK(d2h(out->hist_len, dout.hist_len, b_hl));
+  }
+  for (int i = 0; i < kSlots; ++i) CK(cudaStreamSynchronize(h->slots[i].stream));
+  return CILQR_OK;
+}
+
+int cilqr_kernel_launches(const cilqr_handle* h, int64_t* solve_launches) {
+  if (!h || !solve_launches) return CILQR_E_INVALID;
+  *solve_launches = h->launches;
+  return CILQR_OK;
+}
+
+int cilqr_last_kernel_ms(cilqr_handle* h, float* ms) {
+  if (!h || !ms || !h->timed) return CILQR_E_INVALID;
+  Slot* s = &h->slots[h->last_slot];
+  CK(cudaEventSynchronize(s->ev1));
+  CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+  return CILQR_OK;
+}
+
+int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* warps_per_sm,
+                    int* smem_bytes_per_warp) {
+  if (!h) return CILQR_E_INVALID;
+  Launch L;
+  int rc = plan_launch(const_cast<cilqr_handle*>(h), 1 << 30, N, S_left, S_right, &L);
+  if (rc != CILQR_OK) return rc;
+  if (warps_per_sm) *warps_per_sm = L.blocks_per_sm;
+  if (smem_bytes_per_warp) *smem_bytes_per_warp = L.sm.total_bytes;
+  return CILQR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1135 @@
+// cilqr_kernel.cuh -- device code of the batched CILQR solver (sm_100a).
+//
+// One warp (= one 32-thread CTA) solves one scenario at a time; a persistent grid pulls scenario
+// ids from an atomic ticket because iteration counts are ragged.  The whole horizon of the
+// iterate (x, u), the line-search candidate (x', u'), the feedback gains (K, k), the lane
+// segments and a 32-knot window of the linearisation (A, B, Jx, Ju, Hx, Hu) are staged in
+// shared memory; the shrunk + normalised corridor half-planes live in a per-CTA global
+// workspace ([plane][component][knot] so that lane == knot loads are coalesced) that stays L2
+// resident.  All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>);
+// B200 has a full-rate FP64 pipe (64 lanes/clk/SM), no tensor cores are involved.
+//
+// Reference functions re-created here (file:line relative to the reference root):
+//   ShrinkConstraints / NormalizeHalfPlane   algorithm/ilqr/ilqr_optimizer.cc:438-495
+//   iqr (LQR initial guess)                  algorithm/ilqr/ilqr_optimizer.cc:793-842
+//   Dynamics / DynamicsJacbian               algorithm/ilqr/vehicle_model.cc:88-121, 21-86
+//   RelaxBarrierFunction                     algorithm/ilqr/barrier_function.h:104-140
+//   TotalCost (J, Dynamics, Corridor, Lane)  algorithm/ilqr/ilqr_optimizer.cc:417-436, 497-603
+//   FindNeastLaneSegment / DistanceTo        algorithm/ilqr/ilqr_optimizer.cc:605-618,
+//                                            algorithm/math/line_segment2d.cpp:61-75
+//   CostJacbian / CostHessian                algorithm/ilqr/ilqr_optimizer.cc:620-769
+//   Backward / Forward / CalGradientNorm     algorithm/ilqr/ilqr_optimizer.cc:334-415, 322-332
+//   Optimize (line search, lambda schedule)  algorithm/ilqr/ilqr_optimizer.cc:154-320
+//   TransformToTrajectory                    algorithm/ilqr/ilqr_optimizer.cc:771-791
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cilqr {
+
+constexpr int kNX = 6;
+constexpr int kNU = 2;
+constexpr int kDisc = 5;
+constexpr int kNAlpha = 11;
+constexpr int kLinStride = 31;  // doubles per knot in the linearisation window
+constexpr int kSegStride = 10;  // sx sy ex ey ux uy len a b c
+constexpr int kScratch = 192;   // doubles of per-warp scratch
+constexpr unsigned kFull = 0xffffffffu;
+
+// linearisation record offsets
+constexpr int LA = 0;    // A02 A03 A04 A05 A12 A13 A14 A15 A23 A24 A25
+constexpr int LB21 = 11;
+constexpr int LJX = 12;  // 6
+constexpr int LJU = 18;  // 2
+constexpr int LHX = 20;  // H00 H01 H02 H11 H12 H22 H33 H44 H55
+constexpr int LHU = 29;  // 2
+
+struct DevParams {
+  double dt, L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
+  double vmax, amin, amax, dmin, dmax, jmin, jmax, drmin, drmax;
+  double wx, wy, wth, wv, wa, wd, wj, wdr;
+  double abs_tol, rel_tol;
+  double off[kDisc];  // L_disc*(j-0.5) - rear_hang   (ilqr_optimizer.cc:556-565)
+  double shrink_corr, shrink_lane;
+  int max_iter;
+};
+
+struct SmemLayout {  // offsets in doubles from the start of dynamic shared memory
+  int X, U, Xc, Uc, Kg, kg, lin, seg, scr, nidx;  // nidx: two byte arrays of nidx_bytes each
+  int nidx_bytes;
+  int total_bytes;
+};
+
+struct DebugPtrs {
+  double *corridor, *lanes, *X0, *U0, *cost0, *A11, *Jx, *Ju, *Hx, *Hu, *Kg, *kg, *dV, *Xn, *Un, *costn;
+  int32_t* nearest;
+};
+
+struct KernelArgs {
+  DevParams P;
+  SmemLayout sm;
+  int B, N, M_max, S_left, S_right, Kp;
+  const double* start;
+  const double* coarse;
+  const double* corridor;
+  const int32_t* corridor_cnt;
+  const double* lane_left;
+  const double* lane_right;
+  double* states;
+  double* controls;
+  double* status;
+  double* trajectory;
+  double* init_states;
+  double* init_controls;
+  double* cost_hist;
+  double* iter_states;
+  double* iter_controls;
+  int32_t* hist_len;
+  int hist_cap;
+  double* ws;           // [gridDim.x][M_max*3*Kp]
+  unsigned int* ticket; // scenario counter
+  DebugPtrs dbg;
+  int debug;            // 1: stop after the first iteration and dump stages
+};
+
+__constant__ double kAlphaList[kNAlpha] = {1.0000, 0.5012, 0.2512, 0.1259, 0.0631, 0.0316,
+                                           0.0158, 0.0079, 0.0040, 0.0020, 0.0010};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return __shfl_sync(kFull, v, 0);
+}
+
+// math_utils.cpp:53-59.  fmod(a + pi, 2pi) == a + pi exactly whenever 0 <= a + pi < 2pi, which
+// is the only case the solver produces in practice; the general path is kept for parity.
+__device__ __forceinline__ double normalize_angle(double angle) {
+  const double kPi = 3.14159265358979323846;
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  double a = angle + kPi;
+  if (!(a >= 0.0 && a < kTwoPi)) {
+    a = fmod(a, kTwoPi);
+    if (a < 0.0) a += kTwoPi;
+  }
+  return a - kPi;
+}
+
+// vehicle_model.cc:88-138: midpoint RK2, same control at both stages, wrap theta and delta.
+__device__ __forceinline__ void dynamics_step(const DevParams& P, double* x, double u0, double u1) {
+  double s1, c1;
+  const double th = normalize_angle(x[2]);
+  const double de = normalize_angle(x[5]);
+  sincos(th, &s1, &c1);
+  const double k1x = x[3] * c1, k1y = x[3] * s1, k1t = x[3] * tan(de) / P.L;
+  const double h = 0.5 * P.dt;
+  const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
+  double s2, c2;
+  const double thm = normalize_angle(m2);
+  const double dem = normalize_angle(m5);
+  sincos(thm, &s2, &c2);
+  const double k2x = m3 * c2, k2y = m3 * s2, k2t = m3 * tan(dem) / P.L;
+  x[0] = x[0] + P.dt * k2x;
+  x[1] = x[1] + P.dt * k2y;
+  x[2] = normalize_angle(x[2] + P.dt * k2t);
+  x[3] = x[3] + P.dt * m4;
+  x[4] = x[4] + P.dt * u0;
+  x[5] = normalize_angle(x[5] + P.dt * u1);
+  (void)k1x;
+  (void)k1y;
+}
+
+// vehicle_model.cc:21-86.  Writes the 11 state-dependent entries of A and B(2,1).
+__device__ __forceinline__ void dynamics_jacobian(const DevParams& P, const double* x, double u1,
+                                                  double* A11, double* b21) {
+  const double L = P.L, dt = P.dt;
+  const double v = x[3];
+  const double theta = normalize_angle(x[2]);
+  const double delta = normalize_angle(x[5]);
+  const double a = x[4];
+  const double tan_delta = tan(delta);
+  const double theta_mid = theta + 0.5 * dt * v * tan_delta / L;
+  const double tan_dr = tan(delta + 0.5 * dt * u1);
+  double sm, cm;
+  sincos(theta_mid, &sm, &cm);
+  const double td2 = tan_delta * tan_delta;
+  const double tr2 = tan_dr * tan_dr;
+  const double vm = 0.5 * a * dt + v;
+  A11[0] = -dt * vm * sm;
+  A11[1] = dt * cm - 0.5 * dt * dt * vm * sm * tan_delta / L;
+  A11[2] = 0.5 * dt * dt * cm;
+  A11[3] = -0.5 * dt * dt * v * vm * (td2 + 1) * sm / L;
+  A11[4] = dt * vm * cm;
+  A11[5] = dt * sm + 0.5 * dt * dt * vm * cm * tan_delta / L;
+  A11[6] = 0.5 * dt * dt * sm;
+  A11[7] = 0.5 * dt * dt * v * vm * (td2 + 1) * cm / L;
+  A11[8] = dt * tan_dr / L;
+  A11[9] = 0.5 * dt * dt * tan_dr / L;
+  A11[10] = dt * (v * (tr2 + 1)) / L;
+  *b21 = 0.5 * dt * dt * v * (tr2 + 1) / L;
+}
+
+// Barrier value accumulator: sum of -rt*log(-g) over the log branch is -rt*log(prod(-g)).
+struct BarAcc {
+  double prod, quad;
+};
+__device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P) {
+  const bool lg = g < -P.eps;
+  const double q = (-g - 2.0 * P.eps) * P.inv_eps;
+  a.prod *= lg ? -g : 1.0;
+  a.quad += lg ? 0.0 : fma(0.5 * P.rt * q, q, P.relax_c);
+}
+__device__ __forceinline__ double bar_value(const BarAcc& a, const DevParams& P) {
+  return a.quad - P.rt * log(a.prod);
+}
+// barrier_function.h:115-140: coefficient of dx in the Jacobian (cj), of dx dx^T (co) and of ddx (cd)
+__device__ __forceinline__ void bar_coef(double g, const DevParams& P, double& cj, double& co,
+                                         double& cd) {
+  if (g < -P.eps) {
+    const double inv = 1.0 / g;
+    const double q = P.rt * inv;
+    cj = -q;
+    co = q * inv;
+    cd = q;
+  } else {
+    cj = P.rt * (g + 2.0 * P.eps) * P.inv_eps2;
+    co = cj;
+    cd = 0.0;
+  }
+}
+
+// squared distance point -> segment with the case split of line_segment2d.cpp:61-75
+__device__ __forceinline__ double seg_dist2(const double* sg, double px, double py) {
+  const double x0 = px - sg[0], y0 = py - sg[1];
+  const double x1 = px - sg[2], y1 = py - sg[3];
+  const double proj = x0 * sg[4] + y0 * sg[5];
+  const double cr = x0 * sg[5] - y0 * sg[4];
+  const double d0 = fma(x0, x0, y0 * y0);
+  const double d1 = fma(x1, x1, y1 * y1);
+  double d = cr * cr;
+  d = (proj >= sg[6]) ? d1 : d;
+  d = (proj <= 0.0) ? d0 : d;
+  return d;
+}
+
+struct Ctx {
+  const KernelArgs& a;
+  double* sm;
+  int lane;
+  // scenario
+  const double* goals;  // global [K][6] (row 0 is replaced by g0)
+  double g0[6];
+  const int32_t* cnt;   // global [K]
+  double* ws;           // global workspace of this CTA
+  __device__ Ctx(const KernelArgs& a_, double* s) : a(a_), sm(s) {}
+  __device__ __forceinline__ double goal(int k, int c) const { return k == 0 ? g0[c] : goals[k * 6 + c]; }
+};
+
+// ------------------------------------------------------------------------------------------
+// TotalCost of (Xs, Us): lane == knot.  Also records the nearest lane segment of every
+// (knot, disc, side) in nidx for the linearisation that follows an accepted step.
+__device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, unsigned char* nidx,
+                          double cost5[5]) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int K = a.N + 1, N = a.N;
+  const double* seg = c.sm + a.sm.seg;
+  double sum_j = 0.0, sum_d = 0.0, sum_c = 0.0, sum_l = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + c.lane;
+    const bool act = k < K;
+    const int kk = act ? k : K - 1;
+    const double* x = Xs + kk * 6;
+    const double px = x[0], py = x[1], th = x[2], v = x[3], ac = x[4], de = x[5];
+    double tj = 0.0, td = 0.0, tc = 0.0, tl = 0.0;
+    {
+      const double dx = px - c.goal(kk, 0), dy = py - c.goal(kk, 1), dth = th - c.goal(kk, 2);
+      tj = P.wx * (dx * dx) + P.wy * (dy * dy) + P.wth * (dth * dth);
+      BarAcc bd = {1.0, 0.0};
+      bar_add(bd, -v, P);
+      bar_add(bd, v - P.vmax, P);
+      bar_add(bd, ac - P.amax, P);
+      bar_add(bd, P.amin - ac, P);
+      bar_add(bd, de - P.dmax, P);
+      bar_add(bd, P.dmin - de, P);
+      if (kk < N) {
+        const double u0 = Us[kk * 2], u1 = Us[kk * 2 + 1];
+        tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
+        bar_add(bd, u0 - P.jmax, P);
+        bar_add(bd, P.jmin - u0, P);
+        bar_add(bd, u1 - P.drmax, P);
+        bar_add(bd, P.drmin - u1, P);
+      }
+      td = bar_value(bd, P);
+    }
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    double xd[kDisc], yd[kDisc];
+#pragma unroll
+    for (int d = 0; d < kDisc; ++d) {
+      xd[d] = px + P.off[d] * cs;
+      yd[d] = py + P.off[d] * sn;
+    }
+    // corridor half-planes of this knot
+    {
+      const int M = act ? c.cnt[kk] : 0;
+      const int Mw = __reduce_max_sync(kFull, M);
+      BarAcc bc[kDisc];
+#pragma unroll
+      for (int d = 0; d < kDisc; ++d) bc[d] = {1.0, 0.0};
+      const double* w = c.ws + kk;
+#pragma unroll 2
+      for (int m = 0; m < Mw; ++m) {
+        if (m < M) {
+          const double pa = w[(m * 3 + 0) * a.Kp], pb = w[(m * 3 + 1) * a.Kp], pc = w[(m * 3 + 2) * a.Kp];
+#pragma unroll
+          for (int d = 0; d < kDisc; ++d) bar_add(bc[d], fma(pb, yd[d], pa * xd[d]) - pc, P);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < kDisc; ++d) tc += bar_value(bc[d], P);
+    }
+    // nearest lane segment per disc and side (strict '<': first minimum wins)
+    {
+      BarAcc bl = {1.0, 0.0};
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int S = side == 0 ? a.S_left : a.S_right;
+        const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+        double best[kDisc];
+        int bi[kDisc];
+#pragma unroll
+        for (int d = 0; d < kDisc; ++d) {
+          best[d] = 1.7976931348623157e308;
+          bi[d] = 0;
+        }
+        for (int s = 0; s < S; ++s) {
+          const double* sg = sg0 + s * kSegStride;
+          double r[7];
+#pragma unroll
+          for (int q = 0; q < 7; ++q) r[q] = sg[q];
+#pragma unroll
+          for (int d = 0; d < kDisc; ++d) {
+            const double dd = seg_dist2(r, xd[d], yd[d]);
+            if (dd < best[d]) {
+              best[d] = dd;
+              bi[d] = s;
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < kDisc; ++d) {
+          const double* sg = sg0 + bi[d] * kSegStride;
+          bar_add(bl, fma(sg[8], yd[d], sg[7] * xd[d]) - sg[9], P);
+          if (act) nidx[kk * 10 + d * 2 + side] = (unsigned char)bi[d];
+        }
+      }
+      tl = bar_value(bl, P);
+    }
+    if (act) {
+      sum_j += tj;
+      sum_d += td;
+      sum_c += tc;
+      sum_l += tl;
+    }
+  }
+  const double j = warp_sum(sum_j), d = warp_sum(sum_d), co = warp_sum(sum_c), la = warp_sum(sum_l);
+  cost5[0] = j + d + co + la;
+  cost5[1] = j;
+  cost5[2] = d;
+  cost5[3] = co;
+  cost5[4] = la;
+}
+
+// ------------------------------------------------------------------------------------------
+// CostJacbian + CostHessian + DynamicsJacbian at knot k -> 31-double record.
+__device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const double* Us,
+                               const unsigned char* nidx, double* rec) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N;
+  const double* x = Xs + k * 6;
+  const double u0 = k < N ? Us[k * 2] : 0.0, u1 = k < N ? Us[k * 2 + 1] : 0.0;
+  if (k < N) {
+    double A11[11], b21;
+    dynamics_jacobian(P, x, u1, A11, &b21);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) rec[LA + i] = A11[i];
+    rec[LB21] = b21;
+  }
+  double Jx0 = 2.0 * P.wx * (x[0] - c.goal(k, 0));
+  double Jx1 = 2.0 * P.wy * (x[1] - c.goal(k, 1));
+  double Jx2 = 2.0 * P.wth * (x[2] - c.goal(k, 2));
+  double H00 = 2.0 * P.wx, H01 = 0.0, H02 = 0.0, H11 = 2.0 * P.wy, H12 = 0.0, H22 = 2.0 * P.wth;
+  double cj0, cj1, co0, co1, cd;
+  // DynamicsConsJacbian / Hessian: each state (control) component carries a pair of bounds
+  bar_coef(0.0 - x[3], P, cj0, co0, cd);
+  bar_coef(x[3] - P.vmax, P, cj1, co1, cd);
+  rec[LJX + 3] = cj1 - cj0;
+  rec[LHX + 6] = 2.0 * P.wv + (co0 + co1);
+  bar_coef(P.amin - x[4], P, cj0, co0, cd);
+  bar_coef(x[4] - P.amax, P, cj1, co1, cd);
+  rec[LJX + 4] = cj1 - cj0;
+  rec[LHX + 7] = 2.0 * P.wa + (co0 + co1);
+  bar_coef(P.dmin - x[5], P, cj0, co0, cd);
+  bar_coef(x[5] - P.dmax, P, cj1, co1, cd);
+  rec[LJX + 5] = cj1 - cj0;
+  rec[LHX + 8] = 2.0 * P.wd + (co0 + co1);
+  bar_coef(P.jmin - u0, P, cj0, co0, cd);
+  bar_coef(u0 - P.jmax, P, cj1, co1, cd);
+  rec[LJU + 0] = 2.0 * P.wj * u0 + (cj1 - cj0);
+  rec[LHU + 0] = 2.0 * P.wj + (co0 + co1);
+  bar_coef(P.drmin - u1, P, cj0, co0, cd);
+  bar_coef(u1 - P.drmax, P, cj1, co1, cd);
+  rec[LJU + 1] = 2.0 * P.wdr * u1 + (cj1 - cj0);
+  rec[LHU + 1] = 2.0 * P.wdr + (co0 + co1);
+
+  double sn, cs;
+  sincos(x[2], &sn, &cs);
+  double xd[kDisc], yd[kDisc];
+#pragma unroll
+  for (int d = 0; d < kDisc; ++d) {
+    xd[d] = x[0] + P.off[d] * cs;
+    yd[d] = x[1] + P.off[d] * sn;
+  }
+  // One half-plane (pa,pb,pc) acting on the listed discs.  dx = (a, b, off*t) with
+  // t = -a sin + b cos;  ddx(2,2) = -off*(a cos + b sin).  Sums over discs are factored out.
+  auto plane = [&](double pa, double pb, double pc, int d_lo, int d_hi) {
+    double sj = 0.0, sj1 = 0.0, so = 0.0, so1 = 0.0, so2 = 0.0, sd1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < kDisc; ++d) {
+      if (d >= d_lo && d < d_hi) {
+        const double g = fma(pb, yd[d], pa * xd[d]) - pc;
+        double cj, co, cdd;
+        bar_coef(g, P, cj, co, cdd);
+        const double o = P.off[d];
+        sj += cj;
+        sj1 = fma(cj, o, sj1);
+        so += co;
+        so1 = fma(co, o, so1);
+        so2 = fma(co * o, o, so2);
+        sd1 = fma(cdd, o, sd1);
+      }
+    }
+    const double t = pb * cs - pa * sn;
+    const double w = pa * cs + pb * sn;
+    Jx0 = fma(pa, sj, Jx0);
+    Jx1 = fma(pb, sj, Jx1);
+    Jx2 = fma(t, sj1, Jx2);
+    H00 = fma(pa * pa, so, H00);
+    H01 = fma(pa * pb, so, H01);
+    H11 = fma(pb * pb, so, H11);
+    H02 = fma(pa * t, so1, H02);
+    H12 = fma(pb * t, so1, H12);
+    H22 = fma(t * t, so2, H22);
+    H22 = fma(w, sd1, H22);
+  };
+  const int M = c.cnt[k];
+  const double* w = c.ws + k;
+  for (int m = 0; m < M; ++m) {
+    plane(w[(m * 3 + 0) * a.Kp], w[(m * 3 + 1) * a.Kp], w[(m * 3 + 2) * a.Kp], 0, kDisc);
+  }
+  const double* seg = c.sm + a.sm.seg;
+#pragma unroll
+  for (int d = 0; d < kDisc; ++d) {
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const double* sg = seg + ((side == 0 ? 0 : a.S_left) + nidx[k * 10 + d * 2 + side]) * kSegStride;
+      plane(sg[7], sg[8], sg[9], d, d + 1);
+    }
+  }
+  rec[LJX + 0] = Jx0;
+  rec[LJX + 1] = Jx1;
+  rec[LJX + 2] = Jx2;
+  rec[LHX + 0] = H00;
+  rec[LHX + 1] = H01;
+  rec[LHX + 2] = H02;
+  rec[LHX + 3] = H11;
+  rec[LHX + 4] = H12;
+  rec[LHX + 5] = H22;
+}
+
+// Sparse structure of A = I + Nf (Nf rows 0..3) and B.  Nf is expanded to a dense 4x6 table in
+// scratch so that the cooperating lanes can index it.
+__device__ __forceinline__ void expand_N(const double* rec, double* Nf, int lane, double dt) {
+  // Nf[r][c]: row0: c2..5 = A02,A03,A04,A05; row1: c2..5 = A12..A15; row2: c3..5 = A23,A24,A25; row3: c4 = dt
+  if (lane < 24) {
+    const int r = lane / 6, cc = lane % 6;
+    double v = 0.0;
+    if (r == 0 && cc >= 2) v = rec[LA + cc - 2];
+    else if (r == 1 && cc >= 2) v = rec[LA + 4 + cc - 2];
+    else if (r == 2 && cc >= 3) v = rec[LA + 8 + cc - 3];
+    else if (r == 3 && cc == 4) v = dt;
+    Nf[lane] = v;
+  }
+}
+
+// scratch map (doubles) used by backward / iqr
+constexpr int SV = 0;      // 36  Vxx (or P)
+constexpr int SVX = 36;    // 6   Vx
+constexpr int SW = 42;     // 36  V*A  (or A^T P)
+constexpr int SN = 78;     // 24  Nf
+constexpr int SBV = 102;   // 12  B^T V
+constexpr int SQXX = 114;  // 36  Qxx (upper triangle filled) / C in iqr
+constexpr int SQUX = 150;  // 12
+constexpr int SQX = 162;   // 6
+constexpr int SQU = 168;   // 2
+constexpr int SQUU = 170;  // 4
+constexpr int ST = 174;    // 12  T = Quu K + Qux
+constexpr int SK = 186;    // gains of this knot are read from Kg/kg directly
+static_assert(SK <= kScratch, "scratch overflow");
+
+// ilqr_optimizer.cc:334-390 with the window-wise linearisation fused in (ilqr_optimizer.cc:203-214).
+__device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, const double* Us,
+                              const unsigned char* nidx, double dV[2], const DebugPtrs* dbg, int b) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N, K = N + 1;
+  const int lane = c.lane;
+  double* lin = c.sm + a.sm.lin;
+  double* scr = c.sm + a.sm.scr;
+  double* Kg = c.sm + a.sm.Kg;
+  double* kg = c.sm + a.sm.kg;
+  const double B30 = 0.5 * P.dt * P.dt, B40 = P.dt, B51 = P.dt;
+  // upper-triangle role of this lane
+  int ui = 0, uj = 0;
+  {
+    int e = lane, i = 0;
+    while (i < 5 && e >= 6 - i) {
+      e -= 6 - i;
+      ++i;
+    }
+    ui = i;
+    uj = i + e;
+    if (lane >= 21) {
+      ui = 0;
+      uj = 0;
+    }
+  }
+  double dv0 = 0.0, dv1 = 0.0;
+  const int last_chunk = (K - 1) / 32;
+  for (int ch = last_chunk; ch >= 0; --ch) {
+    const int k0 = ch * 32;
+    const int k = k0 + lane;
+    __syncwarp();
+    if (k < K) linearize_knot(c, k, Xs, Us, nidx, lin + lane * kLinStride);
+    __syncwarp();
+    if (dbg) {
+      if (k < K) {
+        const double* rec = lin + lane * kLinStride;
+        if (k < N) {
+          if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
+          if (dbg->Ju) for (int i = 0; i < 2; ++i) dbg->Ju[((size_t)b * N + k) * 2 + i] = rec[LJU + i];
+          if (dbg->Hu) for (int i = 0; i < 2; ++i) dbg->Hu[((size_t)b * N + k) * 2 + i] = rec[LHU + i];
+        }
+        if (dbg->Jx) for (int i = 0; i < 6; ++i) dbg->Jx[((size_t)b * K + k) * 6 + i] = rec[LJX + i];
+        if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
+      }
+    }
+    int kend = k0 + 31;
+    if (kend > N - 1) kend = N - 1;
+    if (ch == last_chunk) {
+      // Vx = cost_Jx.back(), Vxx = cost_Hx.back()    (:343-344)
+      const double* rec = lin + (N - k0) * kLinStride;
+      for (int e = lane; e < 36; e += 32) {
+        const int i = e / 6, j = e % 6;
+        double v = 0.0;
+        if (i == j) v = i < 3 ? rec[LHX + (i == 0 ? 0 : i == 1 ? 3 : 5)] : rec[LHX + 6 + i - 3];
+        else if (i < 3 && j < 3) {
+          const int lo = i < j ? i : j, hi = i < j ? j : i;
+          v = rec[LHX + (lo == 0 ? hi : 4)];
+        }
+        scr[SV + e] = v;
+      }
+      if (lane < 6) scr[SVX + lane] = rec[LJX + lane];
+    }
+    for (int kn = kend; kn >= k0; --kn) {
+      const double* rec = lin + (kn - k0) * kLinStride;
+      const double b21 = rec[LB21];
+      __syncwarp();
+      expand_N(rec, scr + SN, lane, P.dt);
+      __syncwarp();
+      const double* V = scr + SV;
+      const double* Vx = scr + SVX;
+      const double* Nf = scr + SN;
+      // pass 1: W = V A (36), BtV (12), Qx (6), Qu (2)
+      {
+        const int i = lane / 6, cc = lane % 6;  // lanes 0..31 -> W entries 0..31
+        double w = V[lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) w = fma(V[i * 6 + r], Nf[r * 6 + cc], w);
+        scr[SW + lane] = w;
+        if (lane < 4) {
+          const int e = 32 + lane;
+          double w2 = V[e];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) w2 = fma(V[30 + r], Nf[r * 6 + (e - 30)], w2);
+          scr[SW + e] = w2;
+        } else if (lane < 16) {
+          const int e = lane - 4, rr = e / 6, j = e % 6;
+          scr[SBV + e] = rr == 0 ? fma(B40, V[24 + j], B30 * V[18 + j]) : fma(B51, V[30 + j], b21 * V[12 + j]);
+        } else if (lane < 22) {
+          const int r = lane - 16;
+          double q = rec[LJX + r] + Vx[r];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) q = fma(Nf[i2 * 6 + r], Vx[i2], q);
+          scr[SQX + r] = q;
+        } else if (lane < 24) {
+          scr[SQU + lane - 22] = lane == 22 ? rec[LJU] + fma(B40, Vx[4], B30 * Vx[3])
+                                            : rec[LJU + 1] + fma(B51, Vx[5], b21 * Vx[2]);
+        }
+      }
+      __syncwarp();
+      // pass 2: Qxx upper (21 lanes), Qux (12: lanes 21..31 + lane 0 again), Quu (lanes 1..4)
+      {
+        const double* W = scr + SW;
+        const double* BV = scr + SBV;
+        if (lane < 21) {
+          double hx = 0.0;
+          if (ui == uj) hx = ui < 3 ? rec[LHX + (ui == 0 ? 0 : ui == 1 ? 3 : 5)] : rec[LHX + 6 + ui - 3];
+          else if (uj < 3) hx = rec[LHX + (ui == 0 ? uj : 4)];
+          double q = hx + W[ui * 6 + uj];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) q = fma(Nf[i2 * 6 + ui], W[i2 * 6 + uj], q);
+          scr[SQXX + ui * 6 + uj] = q;
+          scr[SQXX + uj * 6 + ui] = q;
+        } else {
+          const int e = lane - 21, rr = e / 6, cc = e % 6;  // Qux entries 0..10
+          double q = BV[e];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) q = fma(BV[rr * 6 + r], Nf[r * 6 + cc], q);
+          scr[SQUX + e] = q;
+        }
+        if (lane == 0) {
+          double q = BV[11];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) q = fma(BV[6 + r], Nf[r * 6 + 5], q);
+          scr[SQUX + 11] = q;
+        } else if (lane < 5) {
+          const int e = lane - 1, ra = e / 2, cb = e % 2;
+          const double hu = ra == cb ? rec[LHU + ra] : 0.0;
+          scr[SQUU + e] = hu + (cb == 0 ? fma(BV[ra * 6 + 4], B40, BV[ra * 6 + 3] * B30)
+                                        : fma(BV[ra * 6 + 5], B51, BV[ra * 6 + 2] * b21));
+        }
+      }
+      __syncwarp();
+      // pass 3: K = -(Quu + lambda I)^-1 Qux, k = -(Quu + lambda I)^-1 Qu   (:361-366)
+      const double q00 = scr[SQUU + 0], q01 = scr[SQUU + 1], q10 = scr[SQUU + 2], q11 = scr[SQUU + 3];
+      {
+        const double t00 = q00 + lambda, t11 = q11 + lambda;
+        const double det = t00 * t11 - q10 * q01;
+        const double invdet = 1.0 / det;
+        const double i00 = t11 * invdet, i01 = -q01 * invdet, i10 = -q10 * invdet, i11 = t00 * invdet;
+        if (lane < 12) {
+          const int rr = lane / 6, cc = lane % 6;
+          const double n0 = rr == 0 ? -i00 : -i10, n1 = rr == 0 ? -i01 : -i11;
+          Kg[kn * 12 + lane] = fma(n1, scr[SQUX + 6 + cc], n0 * scr[SQUX + cc]);
+        } else if (lane < 14) {
+          const int rr = lane - 12;
+          const double n0 = rr == 0 ? -i00 : -i10, n1 = rr == 0 ? -i01 : -i11;
+          kg[kn * 2 + rr] = fma(n1, scr[SQU + 1], n0 * scr[SQU + 0]);
+        }
+      }
+      __syncwarp();
+      const double* Kk = Kg + kn * 12;
+      const double kk0 = kg[kn * 2], kk1 = kg[kn * 2 + 1];
+      // pass 4: T = Quu K + Qux (12), Vx' (6)   (:379, un-regularised Quu)
+      {
+        if (lane < 12) {
+          const int rr = lane / 6, cc = lane % 6;
+          const double qa = rr == 0 ? q00 : q10, qb = rr == 0 ? q01 : q11;
+          scr[ST + lane] = fma(qb, Kk[6 + cc], fma(qa, Kk[cc], scr[SQUX + lane]));
+        } else if (lane < 18) {
+          const int i = lane - 12;
+          const double qk0 = fma(q01, kk1, q00 * kk0), qk1 = fma(q11, kk1, q10 * kk0);
+          double vx = scr[SQX + i];
+          vx += fma(Kk[6 + i], qk1, Kk[i] * qk0);
+          vx += fma(Kk[6 + i], scr[SQU + 1], Kk[i] * scr[SQU + 0]);
+          vx += fma(scr[SQUX + 6 + i], kk1, scr[SQUX + i] * kk0);
+          scr[SVX + i] = vx;
+        }
+      }
+      __syncwarp();
+      // pass 5: Vxx' = Qxx + K^T T + Qux^T K, symmetrised   (:380-381)
+      if (lane < 21) {
+        const double* T = scr + ST;
+        const double* Qux = scr + SQUX;
+        double vij = scr[SQXX + ui * 6 + uj];
+        vij += fma(Kk[6 + ui], T[6 + uj], Kk[ui] * T[uj]);
+        vij += fma(Qux[6 + ui], Kk[6 + uj], Qux[ui] * Kk[uj]);
+        double vji = scr[SQXX + ui * 6 + uj];
+        vji += fma(Kk[6 + uj], T[6 + ui], Kk[uj] * T[ui]);
+        vji += fma(Qux[6 + uj], Kk[6 + ui], Qux[uj] * Kk[ui]);
+        const double s = 0.5 * (vij + vji);
+        scr[SV + ui * 6 + uj] = s;
+        scr[SV + uj * 6 + ui] = s;
+      }
+      __syncwarp();
+      // :383-384 -- lazy Qu / Quu are evaluated with the UPDATED Vx / Vxx (quirk Q21)
+      {
+        const double* Vn = scr + SV;
+        const double* Vxn = scr + SVX;
+        const double qu0 = rec[LJU] + fma(B40, Vxn[4], B30 * Vxn[3]);
+        const double qu1 = rec[LJU + 1] + fma(B51, Vxn[5], b21 * Vxn[2]);
+        const double bv0_2 = fma(B40, Vn[24 + 2], B30 * Vn[18 + 2]), bv0_3 = fma(B40, Vn[24 + 3], B30 * Vn[18 + 3]);
+        const double bv0_4 = fma(B40, Vn[24 + 4], B30 * Vn[18 + 4]), bv0_5 = fma(B40, Vn[24 + 5], B30 * Vn[18 + 5]);
+        const double bv1_2 = fma(B51, Vn[30 + 2], b21 * Vn[12 + 2]), bv1_3 = fma(B51, Vn[30 + 3], b21 * Vn[12 + 3]);
+        const double bv1_4 = fma(B51, Vn[30 + 4], b21 * Vn[12 + 4]), bv1_5 = fma(B51, Vn[30 + 5], b21 * Vn[12 + 5]);
+        const double n00 = rec[LHU] + fma(bv0_4, B40, bv0_3 * B30);
+        const double n01 = fma(bv0_5, B51, bv0_2 * b21);
+        const double n10 = fma(bv1_4, B40, bv1_3 * B30);
+        const double n11 = rec[LHU + 1] + fma(bv1_5, B51, bv1_2 * b21);
+        dv0 += fma(kk1, qu1, kk0 * qu0);
+        const double h0 = 0.5 * kk0, h1 = 0.5 * kk1;
+        const double r0 = fma(h1, n10, h0 * n00), r1 = fma(h1, n11, h0 * n01);
+        dv1 += fma(r1, kk1, r0 * kk0);
+      }
+    }
+  }
+  __syncwarp();
+  dV[0] = dv0;
+  dV[1] = dv1;
+}
+
+// ilqr_optimizer.cc:392-415.  Every lane carries the same state (uniform work), lane 0 stores.
+__device__ void forward_pass(const Ctx& c, double alpha, const double* Xs, const double* Us, double* Xn,
+                             double* Un) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const double* Kg = c.sm + a.sm.Kg;
+  const double* kg = c.sm + a.sm.kg;
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = c.g0[i];
+  if (c.lane < 6) Xn[c.lane] = c.g0[c.lane];
+  for (int k = 0; k < a.N; ++k) {
+    const double* Kk = Kg + k * 12;
+    const double* xb = Xs + k * 6;
+    double dx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dx[i] = x[i] - xb[i];
+    double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+      s0 = fma(Kk[i], dx[i], s0);
+      s1 = fma(Kk[6 + i], dx[i], s1);
+    }
+    const double u0 = Us[k * 2] + s0 + alpha * kg[k * 2];
+    const double u1 = normalize_angle(Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1]);
+    dynamics_step(P, x, u0, u1);
+    if (c.lane == 0) {
+      Un[k * 2] = u0;
+      Un[k * 2 + 1] = u1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Xn[(k + 1) * 6 + i] = x[i];
+    }
+  }
+  __syncwarp();
+}
+
+// ilqr_optimizer.cc:793-842
+__device__ void iqr_guess(const Ctx& c, double* Xs, double* Us) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N, lane = c.lane;
+  double* Kg = c.sm + a.sm.Kg;
+  double* scr = c.sm + a.sm.scr;
+  const double B30 = 0.5 * P.dt * P.dt, B40 = P.dt, B51 = P.dt;
+  // A_k, B_k about the goals with zero control; parked in the gain slots until consumed
+  for (int k = lane; k < N; k += 32) {
+    double g[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = c.goal(k, i);
+    double A11[11], b21;
+    dynamics_jacobian(P, g, 0.0, A11, &b21);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) Kg[k * 12 + i] = A11[i];
+    Kg[k * 12 + 11] = b21;
+  }
+  const double Qd[6] = {0.001, 0.001, 0.001, 0.001, 0.01, 0.005};
+  for (int e = lane; e < 36; e += 32) scr[SV + e] = (e / 6 == e % 6) ? Qd[e / 6] : 0.0;
+  __syncwarp();
+  double* Pm = scr + SV;     // P
+  double* AtP = scr + SW;    // A^T P
+  double* Nf = scr + SN;
+  double* BtP = scr + SBV;   // 2x6
+  double* Cm = scr + SQXX;   // A - B K
+  double* G = scr + SQUX;    // B^T P A
+  double* S4 = scr + SQUU;   // R + B^T P B
+  for (int k = N - 1; k >= 0; --k) {
+    double rec[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rec[i] = Kg[k * 12 + i];
+    const double b21 = rec[11];
+    __syncwarp();
+    if (lane < 24) {
+      const int r = lane / 6, cc = lane % 6;
+      double v = 0.0;
+      if (r == 0 && cc >= 2) v = rec[cc - 2];
+      else if (r == 1 && cc >= 2) v = rec[4 + cc - 2];
+      else if (r == 2 && cc >= 3) v = rec[8 + cc - 3];
+      else if (r == 3 && cc == 4) v = P.dt;
+      Nf[lane] = v;
+    }
+    if (lane < 12) {
+      const int rr = lane / 6, j = lane % 6;
+      BtP[lane] = rr == 0 ? fma(B40, Pm[24 + j], B30 * Pm[18 + j]) : fma(B51, Pm[30 + j], b21 * Pm[12 + j]);
+    }
+    __syncwarp();
+    // AtP = P + Nf^T P ; G = BtP A ; S = R + BtP B
+    for (int e = lane; e < 36; e += 32) {
+      const int r = e / 6, j = e % 6;
+      double v = Pm[e];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v = fma(Nf[i * 6 + r], Pm[i * 6 + j], v);
+      AtP[e] = v;
+    }
+    if (lane < 12) {
+      const int rr = lane / 6, cc = lane % 6;
+      double q = BtP[lane];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) q = fma(BtP[rr * 6 + r], Nf[r * 6 + cc], q);
+      G[lane] = q;
+    } else if (lane < 16) {
+      const int e = lane - 12, ra = e / 2, cb = e % 2;
+      const double rdiag = ra == cb ? (ra == 0 ? 0.2 : 0.05) : 0.0;
+      S4[e] = rdiag + (cb == 0 ? fma(BtP[ra * 6 + 4], B40, BtP[ra * 6 + 3] * B30)
+                               : fma(BtP[ra * 6 + 5], B51, BtP[ra * 6 + 2] * b21));
+    }
+    __syncwarp();
+    {
+      const double det = S4[0] * S4[3] - S4[2] * S4[1];
+      const double invdet = 1.0 / det;
+      const double i00 = S4[3] * invdet, i01 = -S4[1] * invdet, i10 = -S4[2] * invdet, i11 = S4[0] * invdet;
+      if (lane < 12) {
+        const int rr = lane / 6, cc = lane % 6;
+        Kg[k * 12 + lane] = rr == 0 ? fma(i01, G[6 + cc], i00 * G[cc]) : fma(i11, G[6 + cc], i10 * G[cc]);
+      }
+    }
+    __syncwarp();
+    // C = A - B K
+    for (int e = lane; e < 36; e += 32) {
+      const int r = e / 6, j = e % 6;
+      double av = (r == j ? 1.0 : 0.0) + (r < 4 ? Nf[r * 6 + j] : 0.0);
+      double bk = 0.0;
+      if (r == 2) bk = b21 * Kg[k * 12 + 6 + j];
+      else if (r == 3) bk = B30 * Kg[k * 12 + j];
+      else if (r == 4) bk = B40 * Kg[k * 12 + j];
+      else if (r == 5) bk = B51 * Kg[k * 12 + 6 + j];
+      Cm[e] = av - bk;
+    }
+    __syncwarp();
+    // P = Q + AtP C   (entry `lane`, and entry `lane + 32` on lanes 0..3)
+    double pn0, pn1 = 0.0;
+    {
+      const int r = lane / 6, j = lane % 6;
+      double v = AtP[r * 6] * Cm[j];
+#pragma unroll
+      for (int m = 1; m < 6; ++m) v = fma(AtP[r * 6 + m], Cm[m * 6 + j], v);
+      pn0 = (r == j ? Qd[r] : 0.0) + v;
+    }
+    if (lane < 4) {
+      const int j = lane + 2;
+      double v = AtP[30] * Cm[j];
+#pragma unroll
+      for (int m = 1; m < 6; ++m) v = fma(AtP[30 + m], Cm[m * 6 + j], v);
+      pn1 = (j == 5 ? Qd[5] : 0.0) + v;
+    }
+    __syncwarp();
+    Pm[lane] = pn0;
+    if (lane < 4) Pm[32 + lane] = pn1;
+  }
+  __syncwarp();
+  // rollout with clamped feedback
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = c.g0[i];
+  if (lane < 6) Xs[lane] = c.g0[lane];
+  for (int k = 0; k < N; ++k) {
+    const double* Kk = Kg + k * 12;
+    double dx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dx[i] = x[i] - c.goal(k, i);
+    double s0 = -Kk[0] * dx[0], s1 = -Kk[6] * dx[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+      s0 = fma(-Kk[i], dx[i], s0);
+      s1 = fma(-Kk[6 + i], dx[i], s1);
+    }
+    const double u0 = fmin(P.jmax, fmax(s0, P.jmin));
+    const double u1 = fmin(P.drmax, fmax(s1, P.drmin));
+    dynamics_step(P, x, u0, u1);
+    if (lane == 0) {
+      Us[k * 2] = u0;
+      Us[k * 2 + 1] = u1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Xs[(k + 1) * 6 + i] = x[i];
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ unsigned fnv1a(unsigned h, unsigned byte) { return (h ^ (byte & 0xffu)) * 16777619u; }
+
+__device__ __forceinline__ void copy_out(double* dst, const double* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x;
+  const DevParams& P = a.P;
+  const int N = a.N, K = N + 1;
+  Ctx c(a, smem);
+  c.lane = lane;
+  c.ws = a.ws + (size_t)blockIdx.x * a.M_max * 3 * a.Kp;
+  double* seg = smem + a.sm.seg;
+  unsigned char* nidx_base = reinterpret_cast<unsigned char*>(smem + a.sm.nidx);
+  const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
+
+  while (true) {
+    unsigned int b = 0;
+    if (lane == 0) b = atomicAdd(a.ticket, 1u);
+    b = __shfl_sync(kFull, b, 0);
+    if (b >= (unsigned)a.B) break;
+
+    // ---- load scenario, TransformGoals (:141-152)
+    c.goals = a.coarse + (size_t)b * K * 6;
+    c.cnt = a.corridor_cnt + (size_t)b * K;
+    {
+      const double* st = a.start + (size_t)b * 4;
+      c.g0[0] = st[0];
+      c.g0[1] = st[1];
+      c.g0[2] = st[2];
+      c.g0[3] = st[3];
+      c.g0[4] = 0.0;
+      c.g0[5] = 0.0;
+    }
+    // ---- ShrinkConstraints + NormalizeHalfPlane (:438-495)
+    {
+      const double* raw = a.corridor + (size_t)b * K * a.M_max * 3;
+      const int total = K * a.M_max;
+      for (int idx = lane; idx < total; idx += 32) {
+        const int k = idx / a.M_max, m = idx - k * a.M_max;
+        if (m < c.cnt[k]) {
+          const double e0 = raw[idx * 3], e1 = raw[idx * 3 + 1];
+          double e2 = raw[idx * 3 + 2];
+          e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / hypot(e0, e1);
+          const double nrm = hypot(hypot(e0, e1), e2);
+          c.ws[(m * 3 + 0) * a.Kp + k] = e0 / nrm;
+          c.ws[(m * 3 + 1) * a.Kp + k] = e1 / nrm;
+          c.ws[(m * 3 + 2) * a.Kp + k] = e2 / nrm;
+          if (dbg && dbg->corridor) {
+            double* o = dbg->corridor + ((size_t)b * total + idx) * 3;
+            o[0] = e0 / nrm;
+            o[1] = e1 / nrm;
+            o[2] = e2 / nrm;
+          }
+        }
+      }
+      const int ST_ = a.S_left + a.S_right;
+      for (int s = lane; s < ST_; s += 32) {
+        const double* ln = s < a.S_left ? a.lane_left + ((size_t)b * a.S_left + s) * 7
+                                        : a.lane_right + ((size_t)b * a.S_right + (s - a.S_left)) * 7;
+        const double e0 = ln[0], e1 = ln[1];
+        double e2 = ln[2];
+        e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / hypot(e0, e1);
+        const double nrm = hypot(hypot(e0, e1), e2);
+        double* sg = seg + s * kSegStride;
+        const double dx = ln[5] - ln[3], dy = ln[6] - ln[4];
+        const double len = hypot(dx, dy);
+        sg[0] = ln[3];
+        sg[1] = ln[4];
+        sg[2] = ln[5];
+        sg[3] = ln[6];
+        sg[4] = len <= 1e-10 ? 0.0 : dx / len;  // line_segment2d.cpp:40-49
+        sg[5] = len <= 1e-10 ? 0.0 : dy / len;
+        sg[6] = len;
+        sg[7] = e0 / nrm;
+        sg[8] = e1 / nrm;
+        sg[9] = e2 / nrm;
+        if (dbg && dbg->lanes) {
+          double* o = dbg->lanes + ((size_t)b * ST_ + s) * 3;
+          o[0] = sg[7];
+          o[1] = sg[8];
+          o[2] = sg[9];
+        }
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    double* X = smem + a.sm.X;
+    double* U = smem + a.sm.U;
+    double* Xc = smem + a.sm.Xc;
+    double* Uc = smem + a.sm.Uc;
+    unsigned char* nidx = nidx_base;
+    unsigned char* nidx_c = nidx_base + a.sm.nidx_bytes;
+
+    // ---- initial guess (:169) and its cost (:172)
+    iqr_guess(c, X, U);
+    if (a.init_states) copy_out(a.init_states + (size_t)b * K * 6, X, K * 6, lane);
+    if (a.init_controls) copy_out(a.init_controls + (size_t)b * N * 2, U, N * 2, lane);
+    double cost_acc[5], cost_new5[5];
+    eval_cost(c, X, U, nidx, cost_acc);
+    __syncwarp();
+    double cost_old = cost_acc[0];
+    int n_cost = 0, n_iter_traj = 0;
+    auto push_traj = [&](const double* Xs, const double* Us) {
+      if (a.iter_states && n_iter_traj < a.hist_cap) {
+        copy_out(a.iter_states + ((size_t)b * a.hist_cap + n_iter_traj) * K * 6, Xs, K * 6, lane);
+        if (a.iter_controls) copy_out(a.iter_controls + ((size_t)b * a.hist_cap + n_iter_traj) * N * 2, Us, N * 2, lane);
+      }
+      ++n_iter_traj;
+    };
+    {
+      // cost5 values live in registers indexed by compile-time constants; spill through scratch for the lane-indexed store
+      double* t5 = smem + a.sm.scr + SK;
+      if (lane == 0) for (int i = 0; i < 5; ++i) t5[i] = cost_acc[i];
+      __syncwarp();
+      if (a.cost_hist && 0 < a.hist_cap && lane < 5) a.cost_hist[((size_t)b * a.hist_cap) * 5 + lane] = t5[lane];
+      n_cost = 1;
+      push_traj(X, U);
+      if (dbg) {
+        if (dbg->X0) copy_out(dbg->X0 + (size_t)b * K * 6, X, K * 6, lane);
+        if (dbg->U0) copy_out(dbg->U0 + (size_t)b * N * 2, U, N * 2, lane);
+        if (dbg->cost0 && lane < 5) dbg->cost0[(size_t)b * 5 + lane] = t5[lane];
+        if (dbg->nearest) for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nidx[i];
+      }
+      __syncwarp();
+    }
+
+    // ---- Optimize main loop (:182-320)
+    double dcost = 0.0, lambda = 1.0, dlambda = 1.0;
+    const double reg_ratio = 1.6, reg_min = 1e-8, reg_max = 1e11, gnorm_min = 1e-6, beta_min = 1e-4, beta_max = 10.0;
+    int status = 4;
+    unsigned ahash = 2166136261u;
+    int iter = 0;
+    for (; iter < P.max_iter; ++iter) {
+      double dV[2];
+      backward_pass(c, lambda, X, U, nidx, dV, iter == 0 ? dbg : nullptr, (int)b);
+      if (dbg && iter == 0) {
+        if (dbg->Kg) copy_out(dbg->Kg + (size_t)b * N * 12, smem + a.sm.Kg, N * 12, lane);
+        if (dbg->kg) copy_out(dbg->kg + (size_t)b * N * 2, smem + a.sm.kg, N * 2, lane);
+        if (dbg->dV && lane == 0) {
+          dbg->dV[(size_t)b * 2] = dV[0];
+          dbg->dV[(size_t)b * 2 + 1] = dV[1];
+        }
+      }
+      // CalGradientNorm (:322-332)
+      {
+        const double* kgp = smem + a.sm.kg;
+        double acc = 0.0;
+        for (int k = lane; k < N; k += 32) {
+          const double v0 = fabs(kgp[k * 2]) / (fabs(U[k * 2]) + 1.0);
+          const double v1 = fabs(kgp[k * 2 + 1]) / (fabs(U[k * 2 + 1]) + 1.0);
+          acc += fmax(v0, v1);
+        }
+        const double gnorm = warp_sum(acc) / N;
+        if (gnorm < gnorm_min && lambda < 1e-5) {
+          status = 2;
+          break;
+        }
+      }
+      // line search (:246-265)
+      bool done = false;
+      int alpha_idx = kNAlpha;
+      for (int ai = 0; ai < kNAlpha; ++ai) {
+        const double alpha = kAlphaList[ai];
+        forward_pass(c, alpha, X, U, Xc, Uc);
+        eval_cost(c, Xc, Uc, nidx_c, cost_new5);
+        __syncwarp();
+        if (dbg && iter == 0 && ai == 0) {
+          if (dbg->Xn) copy_out(dbg->Xn + (size_t)b * K * 6, Xc, K * 6, lane);
+          if (dbg->Un) copy_out(dbg->Un + (size_t)b * N * 2, Uc, N * 2, lane);
+          if (dbg->costn && lane == 0) for (int i = 0; i < 5; ++i) dbg->costn[(size_t)b * 5 + i] = cost_new5[i];
+        }
+        dcost = cost_old - cost_new5[0];
+        const double expected = -alpha * (dV[0] + alpha * dV[1]);
+        const double z = dcost / expected;
+        if ((z > beta_min && z < beta_max) && dcost > 0.0) {
+          done = true;
+          alpha_idx = ai;
+          break;
+        }
+      }
+      ahash = fnv1a(ahash, (unsigned)alpha_idx);
+      if (a.debug) {
+        // stage dump mode: one backward + one forward only
+        break;
+      }
+      if (done) {
+        // accept: the candidate becomes the iterate (pointer swap instead of the reference's copies)
+        double* tx = X; X = Xc; Xc = tx;
+        double* tu = U; U = Uc; Uc = tu;
+        unsigned char* tn = nidx; nidx = nidx_c; nidx_c = tn;
+        dlambda = fmin(dlambda / reg_ratio, 1.0 / reg_ratio);
+        lambda = lambda * dlambda * (lambda > reg_min ? 1.0 : 0.0);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cost_acc[i] = cost_new5[i];
+        {
+          double* t5 = smem + a.sm.scr + SK;
+          __syncwarp();
+          if (lane == 0) for (int i = 0; i < 5; ++i) t5[i] = cost_acc[i];
+          __syncwarp();
+          if (a.cost_hist && n_cost < a.hist_cap && lane < 5) a.cost_hist[((size_t)b * a.hist_cap + n_cost) * 5 + lane] = t5[lane];
+          ++n_cost;
+        }
+        if (dcost < P.abs_tol || dcost / cost_old < P.rel_tol) {
+          status = dcost < P.abs_tol ? 0 : 1;
+          cost_old = cost_new5[0];
+          break;
+        }
+        push_traj(X, U);
+        cost_old = cost_new5[0];
+      } else {
+        dlambda = fmax(dlambda * reg_ratio, reg_ratio);
+        lambda = fmax(lambda * dlambda, reg_min);
+        if (lambda > reg_max) {
+          status = 3;
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- outputs
+    copy_out(a.states + (size_t)b * K * 6, X, K * 6, lane);
+    copy_out(a.controls + (size_t)b * N * 2, U, N * 2, lane);
+    if (lane == 0) {
+      double* st = a.status + (size_t)b * 8;
+      st[0] = status;
+      st[1] = iter;
+      for (int i = 0; i < 5; ++i) st[2 + i] = cost_acc[i];
+      st[7] = (double)ahash;
+      if (a.hist_len) {
+        a.hist_len[(size_t)b * 2] = n_cost;
+        a.hist_len[(size_t)b * 2 + 1] = n_iter_traj;
+      }
+    }
+    if (a.trajectory) {
+      // TransformToTrajectory (:771-791): time, s, x, y, theta, kappa, velocity, a, jerk, delta, delta_rate, lb, rb
+      for (int k = lane; k < K; k += 32) {
+        double* tp = a.trajectory + ((size_t)b * K + k) * 13;
+        const double* x = X + k * 6;
+        tp[0] = k * P.dt;
+        tp[1] = 0.0;
+        tp[2] = x[0];
+        tp[3] = x[1];
+        tp[4] = x[2];
+        tp[5] = tan(x[5]) / P.L;
+        tp[6] = x[3];
+        tp[7] = x[4];
+        tp[8] = k < N ? U[k * 2] : 0.0;
+        tp[9] = x[5];
+        tp[10] = k < N ? U[k * 2 + 1] : 0.0;
+        tp[11] = 0.0;
+        tp[12] = 0.0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace cilqr

@@ -1,0 +1,222 @@
+"""ctypes mirror of include/cilqr_b200.h.
+
+``Solver.plan_batch`` corresponds to ``IlqrOptimizer::Plan`` (reference
+``algorithm/ilqr/ilqr_optimizer.cc:53-95``) for a batch of scenarios in host memory;
+``Solver.plan_batch_device`` takes raw device pointers (e.g. ``torch.Tensor.data_ptr()``).
+No computation happens in Python and there is no CPU fallback: if the shared library cannot be
+loaded or no sm_100 GPU is present the calls raise ``CilqrError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+STATUS_NAMES = ["converged_abs", "converged_rel", "converged_grad", "lambda_overflow", "max_iter"]
+E_INVALID, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_SMEM = -1, -2, -3, -4, -5
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class CilqrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cilqr_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """POD mirror of CilqrParams (VehicleParam / IlqrConfig / Weights / barrier constants)."""
+    _fields_ = [(n, C.c_double) for n in (
+        "front_hang_length", "wheel_base", "rear_hang_length", "width",
+        "max_velocity", "min_acceleration", "max_acceleration",
+        "jerk_min", "jerk_max", "delta_min", "delta_max", "delta_rate_min", "delta_rate_max",
+        "safe_margin",
+        "w_jerk", "w_delta_rate", "w_x_target", "w_y_target", "w_theta", "w_v", "w_a", "w_delta",
+        "abs_cost_tol", "rel_cost_tol", "barrier_t", "barrier_eps", "delta_t")] + [
+        ("num_of_disc", C.c_int32), ("max_iter_num", C.c_int32)]
+
+
+class BatchIn(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("M_max", C.c_int32), ("S_left", C.c_int32),
+                ("S_right", C.c_int32), ("start", C.c_void_p), ("coarse", C.c_void_p),
+                ("corridor", C.c_void_p), ("corridor_cnt", C.c_void_p), ("lane_left", C.c_void_p),
+                ("lane_right", C.c_void_p)]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "states", "controls", "status", "trajectory", "init_states", "init_controls", "cost_hist",
+        "iter_states", "iter_controls", "hist_len")] + [("hist_cap", C.c_int32)]
+
+
+class DebugOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "corridor", "lanes", "X0", "U0", "cost0", "A11", "Jx", "Ju", "Hx", "Hu", "Kg", "kg", "dV",
+        "Xn", "Un", "costn", "nearest")]
+
+
+EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_destroy",
+           "cilqr_plan_batch", "cilqr_plan_batch_device", "cilqr_synchronize",
+           "cilqr_kernel_launches", "cilqr_last_kernel_ms", "cilqr_occupancy", "cilqr_strerror",
+           "cilqr_last_cuda_error", "cilqr_debug_first_iteration"]
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library(build_if_missing: bool = True):
+    """Loads libcilqr_b200.so (building it with nvcc when absent).  Raises if that fails."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.is_stale():
+        _build.build_library()
+    if not os.path.exists(_build.LIB_PATH):
+        raise CilqrError(E_NO_DEVICE, f"{_build.LIB_PATH} is missing and could not be built; "
+                         "the CUDA extension is required (no CPU fallback)")
+    L = C.CDLL(_build.LIB_PATH)
+    L.cilqr_abi_version.restype = C.c_int
+    L.cilqr_default_params.argtypes = [C.POINTER(Params)]
+    L.cilqr_default_params.restype = None
+    L.cilqr_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.POINTER(C.c_void_p)]
+    L.cilqr_destroy.argtypes = [C.c_void_p]
+    L.cilqr_destroy.restype = None
+    L.cilqr_plan_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut)]
+    L.cilqr_plan_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_void_p]
+    L.cilqr_synchronize.argtypes = [C.c_void_p]
+    L.cilqr_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.cilqr_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cilqr_occupancy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.cilqr_strerror.argtypes = [C.c_int]
+    L.cilqr_strerror.restype = C.c_char_p
+    L.cilqr_last_cuda_error.argtypes = [C.c_void_p]
+    L.cilqr_last_cuda_error.restype = C.c_char_p
+    L.cilqr_debug_first_iteration.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(DebugOut)]
+    _lib = L
+    return L
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().cilqr_default_params(C.byref(p))
+    return p
+
+
+def _ptr(x):
+    """numpy array / torch tensor / int / None -> address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch.Tensor
+
+
+class Solver:
+    """Owns one cilqr_handle (device buffers + streams) on ``device``."""
+
+    def __init__(self, params: Params | None = None, device: int = 0, N_max: int = 200,
+                 M_max: int = 32, S_max: int = 64, B_max: int = 1 << 21):
+        self._L = load_library()
+        self.params = params or default_params()
+        h = C.c_void_p()
+        rc = self._L.cilqr_create(C.byref(self.params), device, N_max, M_max, S_max, B_max, C.byref(h))
+        if rc != 0:
+            raise CilqrError(rc, self._L.cilqr_strerror(rc).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cilqr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._L.cilqr_strerror(rc).decode()
+            if rc == E_CUDA:
+                msg += " -- " + self._L.cilqr_last_cuda_error(self._h).decode()
+            raise CilqrError(rc, msg)
+
+    @staticmethod
+    def _make_in(B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt, lane_left, lane_right):
+        return BatchIn(B, N, M_max, S_left, S_right, _ptr(start), _ptr(coarse), _ptr(corridor),
+                       _ptr(corridor_cnt), _ptr(lane_left), _ptr(lane_right))
+
+    def plan_batch(self, batch, trajectory: bool = False, init_guess: bool = False, hist_cap: int = 0,
+                   out: dict | None = None) -> dict:
+        """Host path.  ``batch`` is a ScenarioBatch-like object with numpy arrays (pinned memory
+        gives asynchronous copies).  Returns numpy outputs (or fills the arrays given in ``out``)."""
+        B, N, K = batch.B, batch.N, batch.N + 1
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        arrs = [f64(batch.start), f64(batch.coarse), f64(batch.corridor),
+                np.ascontiguousarray(batch.corridor_cnt, dtype=np.int32), f64(batch.lane_left), f64(batch.lane_right)]
+        bi = self._make_in(B, N, batch.M_max, arrs[4].shape[1], arrs[5].shape[1], *arrs)
+        o = out if out is not None else {}
+        o.setdefault("states", np.empty((B, K, 6)))
+        o.setdefault("controls", np.empty((B, N, 2)))
+        o.setdefault("status", np.empty((B, 8)))
+        if trajectory:
+            o.setdefault("trajectory", np.empty((B, K, 13)))
+        if init_guess:
+            o.setdefault("init_states", np.empty((B, K, 6)))
+            o.setdefault("init_controls", np.empty((B, N, 2)))
+        if hist_cap > 0:
+            o.setdefault("cost_hist", np.zeros((B, hist_cap, 5)))
+            o.setdefault("iter_states", np.zeros((B, hist_cap, K, 6)))
+            o.setdefault("iter_controls", np.zeros((B, hist_cap, N, 2)))
+            o.setdefault("hist_len", np.zeros((B, 2), dtype=np.int32))
+        bo = BatchOut(*[_ptr(o.get(n)) for n in ("states", "controls", "status", "trajectory", "init_states",
+                                                  "init_controls", "cost_hist", "iter_states", "iter_controls",
+                                                  "hist_len")], hist_cap)
+        self._check(self._L.cilqr_plan_batch(self._h, C.byref(bi), C.byref(bo)))
+        return o
+
+    def plan_batch_device(self, B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt,
+                          lane_left, lane_right, states, controls, status, trajectory=None,
+                          init_states=None, init_controls=None, stream: int | None = None):
+        """Device path: every array argument is a device pointer (int) or a CUDA torch tensor.
+        Enqueues the solve kernel and returns immediately."""
+        bi = self._make_in(B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt, lane_left, lane_right)
+        bo = BatchOut(_ptr(states), _ptr(controls), _ptr(status), _ptr(trajectory), _ptr(init_states),
+                      _ptr(init_controls), None, None, None, None, 0)
+        self._check(self._L.cilqr_plan_batch_device(self._h, C.byref(bi), C.byref(bo), stream))
+
+    def debug_first_iteration(self, B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt,
+                              lane_left, lane_right, outs: dict):
+        bi = self._make_in(B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt, lane_left, lane_right)
+        d = DebugOut(*[_ptr(outs.get(n)) for n, _ in DebugOut._fields_])
+        self._check(self._L.cilqr_debug_first_iteration(self._h, C.byref(bi), C.byref(d)))
+
+    def synchronize(self):
+        self._check(self._L.cilqr_synchronize(self._h))
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        self._check(self._L.cilqr_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.cilqr_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def occupancy(self, N: int, S_left: int, S_right: int):
+        w, s = C.c_int(), C.c_int()
+        self._check(self._L.cilqr_occupancy(self._h, N, S_left, S_right, C.byref(w), C.byref(s)))
+        return w.value, s.value

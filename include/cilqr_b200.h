@@ -1,0 +1,160 @@
+/*
+ * cilqr_b200.h -- C ABI of the B200-native batched constrained-iLQR solver.
+ *
+ * Drop-in boundary for the hot path of mpt0816/Cilqr:
+ *     planning::IlqrOptimizer::Plan(start_state, coarse_traj, corridor, left_lane_cons,
+ *                                   right_lane_cons, opt_trajectory*, iter_trajs*)
+ *     (reference: algorithm/ilqr/ilqr_optimizer.h:41-48, algorithm/ilqr/ilqr_optimizer.cc:53-95)
+ * The reference has no FFI layer; the seam is that C++ class.  include/cilqr/ilqr_optimizer_b200.h
+ * provides a header-compatible planning::IlqrOptimizer that packs its arguments into the flat
+ * arrays below (B = 1) and calls this ABI.  The same ABI solves B independent scenarios per call.
+ *
+ * Plain pointers and sizes only; no C++/Eigen/torch types.  All functions return 0 on success or a
+ * negative CILQR_E_* code and never throw.  A handle owns its device buffers and CUDA streams; it
+ * is thread-compatible (distinct handles may be used from distinct threads) but not re-entrant.
+ *
+ * Wire format (all floating point is IEEE double -- the reference's arithmetic type; scenario
+ * major, C order, K = N + 1 knots):
+ *   start        [B][4]              x, y, theta, v            trajectory_planner.cpp:73-75
+ *   coarse       [B][K][6]           x, y, theta, v, a, delta  fields TransformGoals reads,
+ *                                                              ilqr_optimizer.cc:141-152
+ *   corridor     [B][K][M_max][3]    raw half-planes (a,b,c), a*x + b*y < c   corridor.h:20-22
+ *   corridor_cnt [B][K] int32        planes used at each knot (slots >= cnt are never read)
+ *   lane_left    [B][S_left][7]      a, b, c, x0, y0, x1, y1: half-plane + LineSegment2d
+ *   lane_right   [B][S_right][7]     start/end as constructed in corridor.cc:279,300
+ *   states       [B][K][6]   out     x, y, theta, v, a, delta
+ *   controls     [B][N][2]   out     jerk, delta_rate
+ *   status       [B][8]      out     see CILQR_ST_* below
+ *   trajectory   [B][K][13]  out     TrajectoryPoint records (discretized_trajectory.h:26-43) as
+ *                                    TransformToTrajectory fills them, ilqr_optimizer.cc:771-791
+ * Shrinking/normalising the constraints (ilqr_optimizer.cc:438-495) is part of the solve.
+ */
+#ifndef CILQR_B200_H_
+#define CILQR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CILQR_ABI_VERSION 1
+
+/* error codes */
+#define CILQR_OK 0
+#define CILQR_E_INVALID (-1)   /* null pointer / bad size: the reference's guards, ilqr_optimizer.cc:64-78 */
+#define CILQR_E_CUDA (-2)      /* CUDA runtime error (see cilqr_last_cuda_error) */
+#define CILQR_E_NO_DEVICE (-3) /* no sm_100 device: there is no CPU fallback */
+#define CILQR_E_CAPACITY (-4)  /* batch/horizon exceeds what the handle was created for */
+#define CILQR_E_SMEM (-5)      /* horizon does not fit the per-warp shared-memory stage */
+
+/* status[b][CILQR_ST_FLAG] values: which exit of Optimize() was taken */
+#define CILQR_CONVERGED_ABS 0    /* dcost < abs_cost_tol         ilqr_optimizer.cc:281,287 */
+#define CILQR_CONVERGED_REL 1    /* dcost/cost_old < rel_tol     ilqr_optimizer.cc:282,289 */
+#define CILQR_CONVERGED_GRAD 2   /* gradient norm exit           ilqr_optimizer.cc:236-241 */
+#define CILQR_LAMBDA_OVERFLOW 3  /* "kUnsolved"                  ilqr_optimizer.cc:302-307 */
+#define CILQR_MAX_ITER 4         /* loop exhausted               ilqr_optimizer.cc:312-319 */
+
+/* layout of one status record (8 doubles) */
+#define CILQR_ST_FLAG 0       /* one of the values above */
+#define CILQR_ST_ITERS 1      /* loop index `iter` at exit */
+#define CILQR_ST_COST 2       /* total cost of the returned trajectory ... */
+#define CILQR_ST_COST_TARGET 3
+#define CILQR_ST_COST_DYNAMIC 4
+#define CILQR_ST_COST_CORRIDOR 5
+#define CILQR_ST_COST_LANE 6  /* ... and its breakdown, struct Cost ilqr_optimizer.h:14-27 */
+#define CILQR_ST_ALPHA_HASH 7 /* FNV-1a over the accepted line-search index per iteration (11 = rejected) */
+#define CILQR_STATUS_DOUBLES 8
+#define CILQR_TRAJPOINT_DOUBLES 13
+
+/* POD mirror of VehicleParam (vehicle_param.h:21-64), IlqrConfig/Weights (planner_config.h:45-73),
+ * the RelaxBarrierFunction members (barrier_function.h:143-146) and delta_t (planner_config.h:94). */
+typedef struct CilqrParams {
+  double front_hang_length, wheel_base, rear_hang_length, width;
+  double max_velocity, min_acceleration, max_acceleration;
+  double jerk_min, jerk_max, delta_min, delta_max, delta_rate_min, delta_rate_max;
+  double safe_margin;
+  double w_jerk, w_delta_rate, w_x_target, w_y_target, w_theta, w_v, w_a, w_delta;
+  double abs_cost_tol, rel_cost_tol;
+  double barrier_t, barrier_eps;
+  double delta_t;
+  int32_t num_of_disc; /* must be 5 (planner_config.h:58); other values -> CILQR_E_INVALID */
+  int32_t max_iter_num;
+} CilqrParams;
+
+typedef struct CilqrBatchIn {
+  int32_t B, N, M_max, S_left, S_right;
+  const double* start;
+  const double* coarse;
+  const double* corridor;
+  const int32_t* corridor_cnt;
+  const double* lane_left;
+  const double* lane_right;
+} CilqrBatchIn;
+
+typedef struct CilqrBatchOut {
+  double* states;        /* required */
+  double* controls;      /* required */
+  double* status;        /* required */
+  double* trajectory;    /* optional: [B][K][13] */
+  double* init_states;   /* optional: [B][K][6]  the initial guess = iter_trajs[0], ilqr_optimizer.cc:170 */
+  double* init_controls; /* optional: [B][N][2] */
+  /* optional per-accept history (debug / adapter use, small B): cost_hist [B][hist_cap][5] mirrors
+   * cost_ (ilqr_optimizer.h:50-52, pushes at ilqr_optimizer.cc:173,283,296); iter_states
+   * [B][hist_cap][K][6] and iter_controls [B][hist_cap][N][2] mirror iter_trajs (:170,294);
+   * hist_len [B][2] int32 = {entries pushed to cost_, entries pushed to iter_trajs} */
+  double* cost_hist;
+  double* iter_states;
+  double* iter_controls;
+  int32_t* hist_len;
+  int32_t hist_cap;
+} CilqrBatchOut;
+
+typedef struct cilqr_handle cilqr_handle;
+
+/* Defaults of the reference's parameter structs. */
+void cilqr_default_params(CilqrParams* p);
+
+/* Creates a solver bound to CUDA device `device` for horizons up to N_max steps, up to M_max planes
+ * per knot, up to S_max lane segments per side and host batches up to B_max scenarios.
+ * Replaces IlqrOptimizer::IlqrOptimizer / Init (ilqr_optimizer.cc:13-51). */
+int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, int S_max, int B_max,
+                 cilqr_handle** out);
+void cilqr_destroy(cilqr_handle* h);
+
+/* Solve B scenarios given HOST pointers: chunks the batch, overlaps H2D / solve / D2H on separate
+ * streams, blocks until the outputs are in host memory.  Replaces IlqrOptimizer::Plan. */
+int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out);
+
+/* Same with DEVICE pointers; enqueues on `cuda_stream` (a cudaStream_t passed as void*, NULL =
+ * the handle's own stream) and returns without synchronising. */
+int cilqr_plan_batch_device(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out,
+                            void* cuda_stream);
+int cilqr_synchronize(cilqr_handle* h);
+
+/* Introspection used by bench.py / tests. */
+int cilqr_kernel_launches(const cilqr_handle* h, int64_t* solve_launches);
+int cilqr_last_kernel_ms(cilqr_handle* h, float* ms);      /* CUDA-event time of the last solve kernel */
+int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* warps_per_sm,
+                    int* smem_bytes_per_warp);
+const char* cilqr_strerror(int code);
+const char* cilqr_last_cuda_error(const cilqr_handle* h);
+int cilqr_abi_version(void);
+
+/* Stage-level dump of the first iteration (test hook; device pointers, B scenarios):
+ *   constraints [B][K][M_max][3] + lanes [B][S_left+S_right][3]  shrunk+normalised (a4)
+ *   init X/U, cost5 of the initial guess, linearisation at the initial guess
+ *   (A11 [B][N][12]: A02,A03,A04,A05,A12,A13,A14,A15,A23,A24,A25,B21; Jx [B][K][6]; Ju [B][N][2];
+ *   Hx [B][K][9]: H00,H01,H02,H11,H12,H22,H33,H44,H55; Hu [B][N][2]),
+ *   gains of Backward(lambda=1) (Kg [B][N][12], kg [B][N][2], dV [B][2]) and Forward(alpha=1)
+ *   (Xn [B][K][6], Un [B][N][2], cost5n [B][5]).  Any pointer may be NULL. */
+typedef struct CilqrDebugOut {
+  double *corridor, *lanes, *X0, *U0, *cost0, *A11, *Jx, *Ju, *Hx, *Hu, *Kg, *kg, *dV, *Xn, *Un, *costn;
+  int32_t* nearest; /* [B][K][5][2] nearest lane segment per disc/side at the initial guess */
+} CilqrDebugOut;
+int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in_dev, const CilqrDebugOut* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CILQR_B200_H_ */
