@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200.so")
 SOURCES = ["cilqr_capi.cu"]
 DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", os.path.join("..", "..", "include", "cilqr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
 
 
 def _nvcc() -> str:
@@ -36,6 +36,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB_PATH
+
+
+ADAPTER_DEMO = os.path.join(LIB_DIR, "adapter_demo")
+
+
+def build_adapter_demo(force: bool = False) -> str:
+    """Compiles tests/adapter/adapter_demo.cc -- the reference's C++ call site driven through the
+    header-compatible planning::IlqrOptimizer (include/cilqr/ilqr_optimizer_b200.h) -- against the
+    type stand-ins in tests/adapter/stubs (Eigen/ROS are not installed here) and links it to the
+    product library."""
+    root = os.path.dirname(_HERE)
+    src = os.path.join(root, "tests", "adapter", "adapter_demo.cc")
+    hdr = os.path.join(root, "include", "cilqr", "ilqr_optimizer_b200.h")
+    if (not force and os.path.exists(ADAPTER_DEMO)
+            and os.path.getmtime(ADAPTER_DEMO) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB_PATH))):
+        return ADAPTER_DEMO
+    build_library()
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(root, "tests", "adapter", "stubs"), src, "-o", ADAPTER_DEMO,
+           "-L", LIB_DIR, "-lcilqr_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return ADAPTER_DEMO
 
 
 if __name__ == "__main__":

@@ -1,0 +1,28 @@
+// Stand-in for algorithm/params/planner_config.h:45-73 (Weights, IlqrConfig without the tracker).
+#pragma once
+#include "algorithm/params/vehicle_param.h"
+namespace planning {
+struct Weights {
+  double jerk = 1;
+  double delta_rate = 1;
+  double x_target = 0.5;
+  double y_target = 0.5;
+  double theta = 1e-3;
+  double v = 0.0;
+  double a = 0.0;
+  double delta = 0.0;
+};
+struct IlqrConfig {
+  int num_of_disc = 5;
+  double safe_margin = 0.2;
+  double t = 100.0;
+  double t_rate = 10.0;
+  Weights weights;
+  int max_iter_num = 200;
+  double abs_cost_tol = 1e-2;
+  double rel_cost_tol = 1e-2;
+  double alpha = 1.0;
+  double gamma = 0.5;
+  double rho = 1e-9;
+};
+}  // namespace planning

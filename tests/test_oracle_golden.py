@@ -1,0 +1,59 @@
+"""CPU-side pins of the oracle: the committed golden fixture and the rounding-noise floor."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from cilqr_b200 import scenarios
+
+
+def rel(a, b):
+    return np.abs(a - b) / (np.abs(b) + 1.0)
+
+
+def test_oracle_reproduces_golden_fixture(oracle):
+    """tests/golden/cilqr_golden_v1.npz (made by tests/golden/make_golden.py) -- regression pin of the
+    oracle itself.  Not reference output: the reference cannot run here."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cilqr_golden_v1.npz"))
+    batch = scenarios.ScenarioBatch(int(z["N"]), int(z["M_max"]), int(z["S"]), z["start"], z["coarse"], z["corridor"],
+                                    z["corridor_cnt"], z["lane_left"], z["lane_right"])
+    # the generator is part of the fixture contract: same seed -> same inputs
+    regen = scenarios.generate(424242, 0, 12, N=40, n_obs=11, M_max=12, S=24)
+    for a, b in ((regen.start, batch.start), (regen.coarse, batch.coarse), (regen.corridor, batch.corridor),
+                 (regen.lane_left, batch.lane_left)):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+    X, U, S, conv = oracle.solve_batch(batch, nthreads=2)
+    assert np.array_equal(S[:, :2], z["status"][:, :2]) and np.array_equal(S[:, 7], z["status"][:, 7])
+    np.testing.assert_allclose(X, z["states"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(U, z["controls"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(S[:, 2:7], z["status"][:, 2:7], rtol=1e-9)
+    # qualitative envelope of the shipped demo (resources/cost.png): the solve lowers the cost
+    assert np.all(S[:, 2] <= z["cost_init"][:, 0] + 1e-9)
+
+
+def test_rounding_noise_floor_of_the_oracle(oracle):
+    """Context for the tolerances above (CPU only, but reported next to the GPU numbers): the same C
+    restatement compiled with FMA contraction (what `-march=native` does to the reference) differs from
+    the default build by rounding only, yet a few scenarios take a different decision path."""
+    import os
+    import subprocess
+    here = os.path.dirname(oracle.__file__)
+    fma = os.path.join(here, "libcilqr_oracle_fma.so")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=fast", "-fPIC", "-std=c99", "-D_GNU_SOURCE", "-shared",
+                           "-o", fma, os.path.join(here, "cilqr_oracle.c"), "-lm", "-lpthread"])
+    L2 = C.CDLL(fma)
+    batch = scenarios.generate(7, 0, 512, N=100)
+    Xo, Uo, So, _ = oracle.solve_batch(batch, nthreads=os.cpu_count() or 1)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    X2, U2, S2 = np.zeros_like(Xo), np.zeros_like(Uo), np.zeros_like(So)
+    p = oracle.default_params()
+    cnt = np.ascontiguousarray(batch.corridor_cnt, dtype=np.int32)
+    d = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    L2.cilqr_oracle_solve_batch(C.byref(p), batch.B, batch.N, batch.M_max, batch.S, batch.S, d(batch.start), d(batch.coarse),
+                                d(batch.corridor), cnt.ctypes.data_as(ip), d(batch.lane_left), d(batch.lane_right),
+                                d(X2), d(U2), d(S2), os.cpu_count() or 1)
+    same = (S2[:, 0] == So[:, 0]) & (S2[:, 1] == So[:, 1]) & (S2[:, 7] == So[:, 7])
+    e = np.maximum(rel(X2, Xo).reshape(batch.B, -1).max(axis=1), rel(U2, Uo).reshape(batch.B, -1).max(axis=1))
+    print(f"\n[noise floor] oracle(-O2) vs oracle(-O2 -mfma -ffp-contract=fast): identical path {same.sum()}/{batch.B}, "
+          f"median {np.median(e[same]):.2e}, p99 {np.quantile(e[same], 0.99):.2e}, max {e[same].max():.2e}")
+    assert same.mean() > 0.9
