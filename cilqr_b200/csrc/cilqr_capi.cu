@@ -115,13 +115,12 @@ SmemLayout make_layout(int N, int S_left, int S_right) {
   int o = 0;
   L.X = o; o += K * 6;
   L.U = o; o += N * 2;
-  L.Xc = o; o += K * 6;
-  L.Uc = o; o += N * 2;
   L.Kg = o; o += N * 12;
   L.kg = o; o += N * 2;
   L.lin = o; o += 32 * cilqr::kLinStride;
   o += (o & 1);
   L.seg = o; o += (S_left + S_right) * cilqr::kSegStride;
+  L.grp = o; o += ((S_left + cilqr::kGroup - 1) / cilqr::kGroup + (S_right + cilqr::kGroup - 1) / cilqr::kGroup) * 3;
   L.scr = o; o += cilqr::kScratch;
   L.nidx = o;
   L.nidx_bytes = (K * 10 + 7) / 8 * 8;
@@ -133,13 +132,15 @@ struct Launch {
   SmemLayout sm;
   int blocks_per_sm = 0;
   int grid = 0;
-  int Kp = 0;
+  int Kp = 0, Kc = 0;
+  size_t ws_stride = 0;
 };
 
 int plan_launch(cilqr_handle* h, int B, int N, int S_left, int S_right, Launch* out) {
   Launch L;
   L.sm = make_layout(N, S_left, S_right);
   L.Kp = (N + 1 + 31) / 32 * 32;
+  L.Kc = (N + 1 + 3) / 4 * 4;
   if (L.sm.total_bytes > h->smem_optin) return CILQR_E_SMEM;
   CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, cilqr::cilqr_solve_kernel, 32, L.sm.total_bytes));
@@ -182,7 +183,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   Launch L;
   int rc = plan_launch(h, in->B, in->N, in->S_left, in->S_right, &L);
   if (rc != CILQR_OK) return rc;
-  rc = ensure_ws(h, s, (size_t)L.grid * in->M_max * 3 * L.Kp * sizeof(double));
+  L.ws_stride = (size_t)in->M_max * 3 * L.Kp + (size_t)cilqr::kNAlpha * 8 * L.Kc;
+  rc = ensure_ws(h, s, (size_t)L.grid * L.ws_stride * sizeof(double));
   if (rc != CILQR_OK) return rc;
   KernelArgs a;
   memset(&a, 0, sizeof(a));
@@ -194,6 +196,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.S_left = in->S_left;
   a.S_right = in->S_right;
   a.Kp = L.Kp;
+  a.Kc = L.Kc;
+  a.ws_stride = L.ws_stride;
   a.start = in->start;
   a.coarse = in->coarse;
   a.corridor = in->corridor;

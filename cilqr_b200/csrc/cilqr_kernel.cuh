@@ -2,11 +2,13 @@
 //
 // One warp (= one 32-thread CTA) solves one scenario at a time; a persistent grid pulls scenario
 // ids from an atomic ticket because iteration counts are ragged.  The whole horizon of the
-// iterate (x, u), the line-search candidate (x', u'), the feedback gains (K, k), the lane
-// segments and a 32-knot window of the linearisation (A, B, Jx, Ju, Hx, Hu) are staged in
-// shared memory; the shrunk + normalised corridor half-planes live in a per-CTA global
-// workspace ([plane][component][knot] so that lane == knot loads are coalesced) that stays L2
-// resident.  All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>);
+// iterate (x, u), the feedback gains (K, k), the lane segments and a 32-knot window of the
+// linearisation (A, B, Jx, Ju, Hx, Hu) are staged in shared memory; the shrunk + normalised
+// corridor half-planes and the eleven line-search candidates live in a per-CTA global workspace
+// ([plane|candidate][component][knot], so that lane == knot accesses are coalesced) that stays
+// L2 resident.  The line search is speculative: lane a rolls out step size alpha_a, so one serial
+// pass over the horizon produces all eleven candidates of ilqr_optimizer.cc:246-265; their costs
+// are then evaluated in the reference's order (lane == knot) until the first one is accepted.  All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>);
 // B200 has a full-rate FP64 pipe (64 lanes/clk/SM), no tensor cores are involved.
 //
 // Reference functions re-created here (file:line relative to the reference root):
@@ -32,8 +34,9 @@ constexpr int kNX = 6;
 constexpr int kNU = 2;
 constexpr int kDisc = 5;
 constexpr int kNAlpha = 11;
-constexpr int kLinStride = 31;  // doubles per knot in the linearisation window
+constexpr int kLinStride = 35;  // doubles per knot in the linearisation window
 constexpr int kSegStride = 10;  // sx sy ex ey ux uy len a b c
+constexpr int kGroup = 8;       // lane segments per bounding-circle group of the pruned nearest search
 constexpr int kScratch = 192;   // doubles of per-warp scratch
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -44,6 +47,10 @@ constexpr int LJX = 12;  // 6
 constexpr int LJU = 18;  // 2
 constexpr int LHX = 20;  // H00 H01 H02 H11 H12 H22 H33 H44 H55
 constexpr int LHU = 29;  // 2
+constexpr int LZ = 31;   // constants 0, 1, dt, dt^2/2 so that A, B, H can be gathered by offset
+constexpr int LO = 32;
+constexpr int LDT = 33;
+constexpr int LB30 = 34;
 
 struct DevParams {
   double dt, L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
@@ -56,7 +63,7 @@ struct DevParams {
 };
 
 struct SmemLayout {  // offsets in doubles from the start of dynamic shared memory
-  int X, U, Xc, Uc, Kg, kg, lin, seg, scr, nidx;  // nidx: two byte arrays of nidx_bytes each
+  int X, U, Kg, kg, lin, seg, grp, scr, nidx;  // nidx: two byte arrays of nidx_bytes each
   int nidx_bytes;
   int total_bytes;
 };
@@ -69,7 +76,8 @@ struct DebugPtrs {
 struct KernelArgs {
   DevParams P;
   SmemLayout sm;
-  int B, N, M_max, S_left, S_right, Kp;
+  int B, N, M_max, S_left, S_right, Kp, Kc;  // Kp / Kc: knot pitch of the plane / candidate arrays
+  size_t ws_stride;  // doubles of workspace per CTA: M_max*3*Kp planes + kNAlpha*8*Kc candidates
   const double* start;
   const double* coarse;
   const double* corridor;
@@ -87,7 +95,7 @@ struct KernelArgs {
   double* iter_controls;
   int32_t* hist_len;
   int hist_cap;
-  double* ws;           // [gridDim.x][M_max*3*Kp]
+  double* ws;           // [gridDim.x][ws_stride]
   unsigned int* ticket; // scenario counter
   DebugPtrs dbg;
   int debug;            // 1: stop after the first iteration and dump stages
@@ -116,7 +124,38 @@ __device__ __forceinline__ double normalize_angle(double angle) {
   return a - kPi;
 }
 
+// Fast branch of normalize_angle only; sets `slow` when the argument needs the general branch.
+__device__ __forceinline__ double normalize_angle_fast(double angle, bool& slow) {
+  const double kPi = 3.14159265358979323846;
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  const double a = angle + kPi;
+  slow = slow || !(a >= 0.0 && a < kTwoPi);
+  return a - kPi;
+}
+
 // vehicle_model.cc:88-138: midpoint RK2, same control at both stages, wrap theta and delta.
+// kFastOnly: never enter the fmod branch of NormalizeAngle; `slow` reports that it was needed
+// (the caller then discards this rollout and repeats it with kFastOnly = false).
+template <bool kFastOnly>
+__device__ __forceinline__ void dynamics_step_t(const DevParams& P, double* x, double u0, double u1, bool& slow) {
+  auto na = [&](double v) { return kFastOnly ? normalize_angle_fast(v, slow) : normalize_angle(v); };
+  double s2, c2;
+  const double de = na(x[5]);
+  const double k1t = x[3] * tan(de) / P.L;  // theta enters k1 only through k1x, k1y, which the midpoint step never uses
+  const double h = 0.5 * P.dt;
+  const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
+  const double thm = na(m2);
+  const double dem = na(m5);
+  sincos(thm, &s2, &c2);
+  const double k2x = m3 * c2, k2y = m3 * s2, k2t = m3 * tan(dem) / P.L;
+  x[0] = x[0] + P.dt * k2x;
+  x[1] = x[1] + P.dt * k2y;
+  x[2] = na(x[2] + P.dt * k2t);
+  x[3] = x[3] + P.dt * m4;
+  x[4] = x[4] + P.dt * u0;
+  x[5] = na(x[5] + P.dt * u1);
+}
+
 __device__ __forceinline__ void dynamics_step(const DevParams& P, double* x, double u0, double u1) {
   double s1, c1;
   const double th = normalize_angle(x[2]);
@@ -221,7 +260,8 @@ struct Ctx {
   const double* goals;  // global [K][6] (row 0 is replaced by g0)
   double g0[6];
   const int32_t* cnt;   // global [K]
-  double* ws;           // global workspace of this CTA
+  double* ws;           // global workspace of this CTA: planes [M_max][3][Kp]
+  double* cand;         // ... followed by the candidates [kNAlpha][8][Kc]: x0..x5, u0, u1
   __device__ Ctx(const KernelArgs& a_, double* s) : a(a_), sm(s) {}
   __device__ __forceinline__ double goal(int k, int c) const { return k == 0 ? g0[c] : goals[k * 6 + c]; }
 };
@@ -229,8 +269,19 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------
 // TotalCost of (Xs, Us): lane == knot.  Also records the nearest lane segment of every
 // (knot, disc, side) in nidx for the linearisation that follows an accepted step.
-__device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, unsigned char* nidx,
-                          double cost5[5]) {
+// kCand = false: (Xs, Us) are the shared-memory iterate ([K][6], [N][2]); kCand = true: Xs points
+// at one candidate block of the global workspace ([8][Kc]) and Us is ignored.
+//
+// Nearest lane segment (FindNeastLaneSegment, ilqr_optimizer.cc:605-618) without scanning all S
+// segments: segments are bundled in groups of kGroup with a bounding circle (centre, radius) built
+// at scenario load.  For every disc the exact distance to the segment that was nearest in the
+// current iterate (`guess`) is an upper bound ub on the minimum; a group whose circle is farther
+// from the rear-axle point than ub + radius + (largest disc offset) cannot contain the minimiser
+// of any disc -- nor tie with it -- and is skipped.  Surviving groups are scanned in index order
+// with the reference's strict '<', so the arg-min (first minimum) is the brute-force one.
+template <bool kCand>
+__device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, const unsigned char* guess,
+                          unsigned char* nidx, double cost5[5]) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
@@ -240,8 +291,14 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, unsi
     const int k = k0 + c.lane;
     const bool act = k < K;
     const int kk = act ? k : K - 1;
-    const double* x = Xs + kk * 6;
-    const double px = x[0], py = x[1], th = x[2], v = x[3], ac = x[4], de = x[5];
+    double px, py, th, v, ac, de;
+    if (kCand) {
+      const double* x = Xs + kk;
+      px = x[0], py = x[a.Kc], th = x[2 * a.Kc], v = x[3 * a.Kc], ac = x[4 * a.Kc], de = x[5 * a.Kc];
+    } else {
+      const double* x = Xs + kk * 6;
+      px = x[0], py = x[1], th = x[2], v = x[3], ac = x[4], de = x[5];
+    }
     double tj = 0.0, td = 0.0, tc = 0.0, tl = 0.0;
     {
       const double dx = px - c.goal(kk, 0), dy = py - c.goal(kk, 1), dth = th - c.goal(kk, 2);
@@ -254,7 +311,8 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, unsi
       bar_add(bd, de - P.dmax, P);
       bar_add(bd, P.dmin - de, P);
       if (kk < N) {
-        const double u0 = Us[kk * 2], u1 = Us[kk * 2 + 1];
+        const double u0 = kCand ? Xs[6 * a.Kc + kk] : Us[kk * 2];
+        const double u1 = kCand ? Xs[7 * a.Kc + kk] : Us[kk * 2 + 1];
         tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
         bar_add(bd, u0 - P.jmax, P);
         bar_add(bd, P.jmin - u0, P);
@@ -297,24 +355,37 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, unsi
       for (int side = 0; side < 2; ++side) {
         const int S = side == 0 ? a.S_left : a.S_right;
         const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+        const int ng = (S + kGroup - 1) / kGroup;
+        const double* gp = c.sm + a.sm.grp + (side == 0 ? 0 : (a.S_left + kGroup - 1) / kGroup) * 3;
         double best[kDisc];
         int bi[kDisc];
+        double ub2 = 0.0;
 #pragma unroll
         for (int d = 0; d < kDisc; ++d) {
           best[d] = 1.7976931348623157e308;
           bi[d] = 0;
+          int gi = guess[kk * 10 + d * 2 + side];
+          gi = gi < S ? gi : S - 1;
+          ub2 = fmax(ub2, seg_dist2(sg0 + gi * kSegStride, xd[d], yd[d]));
         }
-        for (int s = 0; s < S; ++s) {
-          const double* sg = sg0 + s * kSegStride;
-          double r[7];
+        const double ub = sqrt(ub2);
+        for (int g = 0; g < ng; ++g) {
+          const double dcx = px - gp[g * 3], dcy = py - gp[g * 3 + 1];
+          const double thr = ub + gp[g * 3 + 2];
+          if (fma(dcx, dcx, dcy * dcy) > thr * thr) continue;  // (NaN compares false: never pruned)
+          const int s_hi = (g + 1) * kGroup < S ? (g + 1) * kGroup : S;
+          for (int s = g * kGroup; s < s_hi; ++s) {
+            const double* sg = sg0 + s * kSegStride;
+            double r[7];
 #pragma unroll
-          for (int q = 0; q < 7; ++q) r[q] = sg[q];
+            for (int q = 0; q < 7; ++q) r[q] = sg[q];
 #pragma unroll
-          for (int d = 0; d < kDisc; ++d) {
-            const double dd = seg_dist2(r, xd[d], yd[d]);
-            if (dd < best[d]) {
-              best[d] = dd;
-              bi[d] = s;
+            for (int d = 0; d < kDisc; ++d) {
+              const double dd = seg_dist2(r, xd[d], yd[d]);
+              if (dd < best[d]) {
+                best[d] = dd;
+                bi[d] = s;
+              }
             }
           }
         }
@@ -439,6 +510,10 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
       plane(sg[7], sg[8], sg[9], d, d + 1);
     }
   }
+  rec[LZ] = 0.0;
+  rec[LO] = 1.0;
+  rec[LDT] = P.dt;
+  rec[LB30] = 0.5 * P.dt * P.dt;
   rec[LJX + 0] = Jx0;
   rec[LJX + 1] = Jx1;
   rec[LJX + 2] = Jx2;
@@ -480,34 +555,109 @@ constexpr int ST = 174;    // 12  T = Quu K + Qux
 constexpr int SK = 186;    // gains of this knot are read from Kg/kg directly
 static_assert(SK <= kScratch, "scratch overflow");
 
-// ilqr_optimizer.cc:334-390 with the window-wise linearisation fused in (ilqr_optimizer.cc:203-214).
+// ---- Backward (ilqr_optimizer.cc:334-390) in augmented, lane-uniform form --------------------
+// With z = (x, 1) and F = [A | B] (6 x 8) one knot of the recursion is
+//   M   = [Vxx ; Vx^T]                       7 x 6   value function (row 6 = gradient)
+//   G   = M F                                7 x 8
+//   Qh  = Hh + F^T G[0:6]  (8 x 8, sym)      = [[Qxx, Qux^T], [Qux, Quu]]
+//   ql  = Jh + G[6]        (8)               = (Qx, Qu)
+//   Kh  = -(Quu + lambda I)^-1 [Qux | Qu]    2 x 7   = (K, k)            (:361-366)
+//   M' (i,j) = Qz(i,j) + sum_a Kh(a,i) T(a,j) + sum_a Qu_(a,i) Kh(a,j),  T = Quu Kh + [Qux | Qu]
+//                                            (:379-381, un-regularised Quu, quirk Q3)
+// so that every lane evaluates the same expression on operands gathered by per-lane offsets that
+// are fixed before the knot loop.  delta_V (:383-384) is accumulated per lane from the UPDATED
+// value function (lazy-expression quirk Q21): k.Qu' = k.Ju + y.Vx', k.Quu'.k = k.Hu.k + y.Vxx'.y,
+// y = B k, and reduced once at the end of the pass.
+__device__ __forceinline__ int f_off(int r, int cc) {  // offset of F[r][cc] inside a linearisation record
+  if (cc < 6) {
+    if (r == cc) return LO;
+    if (r == 0 && cc >= 2) return LA + cc - 2;
+    if (r == 1 && cc >= 2) return LA + 4 + cc - 2;
+    if (r == 2 && cc >= 3) return LA + 8 + cc - 3;
+    if (r == 3 && cc == 4) return LDT;
+    return LZ;
+  }
+  if (cc == 6) return r == 3 ? LB30 : r == 4 ? LDT : LZ;
+  return r == 2 ? LB21 : r == 5 ? LDT : LZ;
+}
+__device__ __forceinline__ int h_off(int p, int q) {  // offset of Hh[p][q], p <= q
+  if (p == q) {
+    if (p < 3) return LHX + (p == 0 ? 0 : p == 1 ? 3 : 5);
+    if (p < 6) return LHX + 6 + p - 3;
+    return LHU + p - 6;
+  }
+  if (q < 3) return LHX + (p == 0 ? q : 4);
+  return LZ;
+}
+
+constexpr int SM_ = 0;    // 42  M   [7][6]
+constexpr int SG = 42;    // 56  G   [7][8]
+constexpr int SQH = 98;   // 64  Qh  [8][8]
+constexpr int SQL = 162;  // 8   ql
+constexpr int SKH = 170;  // 14  Kh  [2][7]
+static_assert(SKH + 14 <= SK, "scratch overflow");
+
 __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, const double* Us,
                               const unsigned char* nidx, double dV[2], const DebugPtrs* dbg, int b) {
   const KernelArgs& a = c.a;
-  const DevParams& P = a.P;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
   double* lin = c.sm + a.sm.lin;
   double* scr = c.sm + a.sm.scr;
   double* Kg = c.sm + a.sm.Kg;
   double* kg = c.sm + a.sm.kg;
-  const double B30 = 0.5 * P.dt * P.dt, B40 = P.dt, B51 = P.dt;
-  // upper-triangle role of this lane
-  int ui = 0, uj = 0;
-  {
-    int e = lane, i = 0;
-    while (i < 5 && e >= 6 - i) {
-      e -= 6 - i;
-      ++i;
+  double* M = scr + SM_;
+  double* G = scr + SG;
+  double* Qh = scr + SQH;
+  double* ql = scr + SQL;
+  double* Kh = scr + SKH;
+
+  // ---- per-lane roles (fixed for the whole pass)
+  // S1: G[i][cc], cc = lane & 7, i = lane >> 3 and 4 + (lane >> 3)
+  const int s1c = lane & 7, s1i = lane >> 3;
+  int fo1[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) fo1[r] = f_off(r, s1c);
+  // S2 round A: pair e = lane of the 36 (p <= q); round B: lanes 0..3 pairs 32..35, lanes 4..11 ql[lane-4]
+  auto pair_of = [](int e, int& p, int& q) {
+    int pp = 0, rem = e;
+    while (rem >= 8 - pp) {
+      rem -= 8 - pp;
+      ++pp;
     }
-    ui = i;
-    uj = i + e;
-    if (lane >= 21) {
-      ui = 0;
-      uj = 0;
-    }
+    p = pp;
+    q = pp + rem;
+  };
+  int pA, qA, pB = 0, qB = 0;
+  pair_of(lane, pA, qA);
+  if (lane < 4) pair_of(32 + lane, pB, qB);
+  int fo2A[6], fo2B[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    fo2A[r] = f_off(r, pA);
+    fo2B[r] = f_off(r, pB);
   }
-  double dv0 = 0.0, dv1 = 0.0;
+  const int hoA = h_off(pA, qA), hoB = h_off(pB, qB);
+  const int qL = lane - 4;                                   // ql index on lanes 4..11
+  const int joL = qL < 6 ? LJX + qL : LJU + qL - 6;          // Jh offset (valid on lanes 4..11)
+  // S4: entry (vi, vj), vi <= vj <= 6, (6,6) excluded -> 27 lanes
+  int vi = 0, vj = 0;
+  {
+    int rem = lane < 27 ? lane : 0, ii = 0;
+    while (rem >= 7 - ii) {
+      rem -= 7 - ii;
+      ++ii;
+    }
+    vi = ii;
+    vj = ii + rem;
+  }
+  // y = B k: component offset / which k (0 -> k0, 1 -> k1); rows 0,1 of B are zero
+  auto yoff = [](int i) { return i == 2 ? LB21 : i == 3 ? LB30 : (i == 4 || i == 5) ? LDT : LZ; };
+  const int yoi = yoff(vi), yoj = vj < 6 ? yoff(vj) : LZ;
+  const int yki = (vi == 3 || vi == 4) ? 0 : 1, ykj = (vj == 3 || vj == 4) ? 0 : 1;
+  const double wsym = vi == vj ? 0.5 : 1.0;  // 0.5 * (1 or 2) y_i V_ij y_j
+
+  double acc0 = 0.0, acc1 = 0.0;
   const int last_chunk = (K - 1) / 32;
   for (int ch = last_chunk; ch >= 0; --ch) {
     const int k0 = ch * 32;
@@ -532,177 +682,130 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
     if (ch == last_chunk) {
       // Vx = cost_Jx.back(), Vxx = cost_Hx.back()    (:343-344)
       const double* rec = lin + (N - k0) * kLinStride;
-      for (int e = lane; e < 36; e += 32) {
+      for (int e = lane; e < 42; e += 32) {
         const int i = e / 6, j = e % 6;
-        double v = 0.0;
-        if (i == j) v = i < 3 ? rec[LHX + (i == 0 ? 0 : i == 1 ? 3 : 5)] : rec[LHX + 6 + i - 3];
-        else if (i < 3 && j < 3) {
-          const int lo = i < j ? i : j, hi = i < j ? j : i;
-          v = rec[LHX + (lo == 0 ? hi : 4)];
-        }
-        scr[SV + e] = v;
+        M[e] = i == 6 ? rec[LJX + j] : rec[h_off(i < j ? i : j, i < j ? j : i)];
       }
-      if (lane < 6) scr[SVX + lane] = rec[LJX + lane];
+      __syncwarp();
     }
     for (int kn = kend; kn >= k0; --kn) {
       const double* rec = lin + (kn - k0) * kLinStride;
-      const double b21 = rec[LB21];
-      __syncwarp();
-      expand_N(rec, scr + SN, lane, P.dt);
-      __syncwarp();
-      const double* V = scr + SV;
-      const double* Vx = scr + SVX;
-      const double* Nf = scr + SN;
-      // pass 1: W = V A (36), BtV (12), Qx (6), Qu (2)
+      // ---- S1: G = M F
       {
-        const int i = lane / 6, cc = lane % 6;  // lanes 0..31 -> W entries 0..31
-        double w = V[lane];
+        double f[6];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) w = fma(V[i * 6 + r], Nf[r * 6 + cc], w);
-        scr[SW + lane] = w;
+        for (int r = 0; r < 6; ++r) f[r] = rec[fo1[r]];
+        const double* m1 = M + s1i * 6;
+        double g1 = m1[0] * f[0];
+#pragma unroll
+        for (int r = 1; r < 6; ++r) g1 = fma(m1[r], f[r], g1);
+        G[s1i * 8 + s1c] = g1;
+        if (lane < 24) {
+          const double* m2 = M + (4 + s1i) * 6;
+          double g2 = m2[0] * f[0];
+#pragma unroll
+          for (int r = 1; r < 6; ++r) g2 = fma(m2[r], f[r], g2);
+          G[(4 + s1i) * 8 + s1c] = g2;
+        }
+      }
+      __syncwarp();
+      // ---- S2: Qh = Hh + F^T G[0:6], ql = Jh + G[6]
+      {
+        double q = rec[hoA];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) q = fma(rec[fo2A[r]], G[r * 8 + qA], q);
+        Qh[pA * 8 + qA] = q;
+        Qh[qA * 8 + pA] = q;
         if (lane < 4) {
-          const int e = 32 + lane;
-          double w2 = V[e];
+          double q2 = rec[hoB];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) w2 = fma(V[30 + r], Nf[r * 6 + (e - 30)], w2);
-          scr[SW + e] = w2;
-        } else if (lane < 16) {
-          const int e = lane - 4, rr = e / 6, j = e % 6;
-          scr[SBV + e] = rr == 0 ? fma(B40, V[24 + j], B30 * V[18 + j]) : fma(B51, V[30 + j], b21 * V[12 + j]);
-        } else if (lane < 22) {
-          const int r = lane - 16;
-          double q = rec[LJX + r] + Vx[r];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) q = fma(Nf[i2 * 6 + r], Vx[i2], q);
-          scr[SQX + r] = q;
-        } else if (lane < 24) {
-          scr[SQU + lane - 22] = lane == 22 ? rec[LJU] + fma(B40, Vx[4], B30 * Vx[3])
-                                            : rec[LJU + 1] + fma(B51, Vx[5], b21 * Vx[2]);
+          for (int r = 0; r < 6; ++r) q2 = fma(rec[fo2B[r]], G[r * 8 + qB], q2);
+          Qh[pB * 8 + qB] = q2;
+          Qh[qB * 8 + pB] = q2;
+        } else if (lane < 12) {
+          ql[qL] = rec[joL] + G[6 * 8 + qL];
         }
       }
       __syncwarp();
-      // pass 2: Qxx upper (21 lanes), Qux (12: lanes 21..31 + lane 0 again), Quu (lanes 1..4)
-      {
-        const double* W = scr + SW;
-        const double* BV = scr + SBV;
-        if (lane < 21) {
-          double hx = 0.0;
-          if (ui == uj) hx = ui < 3 ? rec[LHX + (ui == 0 ? 0 : ui == 1 ? 3 : 5)] : rec[LHX + 6 + ui - 3];
-          else if (uj < 3) hx = rec[LHX + (ui == 0 ? uj : 4)];
-          double q = hx + W[ui * 6 + uj];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) q = fma(Nf[i2 * 6 + ui], W[i2 * 6 + uj], q);
-          scr[SQXX + ui * 6 + uj] = q;
-          scr[SQXX + uj * 6 + ui] = q;
-        } else {
-          const int e = lane - 21, rr = e / 6, cc = e % 6;  // Qux entries 0..10
-          double q = BV[e];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) q = fma(BV[rr * 6 + r], Nf[r * 6 + cc], q);
-          scr[SQUX + e] = q;
-        }
-        if (lane == 0) {
-          double q = BV[11];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) q = fma(BV[6 + r], Nf[r * 6 + 5], q);
-          scr[SQUX + 11] = q;
-        } else if (lane < 5) {
-          const int e = lane - 1, ra = e / 2, cb = e % 2;
-          const double hu = ra == cb ? rec[LHU + ra] : 0.0;
-          scr[SQUU + e] = hu + (cb == 0 ? fma(BV[ra * 6 + 4], B40, BV[ra * 6 + 3] * B30)
-                                        : fma(BV[ra * 6 + 5], B51, BV[ra * 6 + 2] * b21));
-        }
-      }
-      __syncwarp();
-      // pass 3: K = -(Quu + lambda I)^-1 Qux, k = -(Quu + lambda I)^-1 Qu   (:361-366)
-      const double q00 = scr[SQUU + 0], q01 = scr[SQUU + 1], q10 = scr[SQUU + 2], q11 = scr[SQUU + 3];
-      {
+      // ---- S3: Kh = -(Quu + lambda I)^-1 [Qux | Qu]   (closed-form 2x2 inverse, :361-366)
+      const double q00 = Qh[6 * 8 + 6], q01 = Qh[6 * 8 + 7], q11 = Qh[7 * 8 + 7];
+      if (lane < 14) {
         const double t00 = q00 + lambda, t11 = q11 + lambda;
-        const double det = t00 * t11 - q10 * q01;
+        const double det = t00 * t11 - q01 * q01;
         const double invdet = 1.0 / det;
-        const double i00 = t11 * invdet, i01 = -q01 * invdet, i10 = -q10 * invdet, i11 = t00 * invdet;
-        if (lane < 12) {
-          const int rr = lane / 6, cc = lane % 6;
-          const double n0 = rr == 0 ? -i00 : -i10, n1 = rr == 0 ? -i01 : -i11;
-          Kg[kn * 12 + lane] = fma(n1, scr[SQUX + 6 + cc], n0 * scr[SQUX + cc]);
-        } else if (lane < 14) {
-          const int rr = lane - 12;
-          const double n0 = rr == 0 ? -i00 : -i10, n1 = rr == 0 ? -i01 : -i11;
-          kg[kn * 2 + rr] = fma(n1, scr[SQU + 1], n0 * scr[SQU + 0]);
+        const int rr = lane / 7, j = lane - rr * 7;
+        const double n0 = rr == 0 ? -(t11 * invdet) : q01 * invdet;   // -inv[rr][0]
+        const double n1 = rr == 0 ? q01 * invdet : -(t00 * invdet);   // -inv[rr][1]
+        const double b0 = j < 6 ? Qh[j * 8 + 6] : ql[6];
+        const double b1 = j < 6 ? Qh[j * 8 + 7] : ql[7];
+        const double kv = fma(n1, b1, n0 * b0);
+        Kh[lane] = kv;
+        if (j < 6) Kg[kn * 12 + rr * 6 + j] = kv;
+        else kg[kn * 2 + rr] = kv;
+      }
+      __syncwarp();
+      // ---- S4: M' and the delta_V contributions
+      if (lane < 27) {
+        const double ki0 = Kh[vi], ki1 = Kh[7 + vi], kj0 = Kh[vj], kj1 = Kh[7 + vj];
+        const double ui0 = Qh[vi * 8 + 6], ui1 = Qh[vi * 8 + 7];             // Qux[a][vi]
+        const double uj0 = vj < 6 ? Qh[vj * 8 + 6] : ql[6];                  // Qux[a][vj] or Qu[a]
+        const double uj1 = vj < 6 ? Qh[vj * 8 + 7] : ql[7];
+        const double t0 = fma(q01, kj1, fma(q00, kj0, uj0));                 // T[0][vj]
+        const double t1 = fma(q11, kj1, fma(q01, kj0, uj1));                 // T[1][vj]
+        double v = vj < 6 ? Qh[vi * 8 + vj] : ql[vi];
+        v += fma(ki1, t1, ki0 * t0);
+        v += fma(ui1, kj1, ui0 * kj0);
+        const double k0v = Kh[6], k1v = Kh[13];
+        const double yi = (yki == 0 ? k0v : k1v) * rec[yoi];
+        if (vj < 6) {
+          M[vi * 6 + vj] = v;
+          M[vj * 6 + vi] = v;
+          const double yj = (ykj == 0 ? k0v : k1v) * rec[yoj];
+          acc1 = fma(wsym * yi, v * yj, acc1);
+        } else {
+          M[36 + vi] = v;
+          acc0 = fma(yi, v, acc0);
         }
+      } else if (lane == 27) {
+        const double k0v = Kh[6], k1v = Kh[13];
+        acc0 += fma(k1v, rec[LJU + 1], k0v * rec[LJU]);
+        acc1 += 0.5 * fma(k1v * k1v, rec[LHU + 1], (k0v * k0v) * rec[LHU]);
       }
       __syncwarp();
-      const double* Kk = Kg + kn * 12;
-      const double kk0 = kg[kn * 2], kk1 = kg[kn * 2 + 1];
-      // pass 4: T = Quu K + Qux (12), Vx' (6)   (:379, un-regularised Quu)
-      {
-        if (lane < 12) {
-          const int rr = lane / 6, cc = lane % 6;
-          const double qa = rr == 0 ? q00 : q10, qb = rr == 0 ? q01 : q11;
-          scr[ST + lane] = fma(qb, Kk[6 + cc], fma(qa, Kk[cc], scr[SQUX + lane]));
-        } else if (lane < 18) {
-          const int i = lane - 12;
-          const double qk0 = fma(q01, kk1, q00 * kk0), qk1 = fma(q11, kk1, q10 * kk0);
-          double vx = scr[SQX + i];
-          vx += fma(Kk[6 + i], qk1, Kk[i] * qk0);
-          vx += fma(Kk[6 + i], scr[SQU + 1], Kk[i] * scr[SQU + 0]);
-          vx += fma(scr[SQUX + 6 + i], kk1, scr[SQUX + i] * kk0);
-          scr[SVX + i] = vx;
-        }
-      }
-      __syncwarp();
-      // pass 5: Vxx' = Qxx + K^T T + Qux^T K, symmetrised   (:380-381)
-      if (lane < 21) {
-        const double* T = scr + ST;
-        const double* Qux = scr + SQUX;
-        double vij = scr[SQXX + ui * 6 + uj];
-        vij += fma(Kk[6 + ui], T[6 + uj], Kk[ui] * T[uj]);
-        vij += fma(Qux[6 + ui], Kk[6 + uj], Qux[ui] * Kk[uj]);
-        double vji = scr[SQXX + ui * 6 + uj];
-        vji += fma(Kk[6 + uj], T[6 + ui], Kk[uj] * T[ui]);
-        vji += fma(Qux[6 + uj], Kk[6 + ui], Qux[uj] * Kk[ui]);
-        const double s = 0.5 * (vij + vji);
-        scr[SV + ui * 6 + uj] = s;
-        scr[SV + uj * 6 + ui] = s;
-      }
-      __syncwarp();
-      // :383-384 -- lazy Qu / Quu are evaluated with the UPDATED Vx / Vxx (quirk Q21)
-      {
-        const double* Vn = scr + SV;
-        const double* Vxn = scr + SVX;
-        const double qu0 = rec[LJU] + fma(B40, Vxn[4], B30 * Vxn[3]);
-        const double qu1 = rec[LJU + 1] + fma(B51, Vxn[5], b21 * Vxn[2]);
-        const double bv0_2 = fma(B40, Vn[24 + 2], B30 * Vn[18 + 2]), bv0_3 = fma(B40, Vn[24 + 3], B30 * Vn[18 + 3]);
-        const double bv0_4 = fma(B40, Vn[24 + 4], B30 * Vn[18 + 4]), bv0_5 = fma(B40, Vn[24 + 5], B30 * Vn[18 + 5]);
-        const double bv1_2 = fma(B51, Vn[30 + 2], b21 * Vn[12 + 2]), bv1_3 = fma(B51, Vn[30 + 3], b21 * Vn[12 + 3]);
-        const double bv1_4 = fma(B51, Vn[30 + 4], b21 * Vn[12 + 4]), bv1_5 = fma(B51, Vn[30 + 5], b21 * Vn[12 + 5]);
-        const double n00 = rec[LHU] + fma(bv0_4, B40, bv0_3 * B30);
-        const double n01 = fma(bv0_5, B51, bv0_2 * b21);
-        const double n10 = fma(bv1_4, B40, bv1_3 * B30);
-        const double n11 = rec[LHU + 1] + fma(bv1_5, B51, bv1_2 * b21);
-        dv0 += fma(kk1, qu1, kk0 * qu0);
-        const double h0 = 0.5 * kk0, h1 = 0.5 * kk1;
-        const double r0 = fma(h1, n10, h0 * n00), r1 = fma(h1, n11, h0 * n01);
-        dv1 += fma(r1, kk1, r0 * kk0);
-      }
     }
   }
-  __syncwarp();
-  dV[0] = dv0;
-  dV[1] = dv1;
+  dV[0] = warp_sum(acc0);
+  dV[1] = warp_sum(acc1);
 }
 
-// ilqr_optimizer.cc:392-415.  Every lane carries the same state (uniform work), lane 0 stores.
-__device__ void forward_pass(const Ctx& c, double alpha, const double* Xs, const double* Us, double* Xn,
-                             double* Un) {
+// ilqr_optimizer.cc:392-415 for several step sizes of the line search at once: lane a with bit a of
+// `want` set rolls out alpha_a and writes its candidate to the global workspace (the other lanes
+// shadow the highest wanted lane and store nothing).
+//  * A lane whose state stops being finite is RETIRED: every later state of that rollout would be
+//    non-finite too, its cost NaN/inf, and the reference rejects such a step (the comparisons of
+//    ilqr_optimizer.cc:258 are false).
+//  * kFastOnly: a lane that would need the general (fmod) branch of NormalizeAngle -- a blown-up
+//    rollout -- is DEFERRED instead of dragging the whole warp through that branch at every step;
+//    the caller repeats deferred step sizes with kFastOnly = false only if the line search gets to them.
+// Returns retired | deferred << 16.
+template <bool kFastOnly>
+__device__ unsigned forward_all(const Ctx& c, const double* Xs, const double* Us, unsigned want) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const double* Kg = c.sm + a.sm.Kg;
   const double* kg = c.sm + a.sm.kg;
+  const bool owner = (want >> c.lane) & 1u;
+  const int slot = owner ? c.lane : 31 - __clz(want);
+  const double alpha = kAlphaList[slot];
+  double* out = c.cand + (size_t)slot * 8 * a.Kc;
   double x[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) x[i] = c.g0[i];
-  if (c.lane < 6) Xn[c.lane] = c.g0[c.lane];
+  if (owner) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i * a.Kc] = x[i];
+  }
+  bool dead = false, defer = false, slow = false;
   for (int k = 0; k < a.N; ++k) {
     const double* Kk = Kg + k * 12;
     const double* xb = Xs + k * 6;
@@ -716,16 +819,30 @@ __device__ void forward_pass(const Ctx& c, double alpha, const double* Xs, const
       s1 = fma(Kk[6 + i], dx[i], s1);
     }
     const double u0 = Us[k * 2] + s0 + alpha * kg[k * 2];
-    const double u1 = normalize_angle(Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1]);
-    dynamics_step(P, x, u0, u1);
-    if (c.lane == 0) {
-      Un[k * 2] = u0;
-      Un[k * 2 + 1] = u1;
+    const double u1r = Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1];
+    const double u1 = kFastOnly ? normalize_angle_fast(u1r, slow) : normalize_angle(u1r);
+    dynamics_step_t<kFastOnly>(P, x, u0, u1, slow);
+    if (!dead && !defer) {
+      const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
+      if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
+      else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
+    }
+    if (dead || defer) {
+      // park the lane on the nominal trajectory: benign operands for the remaining steps
 #pragma unroll
-      for (int i = 0; i < 6; ++i) Xn[(k + 1) * 6 + i] = x[i];
+      for (int i = 0; i < 6; ++i) x[i] = Xs[(k + 1) * 6 + i];
+      slow = false;
+    } else if (owner) {
+      out[6 * a.Kc + k] = u0;
+      out[7 * a.Kc + k] = u1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
     }
   }
   __syncwarp();
+  const unsigned retired = __ballot_sync(kFull, dead) & want;
+  const unsigned deferred = __ballot_sync(kFull, defer) & want;
+  return retired | (deferred << 16);
 }
 
 // ilqr_optimizer.cc:793-842
@@ -884,7 +1001,8 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
   const int N = a.N, K = N + 1;
   Ctx c(a, smem);
   c.lane = lane;
-  c.ws = a.ws + (size_t)blockIdx.x * a.M_max * 3 * a.Kp;
+  c.ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
+  c.cand = c.ws + (size_t)a.M_max * 3 * a.Kp;
   double* seg = smem + a.sm.seg;
   unsigned char* nidx_base = reinterpret_cast<unsigned char*>(smem + a.sm.nidx);
   const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
@@ -959,12 +1077,45 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
       }
     }
     __syncwarp();
+    {
+      // bounding circles of the segment groups (see eval_cost)
+      double offmax = 0.0;
+#pragma unroll
+      for (int d = 0; d < kDisc; ++d) offmax = fmax(offmax, fabs(P.off[d]));
+      const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
+      double* grp = smem + a.sm.grp;
+      for (int g = lane; g < ngl + ngr; g += 32) {
+        const int side = g < ngl ? 0 : 1;
+        const int S = side == 0 ? a.S_left : a.S_right;
+        const int s_lo = (side == 0 ? g : g - ngl) * kGroup;
+        const int s_hi = s_lo + kGroup < S ? s_lo + kGroup : S;
+        const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+        double xmin = 1.7976931348623157e308, xmax = -xmin, ymin = xmin, ymax = -xmin;
+        for (int s2 = s_lo; s2 < s_hi; ++s2) {
+          const double* sg = sg0 + s2 * kSegStride;
+          xmin = fmin(xmin, fmin(sg[0], sg[2]));
+          xmax = fmax(xmax, fmax(sg[0], sg[2]));
+          ymin = fmin(ymin, fmin(sg[1], sg[3]));
+          ymax = fmax(ymax, fmax(sg[1], sg[3]));
+        }
+        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+        double r2 = 0.0;
+        for (int s2 = s_lo; s2 < s_hi; ++s2) {
+          const double* sg = sg0 + s2 * kSegStride;
+          const double ax = sg[0] - cx, ay = sg[1] - cy, bx = sg[2] - cx, by = sg[3] - cy;
+          r2 = fmax(r2, fmax(ax * ax + ay * ay, bx * bx + by * by));
+        }
+        grp[g * 3] = cx;
+        grp[g * 3 + 1] = cy;
+        // radius + largest disc offset, inflated so that rounding can only make the test more conservative
+        grp[g * 3 + 2] = (sqrt(r2) + offmax) * (1.0 + 1e-9) + 1e-9;
+      }
+    }
+    __syncwarp();
     __threadfence_block();
 
     double* X = smem + a.sm.X;
     double* U = smem + a.sm.U;
-    double* Xc = smem + a.sm.Xc;
-    double* Uc = smem + a.sm.Uc;
     unsigned char* nidx = nidx_base;
     unsigned char* nidx_c = nidx_base + a.sm.nidx_bytes;
 
@@ -973,7 +1124,9 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
     if (a.init_states) copy_out(a.init_states + (size_t)b * K * 6, X, K * 6, lane);
     if (a.init_controls) copy_out(a.init_controls + (size_t)b * N * 2, U, N * 2, lane);
     double cost_acc[5], cost_new5[5];
-    eval_cost(c, X, U, nidx, cost_acc);
+    for (int i = lane; i < a.sm.nidx_bytes; i += 32) nidx[i] = 0;  // no previous iterate: any valid index is a bound
+    __syncwarp();
+    eval_cost<false>(c, X, U, nidx, nidx, cost_acc);
     __syncwarp();
     double cost_old = cost_acc[0];
     int n_cost = 0, n_iter_traj = 0;
@@ -1033,17 +1186,31 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
           break;
         }
       }
-      // line search (:246-265)
+      // line search (:246-265): all candidates in one rollout, then costs in the reference's order
       bool done = false;
       int alpha_idx = kNAlpha;
+      unsigned fw = forward_all<true>(c, X, U, (1u << kNAlpha) - 1u);
+      unsigned retired = fw & 0xffffu, deferred = fw >> 16;
+      __threadfence_block();
       for (int ai = 0; ai < kNAlpha; ++ai) {
+        if ((deferred >> ai) & 1u) {
+          // the search reached a step size whose rollout needs the general NormalizeAngle branch:
+          // repeat all deferred ones faithfully (one extra pass, lanes = deferred step sizes)
+          fw = forward_all<false>(c, X, U, deferred);
+          retired |= fw & 0xffffu;
+          deferred = 0;
+          __threadfence_block();
+        }
+        if ((retired >> ai) & 1u) continue;  // non-finite rollout: rejected (see forward_all)
         const double alpha = kAlphaList[ai];
-        forward_pass(c, alpha, X, U, Xc, Uc);
-        eval_cost(c, Xc, Uc, nidx_c, cost_new5);
+        const double* cd = c.cand + (size_t)ai * 8 * a.Kc;
+        eval_cost<true>(c, cd, nullptr, nidx, nidx_c, cost_new5);
         __syncwarp();
         if (dbg && iter == 0 && ai == 0) {
-          if (dbg->Xn) copy_out(dbg->Xn + (size_t)b * K * 6, Xc, K * 6, lane);
-          if (dbg->Un) copy_out(dbg->Un + (size_t)b * N * 2, Uc, N * 2, lane);
+          for (int k = lane; k < K; k += 32) {
+            if (dbg->Xn) for (int i = 0; i < 6; ++i) dbg->Xn[((size_t)b * K + k) * 6 + i] = cd[i * a.Kc + k];
+            if (dbg->Un && k < N) for (int i = 0; i < 2; ++i) dbg->Un[((size_t)b * N + k) * 2 + i] = cd[(6 + i) * a.Kc + k];
+          }
           if (dbg->costn && lane == 0) for (int i = 0; i < 5; ++i) dbg->costn[(size_t)b * 5 + i] = cost_new5[i];
         }
         dcost = cost_old - cost_new5[0];
@@ -1061,9 +1228,19 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         break;
       }
       if (done) {
-        // accept: the candidate becomes the iterate (pointer swap instead of the reference's copies)
-        double* tx = X; X = Xc; Xc = tx;
-        double* tu = U; U = Uc; Uc = tu;
+        // accept: the candidate becomes the iterate (workspace -> shared memory)
+        {
+          const double* cd = c.cand + (size_t)alpha_idx * 8 * a.Kc;
+          for (int k = lane; k < K; k += 32) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) X[k * 6 + i] = cd[i * a.Kc + k];
+            if (k < N) {
+              U[k * 2] = cd[6 * a.Kc + k];
+              U[k * 2 + 1] = cd[7 * a.Kc + k];
+            }
+          }
+          __syncwarp();
+        }
         unsigned char* tn = nidx; nidx = nidx_c; nidx_c = tn;
         dlambda = fmin(dlambda / reg_ratio, 1.0 / reg_ratio);
         lambda = lambda * dlambda * (lambda > reg_min ? 1.0 : 0.0);

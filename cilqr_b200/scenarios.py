@@ -332,7 +332,7 @@ def _gen_chunk(seed: int, chunk: int, n: int, N: int, n_obs: int, M_max: int, S:
         best_dy = np.where(better, ky, best_dy)
     dist = np.sqrt(best_d2)
     in_range = (np.abs(best_dx) <= _MAX_DIFF) & (np.abs(best_dy) <= _MAX_DIFF) & (dist > 1e-9)
-    n_plane_obs = M_max - 4
+    n_plane_obs = min(M_max - 4, n_obs)
     order = np.argsort(np.where(in_range, dist, np.inf), axis=1, kind="stable")[:, :n_plane_obs]  # [n,P,K]
     sel_ok = np.take_along_axis(in_range, order, axis=1)
     sel_d = np.take_along_axis(dist, order, axis=1)
@@ -354,7 +354,7 @@ def _gen_chunk(seed: int, chunk: int, n: int, N: int, n_obs: int, M_max: int, S:
         corridor[:, :, f, 2] = 2 * _BOX_HALF * (bx * px + by * py + _BOX_HALF)
     obs_planes = np.stack([nxn * edge, nyn * edge, c_pl * edge], axis=-1)  # [n,P,K,3]
     obs_planes = np.where(sel_ok[..., None], obs_planes, 0.0)
-    corridor[:, :, 4:, :] = np.transpose(obs_planes, (0, 2, 1, 3))
+    corridor[:, :, 4:4 + n_plane_obs, :] = np.transpose(obs_planes, (0, 2, 1, 3))
     corridor_cnt = (4 + cnt_obs).astype(np.int32)
 
     # ---- lanes: window of S segments per side starting ~15 m behind the ego
