@@ -111,87 +111,76 @@ __device__ __forceinline__ double warp_sum(double v) {
   return __shfl_sync(kFull, v, 0);
 }
 
-// math_utils.cpp:53-59.  fmod(a + pi, 2pi) == a + pi exactly whenever 0 <= a + pi < 2pi, which
-// is the only case the solver produces in practice; the general path is kept for parity.
-__device__ __forceinline__ double normalize_angle(double angle) {
+// ---- out-of-line math: ONE copy of each double-precision libdevice routine in the kernel.
+// Inlined at every call site they made the kernel ~300 KB of SASS, which thrashed the instruction
+// cache (ncu: stall_no_instruction 5.4 cycles per issued instruction); see DESIGN.md.
+__device__ __noinline__ double nt_tan(double x) { return tan(x); }
+__device__ __noinline__ double nt_log(double x) { return log(x); }
+__device__ __noinline__ double nt_hypot(double x, double y) { return hypot(x, y); }
+__device__ __noinline__ double2 nt_sincos(double x) {
+  double s, c;
+  sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+// general branch of NormalizeAngle (math_utils.cpp:53-59) on a = angle + pi
+__device__ __noinline__ double nt_wrap_general(double a) {
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  a = fmod(a, kTwoPi);
+  if (a < 0.0) a += kTwoPi;
+  return a;
+}
+
+// math_utils.cpp:53-59.  fmod(a + pi, 2pi) == a + pi exactly whenever 0 <= a + pi < 2pi, which is
+// the only case a sane rollout produces.  allow_general = false: never enter the fmod branch; `slow`
+// reports that it was needed (the caller then discards the rollout and repeats it faithfully).
+__device__ __forceinline__ double wrap_angle(double angle, bool allow_general, bool& slow) {
   const double kPi = 3.14159265358979323846;
   const double kTwoPi = 2.0 * 3.14159265358979323846;
   double a = angle + kPi;
   if (!(a >= 0.0 && a < kTwoPi)) {
-    a = fmod(a, kTwoPi);
-    if (a < 0.0) a += kTwoPi;
+    if (allow_general) a = nt_wrap_general(a);
+    else slow = true;
   }
   return a - kPi;
 }
-
-// Fast branch of normalize_angle only; sets `slow` when the argument needs the general branch.
-__device__ __forceinline__ double normalize_angle_fast(double angle, bool& slow) {
-  const double kPi = 3.14159265358979323846;
-  const double kTwoPi = 2.0 * 3.14159265358979323846;
-  const double a = angle + kPi;
-  slow = slow || !(a >= 0.0 && a < kTwoPi);
-  return a - kPi;
+__device__ __forceinline__ double normalize_angle(double angle) {
+  bool unused = false;
+  return wrap_angle(angle, true, unused);
 }
 
 // vehicle_model.cc:88-138: midpoint RK2, same control at both stages, wrap theta and delta.
-// kFastOnly: never enter the fmod branch of NormalizeAngle; `slow` reports that it was needed
-// (the caller then discards this rollout and repeats it with kFastOnly = false).
-template <bool kFastOnly>
-__device__ __forceinline__ void dynamics_step_t(const DevParams& P, double* x, double u0, double u1, bool& slow) {
-  auto na = [&](double v) { return kFastOnly ? normalize_angle_fast(v, slow) : normalize_angle(v); };
-  double s2, c2;
-  const double de = na(x[5]);
-  const double k1t = x[3] * tan(de) / P.L;  // theta enters k1 only through k1x, k1y, which the midpoint step never uses
+// (theta enters k1 only through k1x, k1y, which the midpoint step never uses.)
+__device__ __forceinline__ void rollout_step(const DevParams& P, double* x, double u0, double u1, bool allow_general,
+                                             bool& slow) {
+  const double de = wrap_angle(x[5], allow_general, slow);
+  const double k1t = x[3] * nt_tan(de) / P.L;
   const double h = 0.5 * P.dt;
   const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
-  const double thm = na(m2);
-  const double dem = na(m5);
-  sincos(thm, &s2, &c2);
-  const double k2x = m3 * c2, k2y = m3 * s2, k2t = m3 * tan(dem) / P.L;
+  const double thm = wrap_angle(m2, allow_general, slow);
+  const double dem = wrap_angle(m5, allow_general, slow);
+  const double2 sc = nt_sincos(thm);
+  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * nt_tan(dem) / P.L;
   x[0] = x[0] + P.dt * k2x;
   x[1] = x[1] + P.dt * k2y;
-  x[2] = na(x[2] + P.dt * k2t);
+  x[2] = wrap_angle(x[2] + P.dt * k2t, allow_general, slow);
   x[3] = x[3] + P.dt * m4;
   x[4] = x[4] + P.dt * u0;
-  x[5] = na(x[5] + P.dt * u1);
-}
-
-__device__ __forceinline__ void dynamics_step(const DevParams& P, double* x, double u0, double u1) {
-  double s1, c1;
-  const double th = normalize_angle(x[2]);
-  const double de = normalize_angle(x[5]);
-  sincos(th, &s1, &c1);
-  const double k1x = x[3] * c1, k1y = x[3] * s1, k1t = x[3] * tan(de) / P.L;
-  const double h = 0.5 * P.dt;
-  const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
-  double s2, c2;
-  const double thm = normalize_angle(m2);
-  const double dem = normalize_angle(m5);
-  sincos(thm, &s2, &c2);
-  const double k2x = m3 * c2, k2y = m3 * s2, k2t = m3 * tan(dem) / P.L;
-  x[0] = x[0] + P.dt * k2x;
-  x[1] = x[1] + P.dt * k2y;
-  x[2] = normalize_angle(x[2] + P.dt * k2t);
-  x[3] = x[3] + P.dt * m4;
-  x[4] = x[4] + P.dt * u0;
-  x[5] = normalize_angle(x[5] + P.dt * u1);
-  (void)k1x;
-  (void)k1y;
+  x[5] = wrap_angle(x[5] + P.dt * u1, allow_general, slow);
 }
 
 // vehicle_model.cc:21-86.  Writes the 11 state-dependent entries of A and B(2,1).
-__device__ __forceinline__ void dynamics_jacobian(const DevParams& P, const double* x, double u1,
-                                                  double* A11, double* b21) {
+__device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double* x, double u1,
+                                               double* A11, double* b21) {
   const double L = P.L, dt = P.dt;
   const double v = x[3];
   const double theta = normalize_angle(x[2]);
   const double delta = normalize_angle(x[5]);
   const double a = x[4];
-  const double tan_delta = tan(delta);
+  const double tan_delta = nt_tan(delta);
   const double theta_mid = theta + 0.5 * dt * v * tan_delta / L;
-  const double tan_dr = tan(delta + 0.5 * dt * u1);
-  double sm, cm;
-  sincos(theta_mid, &sm, &cm);
+  const double tan_dr = nt_tan(delta + 0.5 * dt * u1);
+  const double2 scm = nt_sincos(theta_mid);
+  const double sm = scm.x, cm = scm.y;
   const double td2 = tan_delta * tan_delta;
   const double tr2 = tan_dr * tan_dr;
   const double vm = 0.5 * a * dt + v;
@@ -220,7 +209,7 @@ __device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P)
   a.quad += lg ? 0.0 : fma(0.5 * P.rt * q, q, P.relax_c);
 }
 __device__ __forceinline__ double bar_value(const BarAcc& a, const DevParams& P) {
-  return a.quad - P.rt * log(a.prod);
+  return a.quad - P.rt * nt_log(a.prod);
 }
 // barrier_function.h:115-140: coefficient of dx in the Jacobian (cj), of dx dx^T (co) and of ddx (cd)
 __device__ __forceinline__ void bar_coef(double g, const DevParams& P, double& cj, double& co,
@@ -269,8 +258,7 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------
 // TotalCost of (Xs, Us): lane == knot.  Also records the nearest lane segment of every
 // (knot, disc, side) in nidx for the linearisation that follows an accepted step.
-// kCand = false: (Xs, Us) are the shared-memory iterate ([K][6], [N][2]); kCand = true: Xs points
-// at one candidate block of the global workspace ([8][Kc]) and Us is ignored.
+// Xs points at one candidate block of the global workspace ([8][Kc]: x0..x5, u0, u1).
 //
 // Nearest lane segment (FindNeastLaneSegment, ilqr_optimizer.cc:605-618) without scanning all S
 // segments: segments are bundled in groups of kGroup with a bounding circle (centre, radius) built
@@ -279,9 +267,8 @@ struct Ctx {
 // from the rear-axle point than ub + radius + (largest disc offset) cannot contain the minimiser
 // of any disc -- nor tie with it -- and is skipped.  Surviving groups are scanned in index order
 // with the reference's strict '<', so the arg-min (first minimum) is the brute-force one.
-template <bool kCand>
-__device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, const unsigned char* guess,
-                          unsigned char* nidx, double cost5[5]) {
+__device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const unsigned char* guess,
+                                       unsigned char* nidx, double cost5[5]) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
@@ -291,14 +278,8 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, cons
     const int k = k0 + c.lane;
     const bool act = k < K;
     const int kk = act ? k : K - 1;
-    double px, py, th, v, ac, de;
-    if (kCand) {
-      const double* x = Xs + kk;
-      px = x[0], py = x[a.Kc], th = x[2 * a.Kc], v = x[3 * a.Kc], ac = x[4 * a.Kc], de = x[5 * a.Kc];
-    } else {
-      const double* x = Xs + kk * 6;
-      px = x[0], py = x[1], th = x[2], v = x[3], ac = x[4], de = x[5];
-    }
+    const double* xc = Xs + kk;
+    const double px = xc[0], py = xc[a.Kc], th = xc[2 * a.Kc], v = xc[3 * a.Kc], ac = xc[4 * a.Kc], de = xc[5 * a.Kc];
     double tj = 0.0, td = 0.0, tc = 0.0, tl = 0.0;
     {
       const double dx = px - c.goal(kk, 0), dy = py - c.goal(kk, 1), dth = th - c.goal(kk, 2);
@@ -311,8 +292,7 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, cons
       bar_add(bd, de - P.dmax, P);
       bar_add(bd, P.dmin - de, P);
       if (kk < N) {
-        const double u0 = kCand ? Xs[6 * a.Kc + kk] : Us[kk * 2];
-        const double u1 = kCand ? Xs[7 * a.Kc + kk] : Us[kk * 2 + 1];
+        const double u0 = Xs[6 * a.Kc + kk], u1 = Xs[7 * a.Kc + kk];
         tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
         bar_add(bd, u0 - P.jmax, P);
         bar_add(bd, P.jmin - u0, P);
@@ -321,8 +301,8 @@ __device__ void eval_cost(const Ctx& c, const double* Xs, const double* Us, cons
       }
       td = bar_value(bd, P);
     }
-    double sn, cs;
-    sincos(th, &sn, &cs);
+    const double2 scth = nt_sincos(th);
+    const double sn = scth.x, cs = scth.y;
     double xd[kDisc], yd[kDisc];
 #pragma unroll
     for (int d = 0; d < kDisc; ++d) {
@@ -456,8 +436,8 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
   rec[LJU + 1] = 2.0 * P.wdr * u1 + (cj1 - cj0);
   rec[LHU + 1] = 2.0 * P.wdr + (co0 + co1);
 
-  double sn, cs;
-  sincos(x[2], &sn, &cs);
+  const double2 scth = nt_sincos(x[2]);
+  const double sn = scth.x, cs = scth.y;
   double xd[kDisc], yd[kDisc];
 #pragma unroll
   for (int d = 0; d < kDisc; ++d) {
@@ -523,21 +503,6 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
   rec[LHX + 3] = H11;
   rec[LHX + 4] = H12;
   rec[LHX + 5] = H22;
-}
-
-// Sparse structure of A = I + Nf (Nf rows 0..3) and B.  Nf is expanded to a dense 4x6 table in
-// scratch so that the cooperating lanes can index it.
-__device__ __forceinline__ void expand_N(const double* rec, double* Nf, int lane, double dt) {
-  // Nf[r][c]: row0: c2..5 = A02,A03,A04,A05; row1: c2..5 = A12..A15; row2: c3..5 = A23,A24,A25; row3: c4 = dt
-  if (lane < 24) {
-    const int r = lane / 6, cc = lane % 6;
-    double v = 0.0;
-    if (r == 0 && cc >= 2) v = rec[LA + cc - 2];
-    else if (r == 1 && cc >= 2) v = rec[LA + 4 + cc - 2];
-    else if (r == 2 && cc >= 3) v = rec[LA + 8 + cc - 3];
-    else if (r == 3 && cc == 4) v = dt;
-    Nf[lane] = v;
-  }
 }
 
 // scratch map (doubles) used by backward / iqr
@@ -778,18 +743,22 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
   dV[1] = warp_sum(acc1);
 }
 
-// ilqr_optimizer.cc:392-415 for several step sizes of the line search at once: lane a with bit a of
-// `want` set rolls out alpha_a and writes its candidate to the global workspace (the other lanes
-// shadow the highest wanted lane and store nothing).
+// Rollout of the closed loop u_k = ubar_k + K_k (x - xbar_k) + alpha k_k for several step sizes of the
+// line search at once (Forward, ilqr_optimizer.cc:392-415): lane a with bit a of `want` set rolls out
+// alpha_a and writes its candidate to the global workspace (the other lanes shadow the highest
+// wanted lane and store nothing).  The same code produces the LQR initial guess (iqr,
+// ilqr_optimizer.cc:830-841) when called with iqr = true on (xbar, ubar, K, k) = (goals, 0, -K_lqr, 0):
+// the control is then clamped to its bounds instead of angle-wrapped.
 //  * A lane whose state stops being finite is RETIRED: every later state of that rollout would be
 //    non-finite too, its cost NaN/inf, and the reference rejects such a step (the comparisons of
 //    ilqr_optimizer.cc:258 are false).
-//  * kFastOnly: a lane that would need the general (fmod) branch of NormalizeAngle -- a blown-up
-//    rollout -- is DEFERRED instead of dragging the whole warp through that branch at every step;
-//    the caller repeats deferred step sizes with kFastOnly = false only if the line search gets to them.
+//  * allow_general = false: a lane that would need the general (fmod) branch of NormalizeAngle -- a
+//    blown-up rollout -- is DEFERRED instead of dragging the whole warp through that branch at every
+//    step; the caller repeats deferred step sizes with allow_general = true only if the line search
+//    gets to them.
 // Returns retired | deferred << 16.
-template <bool kFastOnly>
-__device__ unsigned forward_all(const Ctx& c, const double* Xs, const double* Us, unsigned want) {
+__device__ __noinline__ unsigned rollout(const Ctx& c, const double* Xs, const double* Us, unsigned want,
+                                         bool allow_general, bool iqr) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const double* Kg = c.sm + a.sm.Kg;
@@ -818,11 +787,16 @@ __device__ unsigned forward_all(const Ctx& c, const double* Xs, const double* Us
       s0 = fma(Kk[i], dx[i], s0);
       s1 = fma(Kk[6 + i], dx[i], s1);
     }
-    const double u0 = Us[k * 2] + s0 + alpha * kg[k * 2];
-    const double u1r = Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1];
-    const double u1 = kFastOnly ? normalize_angle_fast(u1r, slow) : normalize_angle(u1r);
-    dynamics_step_t<kFastOnly>(P, x, u0, u1, slow);
-    if (!dead && !defer) {
+    double u0 = Us[k * 2] + s0 + alpha * kg[k * 2];
+    double u1 = Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1];
+    if (iqr) {
+      u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
+      u1 = fmin(P.drmax, fmax(u1, P.drmin));
+    } else {
+      u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
+    }
+    rollout_step(P, x, u0, u1, allow_general, slow);
+    if (!iqr && !dead && !defer) {
       const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
       if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
       else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
@@ -845,8 +819,25 @@ __device__ unsigned forward_all(const Ctx& c, const double* Xs, const double* Us
   return retired | (deferred << 16);
 }
 
-// ilqr_optimizer.cc:793-842
-__device__ void iqr_guess(const Ctx& c, double* Xs, double* Us) {
+// Candidate `slot` of the workspace becomes the iterate in shared memory.
+__device__ __forceinline__ void adopt(const Ctx& c, int slot, double* X, double* U) {
+  const KernelArgs& a = c.a;
+  const double* cd = c.cand + (size_t)slot * 8 * a.Kc;
+  for (int k = c.lane; k <= a.N; k += 32) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) X[k * 6 + i] = cd[i * a.Kc + k];
+    if (k < a.N) {
+      U[k * 2] = cd[6 * a.Kc + k];
+      U[k * 2 + 1] = cd[7 * a.Kc + k];
+    }
+  }
+  __syncwarp();
+}
+
+// iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control).  Leaves the
+// NEGATED gains -K_k in the gain stage (k_k = 0) and (xbar, ubar) = (goals, 0) in (Xs, Us), so that
+// rollout(..., iqr = true) evaluates u_k = clamp(-K_k (x - goal_k)) and the RK2 rollout of :830-841.
+__device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int N = a.N, lane = c.lane;
@@ -958,38 +949,20 @@ __device__ void iqr_guess(const Ctx& c, double* Xs, double* Us) {
     if (lane < 4) Pm[32 + lane] = pn1;
   }
   __syncwarp();
-  // rollout with clamped feedback
-  double x[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = c.g0[i];
-  if (lane < 6) Xs[lane] = c.g0[lane];
-  for (int k = 0; k < N; ++k) {
-    const double* Kk = Kg + k * 12;
-    double dx[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dx[i] = x[i] - c.goal(k, i);
-    double s0 = -Kk[0] * dx[0], s1 = -Kk[6] * dx[0];
-#pragma unroll
-    for (int i = 1; i < 6; ++i) {
-      s0 = fma(-Kk[i], dx[i], s0);
-      s1 = fma(-Kk[6 + i], dx[i], s1);
-    }
-    const double u0 = fmin(P.jmax, fmax(s0, P.jmin));
-    const double u1 = fmin(P.drmax, fmax(s1, P.drmin));
-    dynamics_step(P, x, u0, u1);
-    if (lane == 0) {
-      Us[k * 2] = u0;
-      Us[k * 2 + 1] = u1;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) Xs[(k + 1) * 6 + i] = x[i];
-    }
+  for (int i = lane; i < N * 12; i += 32) Kg[i] = -Kg[i];
+  double* kg = c.sm + a.sm.kg;
+  for (int i = lane; i < N * 2; i += 32) {
+    kg[i] = 0.0;
+    Us[i] = 0.0;
   }
+  for (int i = lane; i < (N + 1) * 6; i += 32) Xs[i] = c.goal(i / 6, i % 6);
   __syncwarp();
 }
 
 __device__ __forceinline__ unsigned fnv1a(unsigned h, unsigned byte) { return (h ^ (byte & 0xffu)) * 16777619u; }
 
-__device__ __forceinline__ void copy_out(double* dst, const double* src, int n, int lane) {
+__device__ __noinline__ void copy_out(double* dst, const double* src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -1029,13 +1002,14 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
     {
       const double* raw = a.corridor + (size_t)b * K * a.M_max * 3;
       const int total = K * a.M_max;
+#pragma unroll 1
       for (int idx = lane; idx < total; idx += 32) {
         const int k = idx / a.M_max, m = idx - k * a.M_max;
         if (m < c.cnt[k]) {
           const double e0 = raw[idx * 3], e1 = raw[idx * 3 + 1];
           double e2 = raw[idx * 3 + 2];
-          e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / hypot(e0, e1);
-          const double nrm = hypot(hypot(e0, e1), e2);
+          e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+          const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
           c.ws[(m * 3 + 0) * a.Kp + k] = e0 / nrm;
           c.ws[(m * 3 + 1) * a.Kp + k] = e1 / nrm;
           c.ws[(m * 3 + 2) * a.Kp + k] = e2 / nrm;
@@ -1048,16 +1022,17 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         }
       }
       const int ST_ = a.S_left + a.S_right;
+#pragma unroll 1
       for (int s = lane; s < ST_; s += 32) {
         const double* ln = s < a.S_left ? a.lane_left + ((size_t)b * a.S_left + s) * 7
                                         : a.lane_right + ((size_t)b * a.S_right + (s - a.S_left)) * 7;
         const double e0 = ln[0], e1 = ln[1];
         double e2 = ln[2];
-        e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / hypot(e0, e1);
-        const double nrm = hypot(hypot(e0, e1), e2);
+        e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+        const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
         double* sg = seg + s * kSegStride;
         const double dx = ln[5] - ln[3], dy = ln[6] - ln[4];
-        const double len = hypot(dx, dy);
+        const double len = nt_hypot(dx, dy);
         sg[0] = ln[3];
         sg[1] = ln[4];
         sg[2] = ln[5];
@@ -1084,6 +1059,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
       for (int d = 0; d < kDisc; ++d) offmax = fmax(offmax, fabs(P.off[d]));
       const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
       double* grp = smem + a.sm.grp;
+#pragma unroll 1
       for (int g = lane; g < ngl + ngr; g += 32) {
         const int side = g < ngl ? 0 : 1;
         const int S = side == 0 ? a.S_left : a.S_right;
@@ -1091,6 +1067,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         const int s_hi = s_lo + kGroup < S ? s_lo + kGroup : S;
         const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
         double xmin = 1.7976931348623157e308, xmax = -xmin, ymin = xmin, ymax = -xmin;
+#pragma unroll 1
         for (int s2 = s_lo; s2 < s_hi; ++s2) {
           const double* sg = sg0 + s2 * kSegStride;
           xmin = fmin(xmin, fmin(sg[0], sg[2]));
@@ -1100,6 +1077,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         }
         const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
         double r2 = 0.0;
+#pragma unroll 1
         for (int s2 = s_lo; s2 < s_hi; ++s2) {
           const double* sg = sg0 + s2 * kSegStride;
           const double ax = sg[0] - cx, ay = sg[1] - cy, bx = sg[2] - cx, by = sg[3] - cy;
@@ -1120,13 +1098,17 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
     unsigned char* nidx_c = nidx_base + a.sm.nidx_bytes;
 
     // ---- initial guess (:169) and its cost (:172)
-    iqr_guess(c, X, U);
+    iqr_gains(c, X, U);
+    rollout(c, X, U, 1u, true, true);
+    __threadfence_block();
+    adopt(c, 0, X, U);
     if (a.init_states) copy_out(a.init_states + (size_t)b * K * 6, X, K * 6, lane);
     if (a.init_controls) copy_out(a.init_controls + (size_t)b * N * 2, U, N * 2, lane);
     double cost_acc[5], cost_new5[5];
+#pragma unroll 1
     for (int i = lane; i < a.sm.nidx_bytes; i += 32) nidx[i] = 0;  // no previous iterate: any valid index is a bound
     __syncwarp();
-    eval_cost<false>(c, X, U, nidx, nidx, cost_acc);
+    eval_cost(c, c.cand, nidx, nidx, cost_acc);
     __syncwarp();
     double cost_old = cost_acc[0];
     int n_cost = 0, n_iter_traj = 0;
@@ -1149,7 +1131,9 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         if (dbg->X0) copy_out(dbg->X0 + (size_t)b * K * 6, X, K * 6, lane);
         if (dbg->U0) copy_out(dbg->U0 + (size_t)b * N * 2, U, N * 2, lane);
         if (dbg->cost0 && lane < 5) dbg->cost0[(size_t)b * 5 + lane] = t5[lane];
-        if (dbg->nearest) for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nidx[i];
+        if (dbg->nearest)
+#pragma unroll 1
+          for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nidx[i];
       }
       __syncwarp();
     }
@@ -1175,6 +1159,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
       {
         const double* kgp = smem + a.sm.kg;
         double acc = 0.0;
+#pragma unroll 1
         for (int k = lane; k < N; k += 32) {
           const double v0 = fabs(kgp[k * 2]) / (fabs(U[k * 2]) + 1.0);
           const double v1 = fabs(kgp[k * 2 + 1]) / (fabs(U[k * 2 + 1]) + 1.0);
@@ -1189,14 +1174,14 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
       // line search (:246-265): all candidates in one rollout, then costs in the reference's order
       bool done = false;
       int alpha_idx = kNAlpha;
-      unsigned fw = forward_all<true>(c, X, U, (1u << kNAlpha) - 1u);
+      unsigned fw = rollout(c, X, U, (1u << kNAlpha) - 1u, false, false);
       unsigned retired = fw & 0xffffu, deferred = fw >> 16;
       __threadfence_block();
       for (int ai = 0; ai < kNAlpha; ++ai) {
         if ((deferred >> ai) & 1u) {
           // the search reached a step size whose rollout needs the general NormalizeAngle branch:
           // repeat all deferred ones faithfully (one extra pass, lanes = deferred step sizes)
-          fw = forward_all<false>(c, X, U, deferred);
+          fw = rollout(c, X, U, deferred, true, false);
           retired |= fw & 0xffffu;
           deferred = 0;
           __threadfence_block();
@@ -1204,7 +1189,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         if ((retired >> ai) & 1u) continue;  // non-finite rollout: rejected (see forward_all)
         const double alpha = kAlphaList[ai];
         const double* cd = c.cand + (size_t)ai * 8 * a.Kc;
-        eval_cost<true>(c, cd, nullptr, nidx, nidx_c, cost_new5);
+        eval_cost(c, cd, nidx, nidx_c, cost_new5);
         __syncwarp();
         if (dbg && iter == 0 && ai == 0) {
           for (int k = lane; k < K; k += 32) {
@@ -1229,18 +1214,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
       }
       if (done) {
         // accept: the candidate becomes the iterate (workspace -> shared memory)
-        {
-          const double* cd = c.cand + (size_t)alpha_idx * 8 * a.Kc;
-          for (int k = lane; k < K; k += 32) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) X[k * 6 + i] = cd[i * a.Kc + k];
-            if (k < N) {
-              U[k * 2] = cd[6 * a.Kc + k];
-              U[k * 2 + 1] = cd[7 * a.Kc + k];
-            }
-          }
-          __syncwarp();
-        }
+        adopt(c, alpha_idx, X, U);
         unsigned char* tn = nidx; nidx = nidx_c; nidx_c = tn;
         dlambda = fmin(dlambda / reg_ratio, 1.0 / reg_ratio);
         lambda = lambda * dlambda * (lambda > reg_min ? 1.0 : 0.0);
@@ -1287,6 +1261,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
     }
     if (a.trajectory) {
       // TransformToTrajectory (:771-791): time, s, x, y, theta, kappa, velocity, a, jerk, delta, delta_rate, lb, rb
+#pragma unroll 1
       for (int k = lane; k < K; k += 32) {
         double* tp = a.trajectory + ((size_t)b * K + k) * 13;
         const double* x = X + k * 6;
@@ -1295,7 +1270,7 @@ __global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__
         tp[2] = x[0];
         tp[3] = x[1];
         tp[4] = x[2];
-        tp[5] = tan(x[5]) / P.L;
+        tp[5] = nt_tan(x[5]) / P.L;
         tp[6] = x[3];
         tp[7] = x[4];
         tp[8] = k < N ? U[k * 2] : 0.0;
