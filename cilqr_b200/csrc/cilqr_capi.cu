@@ -117,7 +117,7 @@ SmemLayout make_layout(int N, int S_left, int S_right) {
   L.U = o; o += N * 2;
   L.Kg = o; o += N * 12;
   L.kg = o; o += N * 2;
-  L.lin = o; o += 32 * cilqr::kLinStride;
+  L.lin = o; o += cilqr::kWin * cilqr::kLinStride;
   o += (o & 1);
   L.seg = o; o += (S_left + S_right) * cilqr::kSegStride;
   L.grp = o; o += ((S_left + cilqr::kGroup - 1) / cilqr::kGroup + (S_right + cilqr::kGroup - 1) / cilqr::kGroup) * 3;
@@ -125,6 +125,8 @@ SmemLayout make_layout(int N, int S_left, int S_right) {
   L.nidx = o;
   L.nidx_bytes = (K * 10 + 7) / 8 * 8;
   L.total_bytes = o * 8 + 2 * L.nidx_bytes;
+  // development knob (tools/occ_sweep.py): pad the CTA's shared memory to cap the resident warps per SM
+  if (const char* pad = getenv("CILQR_B200_SMEM_PAD")) L.total_bytes += atoi(pad);
   return L;
 }
 

@@ -38,6 +38,11 @@ constexpr int kLinStride = 35;  // doubles per knot in the linearisation window
 constexpr int kSegStride = 10;  // sx sy ex ey ux uy len a b c
 constexpr int kGroup = 8;       // lane segments per bounding-circle group of the pruned nearest search
 constexpr int kScratch = 192;   // doubles of per-warp scratch
+#ifndef CILQR_LIN_WINDOW
+#define CILQR_LIN_WINDOW 32
+#endif
+constexpr int kWin = CILQR_LIN_WINDOW;  // knots per linearisation window (<= 32: lane == knot inside a window)
+static_assert(kWin >= 1 && kWin <= 32, "linearisation window is at most one knot per lane");
 constexpr unsigned kFull = 0xffffffffu;
 
 // linearisation record offsets
@@ -623,15 +628,16 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
   const double wsym = vi == vj ? 0.5 : 1.0;  // 0.5 * (1 or 2) y_i V_ij y_j
 
   double acc0 = 0.0, acc1 = 0.0;
-  const int last_chunk = (K - 1) / 32;
+  const int last_chunk = (K - 1) / kWin;
   for (int ch = last_chunk; ch >= 0; --ch) {
-    const int k0 = ch * 32;
+    const int k0 = ch * kWin;
     const int k = k0 + lane;
+    const bool lin_lane = lane < kWin && k < K;
     __syncwarp();
-    if (k < K) linearize_knot(c, k, Xs, Us, nidx, lin + lane * kLinStride);
+    if (lin_lane) linearize_knot(c, k, Xs, Us, nidx, lin + lane * kLinStride);
     __syncwarp();
     if (dbg) {
-      if (k < K) {
+      if (lin_lane) {
         const double* rec = lin + lane * kLinStride;
         if (k < N) {
           if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
@@ -642,7 +648,7 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
         if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
       }
     }
-    int kend = k0 + 31;
+    int kend = k0 + kWin - 1;
     if (kend > N - 1) kend = N - 1;
     if (ch == last_chunk) {
       // Vx = cost_Jx.back(), Vxx = cost_Hx.back()    (:343-344)
@@ -967,7 +973,10 @@ __device__ __noinline__ void copy_out(double* dst, const double* src, int n, int
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
+#ifndef CILQR_MIN_BLOCKS
+#define CILQR_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(32, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const DevParams& P = a.P;
