@@ -127,6 +127,7 @@ SmemLayout make_layout(int N, int S_left, int S_right) {
   L.total_bytes = o * 8 + 2 * L.nidx_bytes;
   // development knob (tools/occ_sweep.py): pad the CTA's shared memory to cap the resident warps per SM
   if (const char* pad = getenv("CILQR_B200_SMEM_PAD")) L.total_bytes += atoi(pad);
+  L.total_bytes = (L.total_bytes + 15) / 16 * 16;  // per-warp stages are packed back to back in the CTA
   return L;
 }
 
@@ -143,12 +144,13 @@ int plan_launch(cilqr_handle* h, int B, int N, int S_left, int S_right, Launch* 
   L.sm = make_layout(N, S_left, S_right);
   L.Kp = (N + 1 + 31) / 32 * 32;
   L.Kc = (N + 1 + 3) / 4 * 4;
-  if (L.sm.total_bytes > h->smem_optin) return CILQR_E_SMEM;
-  CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, cilqr::cilqr_solve_kernel, 32, L.sm.total_bytes));
+  const int W = cilqr::kCtaWarps;
+  if (L.sm.total_bytes * W > h->smem_optin) return CILQR_E_SMEM;
+  CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes * W));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, cilqr::cilqr_solve_kernel, 32 * W, L.sm.total_bytes * W));
   if (L.blocks_per_sm < 1) return CILQR_E_SMEM;
-  // persistent grid: one CTA (= one warp) per resident slot of every SM
-  L.grid = std::min(B, h->num_sms * L.blocks_per_sm);
+  // persistent grid: one CTA (W warps, one scenario each) per resident slot of every SM
+  L.grid = std::min((B + W - 1) / W, h->num_sms * L.blocks_per_sm);
   if (L.grid < 1) L.grid = 1;
   *out = L;
   return CILQR_OK;
@@ -186,7 +188,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   int rc = plan_launch(h, in->B, in->N, in->S_left, in->S_right, &L);
   if (rc != CILQR_OK) return rc;
   L.ws_stride = (size_t)in->M_max * 3 * L.Kp + (size_t)cilqr::kNAlpha * 8 * L.Kc;
-  rc = ensure_ws(h, s, (size_t)L.grid * L.ws_stride * sizeof(double));
+  rc = ensure_ws(h, s, (size_t)L.grid * cilqr::kCtaWarps * L.ws_stride * sizeof(double));
   if (rc != CILQR_OK) return rc;
   KernelArgs a;
   memset(&a, 0, sizeof(a));
@@ -242,7 +244,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   }
   CK(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), stream));
   CK(cudaEventRecord(s->ev0, stream));
-  cilqr::cilqr_solve_kernel<<<L.grid, 32, L.sm.total_bytes, stream>>>(a);
+  cilqr::cilqr_solve_kernel<<<L.grid, 32 * cilqr::kCtaWarps, L.sm.total_bytes * cilqr::kCtaWarps, stream>>>(a);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s->ev1, stream));
   h->launches += 1;
@@ -539,7 +541,7 @@ int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* 
   Launch L;
   int rc = plan_launch(const_cast<cilqr_handle*>(h), 1 << 30, N, S_left, S_right, &L);
   if (rc != CILQR_OK) return rc;
-  if (warps_per_sm) *warps_per_sm = L.blocks_per_sm;
+  if (warps_per_sm) *warps_per_sm = L.blocks_per_sm * cilqr::kCtaWarps;
   if (smem_bytes_per_warp) *smem_bytes_per_warp = L.sm.total_bytes;
   return CILQR_OK;
 }

@@ -976,14 +976,20 @@ __device__ __noinline__ void copy_out(double* dst, const double* src, int n, int
 #ifndef CILQR_MIN_BLOCKS
 #define CILQR_MIN_BLOCKS 1
 #endif
-__global__ void __launch_bounds__(32, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x;
+#ifndef CILQR_CTA_WARPS
+#define CILQR_CTA_WARPS 1
+#endif
+constexpr int kCtaWarps = CILQR_CTA_WARPS;  // warps (= concurrently solved scenarios) per CTA
+__global__ void __launch_bounds__(32 * kCtaWarps, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) double smem_cta[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* smem = smem_cta + (size_t)warp * (a.sm.total_bytes / 8);
   const DevParams& P = a.P;
   const int N = a.N, K = N + 1;
   Ctx c(a, smem);
   c.lane = lane;
-  c.ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
+  c.ws = a.ws + ((size_t)blockIdx.x * kCtaWarps + warp) * a.ws_stride;
   c.cand = c.ws + (size_t)a.M_max * 3 * a.Kp;
   double* seg = smem + a.sm.seg;
   unsigned char* nidx_base = reinterpret_cast<unsigned char*>(smem + a.sm.nidx);
@@ -991,8 +997,27 @@ __global__ void __launch_bounds__(32, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const
 
   while (true) {
     unsigned int b = 0;
+#if defined(CILQR_LOCKSTEP_TEST) && CILQR_LOCKSTEP_TEST == 2
+    // experiment: the warps of one scheduler (warp & 3) solve the SAME scenario side by side
+    __shared__ unsigned int s_bg[4];
+    {
+      const int grp = warp & 3, gthreads = (kCtaWarps / 4) * 32;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
+      if (warp == grp && lane == 0) s_bg[grp] = atomicAdd(a.ticket, 1u);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
+      b = s_bg[grp];
+    }
+#elif defined(CILQR_LOCKSTEP_TEST)
+    // experiment: all warps of the CTA solve the SAME scenario side by side (aligned instruction streams)
+    __shared__ unsigned int s_b;
+    __syncthreads();
+    if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    b = s_b;
+#else
     if (lane == 0) b = atomicAdd(a.ticket, 1u);
     b = __shfl_sync(kFull, b, 0);
+#endif
     if (b >= (unsigned)a.B) break;
 
     // ---- load scenario, TransformGoals (:141-152)
@@ -1153,6 +1178,24 @@ __global__ void __launch_bounds__(32, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const
     int status = 4;
     unsigned ahash = 2166136261u;
     int iter = 0;
+#ifdef CILQR_PHASE_TEST
+    // experiment: hammer ONE phase (1 rollout, 2 cost evaluation, 3 linearise + backward) to see how
+    // unaligned warps scale when they all run the same code
+    {
+      double dVt[2];
+      backward_pass(c, lambda, X, U, nidx, dVt, nullptr, (int)b);
+      rollout(c, X, U, (1u << kNAlpha) - 1u, true, false);
+      __threadfence_block();
+      for (int rep = 0; rep < 50; ++rep) {
+        if (CILQR_PHASE_TEST == 1) rollout(c, X, U, (1u << kNAlpha) - 1u, true, false);
+        if (CILQR_PHASE_TEST == 2) eval_cost(c, c.cand + (size_t)(rep % 3 + 1) * 8 * a.Kc, nidx, nidx_c, cost_new5);
+        if (CILQR_PHASE_TEST == 3) backward_pass(c, lambda, X, U, nidx, dVt, nullptr, (int)b);
+        __syncwarp();
+      }
+      cost_acc[0] += cost_new5[0] + dVt[0];
+      iter = P.max_iter;
+    }
+#endif
     for (; iter < P.max_iter; ++iter) {
       double dV[2];
       backward_pass(c, lambda, X, U, nidx, dV, iter == 0 ? dbg : nullptr, (int)b);

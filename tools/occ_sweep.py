@@ -42,7 +42,7 @@ def child(a):
         ms.append(solver.last_kernel_ms())
     w, smem = solver.occupancy(N, batch.S, batch.S)
     conv = int((ss[:, 0] <= 2).sum().item())
-    best = min(ms[1:])
+    best = min(ms[1:] or ms)
     print(json.dumps({"lib": os.path.basename(a.lib or "default"), "pad": int(os.environ.get("CILQR_B200_SMEM_PAD", "0")),
                       "N": N, "B": B, "warps_per_sm": w, "smem_per_warp": smem, "ms": round(best, 3),
                       "traj_per_s": round(conv / best * 1e3), "converged": conv,
