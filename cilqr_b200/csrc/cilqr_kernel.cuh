@@ -34,7 +34,7 @@ constexpr int kNX = 6;
 constexpr int kNU = 2;
 constexpr int kDisc = 5;
 constexpr int kNAlpha = 11;
-constexpr int kLinStride = 35;  // doubles per knot in the linearisation window
+constexpr int kLinStride = 37;  // doubles per knot in the linearisation window
 constexpr int kSegStride = 10;  // sx sy ex ey ux uy len a b c
 constexpr int kGroup = 8;       // lane segments per bounding-circle group of the pruned nearest search
 constexpr int kScratch = 192;   // doubles of per-warp scratch
@@ -56,6 +56,8 @@ constexpr int LZ = 31;   // constants 0, 1, dt, dt^2/2 so that A, B, H can be ga
 constexpr int LO = 32;
 constexpr int LDT = 33;
 constexpr int LB30 = 34;
+constexpr int LSN = 35;   // sin, cos of the heading (consumed by linearize_discs)
+constexpr int LCS = 36;
 
 struct DevParams {
   double dt, L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
@@ -261,131 +263,119 @@ struct Ctx {
 };
 
 // ------------------------------------------------------------------------------------------
-// TotalCost of (Xs, Us): lane == knot.  Also records the nearest lane segment of every
-// (knot, disc, side) in nidx for the linearisation that follows an accepted step.
-// Xs points at one candidate block of the global workspace ([8][Kc]: x0..x5, u0, u1).
-//
-// Nearest lane segment (FindNeastLaneSegment, ilqr_optimizer.cc:605-618) without scanning all S
-// segments: segments are bundled in groups of kGroup with a bounding circle (centre, radius) built
-// at scenario load.  For every disc the exact distance to the segment that was nearest in the
-// current iterate (`guess`) is an upper bound ub on the minimum; a group whose circle is farther
-// from the rear-axle point than ub + radius + (largest disc offset) cannot contain the minimiser
-// of any disc -- nor tie with it -- and is skipped.  Surviving groups are scanned in index order
-// with the reference's strict '<', so the arg-min (first minimum) is the brute-force one.
+// Nearest lane segment of one disc centre (FindNeastLaneSegment, ilqr_optimizer.cc:605-618) without
+// scanning all S segments: segments are bundled in groups of kGroup with a bounding circle (centre,
+// radius) built at scenario load.  The exact distance to the segment that was nearest in the current
+// iterate (`guess`) is an upper bound ub on the minimum; a group whose circle is farther from the disc
+// centre than ub + radius cannot contain the minimiser -- nor tie with it -- and is skipped.  Surviving
+// groups are scanned in index order with the reference's strict '<', so the arg-min (first minimum)
+// is the brute-force one.
+__device__ __forceinline__ int nearest_segment(const double* sg0, const double* gp, int S, int guess, double xd,
+                                               double yd) {
+  const int gi = guess < S ? guess : S - 1;
+  const double ub = sqrt(seg_dist2(sg0 + gi * kSegStride, xd, yd));
+  const int ng = (S + kGroup - 1) / kGroup;
+  double best = 1.7976931348623157e308;
+  int bi = 0;
+#pragma unroll 1
+  for (int g = 0; g < ng; ++g) {
+    const double dcx = xd - gp[g * 3], dcy = yd - gp[g * 3 + 1];
+    const double thr = ub + gp[g * 3 + 2];
+    if (fma(dcx, dcx, dcy * dcy) > thr * thr) continue;  // (NaN compares false: never pruned)
+    const int s_hi = (g + 1) * kGroup < S ? (g + 1) * kGroup : S;
+#pragma unroll 2
+    for (int s = g * kGroup; s < s_hi; ++s) {
+      const double dd = seg_dist2(sg0 + s * kSegStride, xd, yd);
+      if (dd < best) {
+        best = dd;
+        bi = s;
+      }
+    }
+  }
+  return bi;
+}
+
+// ------------------------------------------------------------------------------------------
+// TotalCost of (Xs, Us) (ilqr_optimizer.cc:417-436) in two passes over the candidate block Xs of the
+// global workspace ([8][Kc]: x0..x5, u0, u1):
+//   pass 1, lane == knot:          JCost + DynamicsCost (:497-551), sin/cos of the heading -> trig
+//   pass 2, lane == (knot, disc):  CorridorCost + LaneBoundaryCost (:553-603) of ONE disc per lane
+// (one disc per lane keeps the code five times smaller than a disc-unrolled knot-per-lane body and
+// fills 505 of 512 lane slots at K = 101 instead of 101 of 128).  Also records the nearest lane
+// segment of every (knot, disc, side) in nidx for the linearisation that follows an accepted step.
 __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const unsigned char* guess,
                                        unsigned char* nidx, double cost5[5]) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
   const double* seg = c.sm + a.sm.seg;
+  double* trig = c.sm + a.sm.lin;  // [K][2] sin, cos (the linearisation window is idle here)
   double sum_j = 0.0, sum_d = 0.0, sum_c = 0.0, sum_l = 0.0;
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    const int k = k0 + c.lane;
-    const bool act = k < K;
-    const int kk = act ? k : K - 1;
-    const double* xc = Xs + kk;
+#pragma unroll 1
+  for (int k = c.lane; k < K; k += 32) {
+    const double* xc = Xs + k;
     const double px = xc[0], py = xc[a.Kc], th = xc[2 * a.Kc], v = xc[3 * a.Kc], ac = xc[4 * a.Kc], de = xc[5 * a.Kc];
-    double tj = 0.0, td = 0.0, tc = 0.0, tl = 0.0;
-    {
-      const double dx = px - c.goal(kk, 0), dy = py - c.goal(kk, 1), dth = th - c.goal(kk, 2);
-      tj = P.wx * (dx * dx) + P.wy * (dy * dy) + P.wth * (dth * dth);
-      BarAcc bd = {1.0, 0.0};
-      bar_add(bd, -v, P);
-      bar_add(bd, v - P.vmax, P);
-      bar_add(bd, ac - P.amax, P);
-      bar_add(bd, P.amin - ac, P);
-      bar_add(bd, de - P.dmax, P);
-      bar_add(bd, P.dmin - de, P);
-      if (kk < N) {
-        const double u0 = Xs[6 * a.Kc + kk], u1 = Xs[7 * a.Kc + kk];
-        tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
-        bar_add(bd, u0 - P.jmax, P);
-        bar_add(bd, P.jmin - u0, P);
-        bar_add(bd, u1 - P.drmax, P);
-        bar_add(bd, P.drmin - u1, P);
-      }
-      td = bar_value(bd, P);
+    const double dx = px - c.goal(k, 0), dy = py - c.goal(k, 1), dth = th - c.goal(k, 2);
+    double tj = P.wx * (dx * dx) + P.wy * (dy * dy) + P.wth * (dth * dth);
+    BarAcc bd = {1.0, 0.0};
+    bar_add(bd, -v, P);
+    bar_add(bd, v - P.vmax, P);
+    bar_add(bd, ac - P.amax, P);
+    bar_add(bd, P.amin - ac, P);
+    bar_add(bd, de - P.dmax, P);
+    bar_add(bd, P.dmin - de, P);
+    if (k < N) {
+      const double u0 = Xs[6 * a.Kc + k], u1 = Xs[7 * a.Kc + k];
+      tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
+      bar_add(bd, u0 - P.jmax, P);
+      bar_add(bd, P.jmin - u0, P);
+      bar_add(bd, u1 - P.drmax, P);
+      bar_add(bd, P.drmin - u1, P);
     }
+    sum_j += tj;
+    sum_d += bar_value(bd, P);
     const double2 scth = nt_sincos(th);
-    const double sn = scth.x, cs = scth.y;
-    double xd[kDisc], yd[kDisc];
-#pragma unroll
-    for (int d = 0; d < kDisc; ++d) {
-      xd[d] = px + P.off[d] * cs;
-      yd[d] = py + P.off[d] * sn;
-    }
+    trig[k * 2] = scth.x;
+    trig[k * 2 + 1] = scth.y;
+  }
+  __syncwarp();
+  const int items = K * kDisc;
+  const int ngl = (a.S_left + kGroup - 1) / kGroup;
+  const double* grp = c.sm + a.sm.grp;
+#pragma unroll 1
+  for (int j0 = 0; j0 < items; j0 += 32) {
+    const int j = j0 + c.lane;
+    const bool act = j < items;
+    const int jj = act ? j : items - 1;
+    const int k = jj / kDisc, d = jj - k * kDisc;
+    const double o = P.off[d];
+    const double xd = fma(o, trig[k * 2 + 1], Xs[k]);
+    const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
     // corridor half-planes of this knot
-    {
-      const int M = act ? c.cnt[kk] : 0;
-      const int Mw = __reduce_max_sync(kFull, M);
-      BarAcc bc[kDisc];
-#pragma unroll
-      for (int d = 0; d < kDisc; ++d) bc[d] = {1.0, 0.0};
-      const double* w = c.ws + kk;
-#pragma unroll 2
-      for (int m = 0; m < Mw; ++m) {
-        if (m < M) {
-          const double pa = w[(m * 3 + 0) * a.Kp], pb = w[(m * 3 + 1) * a.Kp], pc = w[(m * 3 + 2) * a.Kp];
-#pragma unroll
-          for (int d = 0; d < kDisc; ++d) bar_add(bc[d], fma(pb, yd[d], pa * xd[d]) - pc, P);
-        }
+    const int M = act ? c.cnt[k] : 0;
+    const int Mw = __reduce_max_sync(kFull, M);
+    BarAcc bc = {1.0, 0.0};
+    const double* w = c.ws + k;
+#pragma unroll 4
+    for (int m = 0; m < Mw; ++m) {
+      if (m < M) {
+        const double pa = w[(m * 3 + 0) * a.Kp], pb = w[(m * 3 + 1) * a.Kp], pc = w[(m * 3 + 2) * a.Kp];
+        bar_add(bc, fma(pb, yd, pa * xd) - pc, P);
       }
-#pragma unroll
-      for (int d = 0; d < kDisc; ++d) tc += bar_value(bc[d], P);
     }
-    // nearest lane segment per disc and side (strict '<': first minimum wins)
-    {
-      BarAcc bl = {1.0, 0.0};
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const int S = side == 0 ? a.S_left : a.S_right;
-        const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
-        const int ng = (S + kGroup - 1) / kGroup;
-        const double* gp = c.sm + a.sm.grp + (side == 0 ? 0 : (a.S_left + kGroup - 1) / kGroup) * 3;
-        double best[kDisc];
-        int bi[kDisc];
-        double ub2 = 0.0;
-#pragma unroll
-        for (int d = 0; d < kDisc; ++d) {
-          best[d] = 1.7976931348623157e308;
-          bi[d] = 0;
-          int gi = guess[kk * 10 + d * 2 + side];
-          gi = gi < S ? gi : S - 1;
-          ub2 = fmax(ub2, seg_dist2(sg0 + gi * kSegStride, xd[d], yd[d]));
-        }
-        const double ub = sqrt(ub2);
-        for (int g = 0; g < ng; ++g) {
-          const double dcx = px - gp[g * 3], dcy = py - gp[g * 3 + 1];
-          const double thr = ub + gp[g * 3 + 2];
-          if (fma(dcx, dcx, dcy * dcy) > thr * thr) continue;  // (NaN compares false: never pruned)
-          const int s_hi = (g + 1) * kGroup < S ? (g + 1) * kGroup : S;
-          for (int s = g * kGroup; s < s_hi; ++s) {
-            const double* sg = sg0 + s * kSegStride;
-            double r[7];
-#pragma unroll
-            for (int q = 0; q < 7; ++q) r[q] = sg[q];
-#pragma unroll
-            for (int d = 0; d < kDisc; ++d) {
-              const double dd = seg_dist2(r, xd[d], yd[d]);
-              if (dd < best[d]) {
-                best[d] = dd;
-                bi[d] = s;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int d = 0; d < kDisc; ++d) {
-          const double* sg = sg0 + bi[d] * kSegStride;
-          bar_add(bl, fma(sg[8], yd[d], sg[7] * xd[d]) - sg[9], P);
-          if (act) nidx[kk * 10 + d * 2 + side] = (unsigned char)bi[d];
-        }
-      }
-      tl = bar_value(bl, P);
+    // nearest lane segment per side (strict '<': first minimum wins)
+    BarAcc bl = {1.0, 0.0};
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int S = side == 0 ? a.S_left : a.S_right;
+      const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, S, guess[jj * 2 + side], xd, yd);
+      const double* sg = sg0 + bi * kSegStride;
+      bar_add(bl, fma(sg[8], yd, sg[7] * xd) - sg[9], P);
+      if (act) nidx[jj * 2 + side] = (unsigned char)bi;
     }
+    const double tc = bar_value(bc, P), tl = bar_value(bl, P);
     if (act) {
-      sum_j += tj;
-      sum_d += td;
       sum_c += tc;
       sum_l += tl;
     }
@@ -399,9 +389,12 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
 }
 
 // ------------------------------------------------------------------------------------------
-// CostJacbian + CostHessian + DynamicsJacbian at knot k -> 31-double record.
-__device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const double* Us,
-                               const unsigned char* nidx, double* rec) {
+// CostJacbian + CostHessian + DynamicsJacbian (ilqr_optimizer.cc:620-769, vehicle_model.cc:21-86) of one
+// window of knots -> 37-double records, in two passes:
+//   linearize_knot, lane == knot:        A, B, the running-cost and bound-barrier terms, sin/cos heading
+//   linearize_discs, lane == (disc, knot): corridor and lane-boundary barrier terms of ONE disc per lane,
+//                                        reduced over the five disc lanes of a knot by shuffles
+__device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const double* Us, double* rec) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int N = a.N;
@@ -414,10 +407,6 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
     for (int i = 0; i < 11; ++i) rec[LA + i] = A11[i];
     rec[LB21] = b21;
   }
-  double Jx0 = 2.0 * P.wx * (x[0] - c.goal(k, 0));
-  double Jx1 = 2.0 * P.wy * (x[1] - c.goal(k, 1));
-  double Jx2 = 2.0 * P.wth * (x[2] - c.goal(k, 2));
-  double H00 = 2.0 * P.wx, H01 = 0.0, H02 = 0.0, H11 = 2.0 * P.wy, H12 = 0.0, H22 = 2.0 * P.wth;
   double cj0, cj1, co0, co1, cd;
   // DynamicsConsJacbian / Hessian: each state (control) component carries a pair of bounds
   bar_coef(0.0 - x[3], P, cj0, co0, cd);
@@ -440,74 +429,107 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
   bar_coef(u1 - P.drmax, P, cj1, co1, cd);
   rec[LJU + 1] = 2.0 * P.wdr * u1 + (cj1 - cj0);
   rec[LHU + 1] = 2.0 * P.wdr + (co0 + co1);
-
   const double2 scth = nt_sincos(x[2]);
-  const double sn = scth.x, cs = scth.y;
-  double xd[kDisc], yd[kDisc];
-#pragma unroll
-  for (int d = 0; d < kDisc; ++d) {
-    xd[d] = x[0] + P.off[d] * cs;
-    yd[d] = x[1] + P.off[d] * sn;
-  }
-  // One half-plane (pa,pb,pc) acting on the listed discs.  dx = (a, b, off*t) with
-  // t = -a sin + b cos;  ddx(2,2) = -off*(a cos + b sin).  Sums over discs are factored out.
-  auto plane = [&](double pa, double pb, double pc, int d_lo, int d_hi) {
-    double sj = 0.0, sj1 = 0.0, so = 0.0, so1 = 0.0, so2 = 0.0, sd1 = 0.0;
-#pragma unroll
-    for (int d = 0; d < kDisc; ++d) {
-      if (d >= d_lo && d < d_hi) {
-        const double g = fma(pb, yd[d], pa * xd[d]) - pc;
-        double cj, co, cdd;
-        bar_coef(g, P, cj, co, cdd);
-        const double o = P.off[d];
-        sj += cj;
-        sj1 = fma(cj, o, sj1);
-        so += co;
-        so1 = fma(co, o, so1);
-        so2 = fma(co * o, o, so2);
-        sd1 = fma(cdd, o, sd1);
-      }
-    }
-    const double t = pb * cs - pa * sn;
-    const double w = pa * cs + pb * sn;
-    Jx0 = fma(pa, sj, Jx0);
-    Jx1 = fma(pb, sj, Jx1);
-    Jx2 = fma(t, sj1, Jx2);
-    H00 = fma(pa * pa, so, H00);
-    H01 = fma(pa * pb, so, H01);
-    H11 = fma(pb * pb, so, H11);
-    H02 = fma(pa * t, so1, H02);
-    H12 = fma(pb * t, so1, H12);
-    H22 = fma(t * t, so2, H22);
-    H22 = fma(w, sd1, H22);
-  };
-  const int M = c.cnt[k];
-  const double* w = c.ws + k;
-  for (int m = 0; m < M; ++m) {
-    plane(w[(m * 3 + 0) * a.Kp], w[(m * 3 + 1) * a.Kp], w[(m * 3 + 2) * a.Kp], 0, kDisc);
-  }
-  const double* seg = c.sm + a.sm.seg;
-#pragma unroll
-  for (int d = 0; d < kDisc; ++d) {
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const double* sg = seg + ((side == 0 ? 0 : a.S_left) + nidx[k * 10 + d * 2 + side]) * kSegStride;
-      plane(sg[7], sg[8], sg[9], d, d + 1);
-    }
-  }
+  rec[LSN] = scth.x;
+  rec[LCS] = scth.y;
   rec[LZ] = 0.0;
   rec[LO] = 1.0;
   rec[LDT] = P.dt;
   rec[LB30] = 0.5 * P.dt * P.dt;
-  rec[LJX + 0] = Jx0;
-  rec[LJX + 1] = Jx1;
-  rec[LJX + 2] = Jx2;
-  rec[LHX + 0] = H00;
-  rec[LHX + 1] = H01;
-  rec[LHX + 2] = H02;
-  rec[LHX + 3] = H11;
-  rec[LHX + 4] = H12;
-  rec[LHX + 5] = H22;
+  rec[LJX + 0] = 2.0 * P.wx * (x[0] - c.goal(k, 0));
+  rec[LJX + 1] = 2.0 * P.wy * (x[1] - c.goal(k, 1));
+  rec[LJX + 2] = 2.0 * P.wth * (x[2] - c.goal(k, 2));
+  rec[LHX + 0] = 2.0 * P.wx;
+  rec[LHX + 1] = 0.0;
+  rec[LHX + 2] = 0.0;
+  rec[LHX + 3] = 2.0 * P.wy;
+  rec[LHX + 4] = 0.0;
+  rec[LHX + 5] = 2.0 * P.wth;
+}
+
+constexpr int kKnotsPerPass = 6;  // 6 knots x 5 discs = 30 lanes per pass of linearize_discs
+
+// Barrier terms of the half-planes acting on disc d of knot k (CorridorConsJacbian/Hessian :690-727,
+// LaneBoundaryConsJacbian/Hessian :729-769).  dx = (a, b, off*t) with t = -a sin + b cos;
+// ddx(2,2) = -off*(a cos + b sin).  lane = d * 6 + (knot inside the group of six).
+__device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, const unsigned char* nidx,
+                                double* lin) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const double* seg = c.sm + a.sm.seg;
+  const int d = c.lane / kKnotsPerPass, kl = c.lane - d * kKnotsPerPass;
+#pragma unroll 1
+  for (int g0 = 0; g0 < nk; g0 += kKnotsPerPass) {
+    const bool act = d < kDisc && g0 + kl < nk;
+    const int ko = act ? g0 + kl : 0;  // knot inside the window
+    const int k = k0 + ko;
+    double* rec = lin + ko * kLinStride;
+    const double sn = rec[LSN], cs = rec[LCS];
+    const double o = P.off[act ? d : 0];
+    const double xd = fma(o, cs, Xs[k * 6]), yd = fma(o, sn, Xs[k * 6 + 1]);
+    double J0 = 0.0, J1 = 0.0, J2 = 0.0, H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
+    auto plane = [&](double pa, double pb, double pc) {
+      const double g = fma(pb, yd, pa * xd) - pc;
+      double cj, co, cdd;
+      bar_coef(g, P, cj, co, cdd);
+      const double to = (pb * cs - pa * sn) * o;
+      const double wo = (pa * cs + pb * sn) * o;
+      const double ca = pa * co, cb = pb * co;
+      J0 = fma(pa, cj, J0);
+      J1 = fma(pb, cj, J1);
+      J2 = fma(to, cj, J2);
+      H00 = fma(pa, ca, H00);
+      H01 = fma(pa, cb, H01);
+      H11 = fma(pb, cb, H11);
+      H02 = fma(to, ca, H02);
+      H12 = fma(to, cb, H12);
+      H22 = fma(to, to * co, H22);
+      H22 = fma(wo, cdd, H22);
+    };
+    const int M = act ? c.cnt[k] : 0;
+    const int Mw = __reduce_max_sync(kFull, M);
+    const double* w = c.ws + k;
+#pragma unroll 2
+    for (int m = 0; m < Mw; ++m) {
+      if (m < M) plane(w[(m * 3 + 0) * a.Kp], w[(m * 3 + 1) * a.Kp], w[(m * 3 + 2) * a.Kp]);
+    }
+    if (act) {
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        const double* sg = seg + ((side == 0 ? 0 : a.S_left) + nidx[(k * kDisc + d) * 2 + side]) * kSegStride;
+        plane(sg[7], sg[8], sg[9]);
+      }
+    }
+    // sum over the five disc lanes of each knot: (d0 + d3) + (d1 + d4), then + d2
+    auto red = [&](double v) {
+      const double hi = __shfl_down_sync(kFull, v, 3 * kKnotsPerPass);
+      v += c.lane < 2 * kKnotsPerPass ? hi : 0.0;
+      const double a1 = __shfl_down_sync(kFull, v, kKnotsPerPass);
+      const double a2 = __shfl_down_sync(kFull, v, 2 * kKnotsPerPass);
+      return (v + a1) + a2;
+    };
+    J0 = red(J0);
+    J1 = red(J1);
+    J2 = red(J2);
+    H00 = red(H00);
+    H01 = red(H01);
+    H02 = red(H02);
+    H11 = red(H11);
+    H12 = red(H12);
+    H22 = red(H22);
+    if (d == 0 && act) {
+      rec[LJX + 0] += J0;
+      rec[LJX + 1] += J1;
+      rec[LJX + 2] += J2;
+      rec[LHX + 0] += H00;
+      rec[LHX + 1] += H01;
+      rec[LHX + 2] += H02;
+      rec[LHX + 3] += H11;
+      rec[LHX + 4] += H12;
+      rec[LHX + 5] += H22;
+    }
+    __syncwarp();
+  }
 }
 
 // scratch map (doubles) used by backward / iqr
@@ -634,8 +656,9 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
     const int k = k0 + lane;
     const bool lin_lane = lane < kWin && k < K;
     __syncwarp();
-    if (lin_lane) linearize_knot(c, k, Xs, Us, nidx, lin + lane * kLinStride);
+    if (lin_lane) linearize_knot(c, k, Xs, Us, lin + lane * kLinStride);
     __syncwarp();
+    linearize_discs(c, k0, (K - k0 < kWin ? K - k0 : kWin), Xs, nidx, lin);
     if (dbg) {
       if (lin_lane) {
         const double* rec = lin + lane * kLinStride;

@@ -1,3 +1,4 @@
 #!/bin/bash
 V=cilqr_b200/lib/variants
-for v in pt1 pt2 pt3; do python tools/occ_sweep.py --lib $V/libcilqr_b200_$v.so --horizon 20 --batch 8192 --pads 32000,8000,0; done
+CILQR_B200_SMEM_PAD=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cilqr_solve -c 1 -f -o gpurun_out/v5_occ12 \
+    python tools/occ_sweep.py --child --lib $V/libcilqr_b200_w16_b12.so --horizon 20 --batch 8192 --reps 0 2>&1 | tail -1
