@@ -20,6 +20,7 @@
 using cilqr::DevParams;
 using cilqr::KernelArgs;
 using cilqr::SmemLayout;
+using cilqr::CtxLayout;
 
 namespace {
 
@@ -74,6 +75,7 @@ int fail_cuda(cilqr_handle* h, cudaError_t e, const char* where) {
 void make_dev_params(const CilqrParams& p, DevParams* d) {
   d->dt = p.delta_t;
   d->L = p.wheel_base;
+  d->inv_L = 1.0 / p.wheel_base;
   d->rt = 1.0 / p.barrier_t;
   d->eps = p.barrier_eps;
   d->inv_eps = 1.0 / p.barrier_eps;
@@ -109,49 +111,71 @@ void make_dev_params(const CilqrParams& p, DevParams* d) {
   d->max_iter = p.max_iter_num;
 }
 
-SmemLayout make_layout(int N, int S_left, int S_right) {
+SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   SmemLayout L;
-  const int K = N + 1;
-  int o = 0;
-  L.X = o; o += K * 6;
-  L.U = o; o += N * 2;
-  L.Kg = o; o += N * 12;
-  L.kg = o; o += N * 2;
-  L.lin = o; o += cilqr::kWin * cilqr::kLinStride;
-  o += (o & 1);
-  L.seg = o; o += (S_left + S_right) * cilqr::kSegStride;
-  L.grp = o; o += ((S_left + cilqr::kGroup - 1) / cilqr::kGroup + (S_right + cilqr::kGroup - 1) / cilqr::kGroup) * 3;
-  L.scr = o; o += cilqr::kScratch;
-  L.nidx = o;
-  L.nidx_bytes = (K * 10 + 7) / 8 * 8;
-  L.total_bytes = o * 8 + 2 * L.nidx_bytes;
-  // development knob (tools/occ_sweep.py): pad the CTA's shared memory to cap the resident warps per SM
-  if (const char* pad = getenv("CILQR_B200_SMEM_PAD")) L.total_bytes += atoi(pad);
-  L.total_bytes = (L.total_bytes + 15) / 16 * 16;  // per-warp stages are packed back to back in the CTA
+  const int K = N + 1, S = S_left + S_right;
+  const int ng = (S_left + cilqr::kGroup - 1) / cilqr::kGroup + (S_right + cilqr::kGroup - 1) / cilqr::kGroup;
+  auto even = [](int x) { return (x + 1) & ~1; };
+  // EVAL: seg, grp, trig
+  L.seg = 0;
+  L.grp = S * cilqr::kSegStride;
+  L.trig = even(L.grp + ng * 3);
+  L.pl_e = even(L.trig + 2 * K);
+  const int e_end = L.pl_e + 2 * M_max * cilqr::kPlaneTile;
+  // BACK: lin, scr; INIT builds seg/grp while iqr uses scr, so scr lies behind both
+  L.lin = 0;
+  L.scr = std::max(even(cilqr::kWin * cilqr::kLinStride), L.trig);
+  L.pl_b = L.scr + cilqr::kScratch;
+  const int b_end = L.pl_b + 2 * M_max * cilqr::kPlaneTile;
+  // ROLL: ring
+  L.ring = 0;
+  const int total = std::max(std::max(e_end, b_end), cilqr::kRingDoubles);
+  L.total_bytes = (total * 8 + 15) / 16 * 16;  // per-warp stages are packed back to back in the CTA
   return L;
+}
+
+CtxLayout make_ctx_layout(int N, int M_max, int S_left, int S_right) {
+  CtxLayout C;
+  const int K = N + 1, Kc = (K + 3) / 4 * 4, S = S_left + S_right;
+  const int ng = (S_left + cilqr::kGroup - 1) / cilqr::kGroup + (S_right + cilqr::kGroup - 1) / cilqr::kGroup;
+  auto even = [](int x) { return (x + 1) & ~1; };
+  C.planes = 0;
+  C.slots = M_max * 3 * Kc;
+  C.gains = C.slots + cilqr::kTrajSlots * 8 * Kc;
+  C.seg = C.gains + (N + cilqr::kRollChunk - 1) / cilqr::kRollChunk * cilqr::kRollChunk * cilqr::kGainStride;
+  C.grp = C.seg + S * cilqr::kSegStride;
+  C.nidx = even(C.grp + ng * 3);
+  C.nidx_bytes = (K * 10 + 7) / 8 * 8;
+  C.hdr = C.nidx + 2 * C.nidx_bytes / 8;
+  C.stride = (C.hdr + cilqr::kHdrDoubles + 15) / 16 * 16;
+  return C;
 }
 
 struct Launch {
   SmemLayout sm;
-  int blocks_per_sm = 0;
+  CtxLayout cl;
   int grid = 0;
-  int Kp = 0, Kc = 0;
-  size_t ws_stride = 0;
+  int warps = 0;
+  int ctx = 0;
+  int Kc = 0;
 };
 
-int plan_launch(cilqr_handle* h, int B, int N, int S_left, int S_right, Launch* out) {
+int plan_launch(cilqr_handle* h, int B, int N, int M_max, int S_left, int S_right, Launch* out) {
   Launch L;
-  L.sm = make_layout(N, S_left, S_right);
-  L.Kp = (N + 1 + 31) / 32 * 32;
+  L.sm = make_layout(N, M_max, S_left, S_right);
+  L.cl = make_ctx_layout(N, M_max, S_left, S_right);
   L.Kc = (N + 1 + 3) / 4 * 4;
-  const int W = cilqr::kCtaWarps;
-  if (L.sm.total_bytes * W > h->smem_optin) return CILQR_E_SMEM;
+  // warps per CTA: as many per-warp stages as fit the SM's shared memory, at most kCtaWarps
+  const int W = std::min(cilqr::kCtaWarps, h->smem_optin / L.sm.total_bytes);
+  if (W < 1) return CILQR_E_SMEM;
+  L.warps = W;
   CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes * W));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, cilqr::cilqr_solve_kernel, 32 * W, L.sm.total_bytes * W));
-  if (L.blocks_per_sm < 1) return CILQR_E_SMEM;
-  // persistent grid: one CTA (W warps, one scenario each) per resident slot of every SM
-  L.grid = std::min((B + W - 1) / W, h->num_sms * L.blocks_per_sm);
-  if (L.grid < 1) L.grid = 1;
+  // persistent grid: one CTA (W warps) per SM, each owning `ctx` scenario contexts
+  L.grid = std::max(1, std::min(B, h->num_sms));
+  int ctx = 2 * W;
+  if (const char* e = getenv("CILQR_B200_CTX")) ctx = atoi(e);  // development knob
+  ctx = std::max(1, std::min(ctx, cilqr::kMaxCtx));
+  L.ctx = std::max(1, std::min(ctx, (B + L.grid - 1) / L.grid));
   *out = L;
   return CILQR_OK;
 }
@@ -185,10 +209,9 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
                  const CilqrDebugOut* dbg) {
   if (in->B == 0) return CILQR_OK;
   Launch L;
-  int rc = plan_launch(h, in->B, in->N, in->S_left, in->S_right, &L);
+  int rc = plan_launch(h, in->B, in->N, in->M_max, in->S_left, in->S_right, &L);
   if (rc != CILQR_OK) return rc;
-  L.ws_stride = (size_t)in->M_max * 3 * L.Kp + (size_t)cilqr::kNAlpha * 8 * L.Kc;
-  rc = ensure_ws(h, s, (size_t)L.grid * cilqr::kCtaWarps * L.ws_stride * sizeof(double));
+  rc = ensure_ws(h, s, (size_t)L.grid * L.ctx * L.cl.stride * sizeof(double));
   if (rc != CILQR_OK) return rc;
   KernelArgs a;
   memset(&a, 0, sizeof(a));
@@ -199,9 +222,9 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.M_max = in->M_max;
   a.S_left = in->S_left;
   a.S_right = in->S_right;
-  a.Kp = L.Kp;
+  a.cl = L.cl;
   a.Kc = L.Kc;
-  a.ws_stride = L.ws_stride;
+  a.ctx_per_cta = L.ctx;
   a.start = in->start;
   a.coarse = in->coarse;
   a.corridor = in->corridor;
@@ -244,7 +267,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   }
   CK(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), stream));
   CK(cudaEventRecord(s->ev0, stream));
-  cilqr::cilqr_solve_kernel<<<L.grid, 32 * cilqr::kCtaWarps, L.sm.total_bytes * cilqr::kCtaWarps, stream>>>(a);
+  cilqr::cilqr_solve_kernel<<<L.grid, 32 * L.warps, L.sm.total_bytes * L.warps, stream>>>(a);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s->ev1, stream));
   h->launches += 1;
@@ -343,7 +366,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
   if (prop.major != 10) return bail(CILQR_E_NO_DEVICE);
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-  if (make_layout(N_max, S_max, S_max).total_bytes > h->smem_optin) return bail(CILQR_E_SMEM);
+  if (make_layout(N_max, M_max, S_max, S_max).total_bytes > h->smem_optin) return bail(CILQR_E_SMEM);
   for (int i = 0; i < kSlots; ++i) {
     Slot* s = &h->slots[i];
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
@@ -539,9 +562,9 @@ int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* 
                     int* smem_bytes_per_warp) {
   if (!h) return CILQR_E_INVALID;
   Launch L;
-  int rc = plan_launch(const_cast<cilqr_handle*>(h), 1 << 30, N, S_left, S_right, &L);
+  int rc = plan_launch(const_cast<cilqr_handle*>(h), 1 << 30, N, h->M_max, S_left, S_right, &L);
   if (rc != CILQR_OK) return rc;
-  if (warps_per_sm) *warps_per_sm = L.blocks_per_sm * cilqr::kCtaWarps;
+  if (warps_per_sm) *warps_per_sm = L.warps;
   if (smem_bytes_per_warp) *smem_bytes_per_warp = L.sm.total_bytes;
   return CILQR_OK;
 }

@@ -1,15 +1,22 @@
 // cilqr_kernel.cuh -- device code of the batched CILQR solver (sm_100a).
 //
-// One warp (= one 32-thread CTA) solves one scenario at a time; a persistent grid pulls scenario
-// ids from an atomic ticket because iteration counts are ragged.  The whole horizon of the
-// iterate (x, u), the feedback gains (K, k), the lane segments and a 32-knot window of the
-// linearisation (A, B, Jx, Ju, Hx, Hu) are staged in shared memory; the shrunk + normalised
-// corridor half-planes and the eleven line-search candidates live in a per-CTA global workspace
-// ([plane|candidate][component][knot], so that lane == knot accesses are coalesced) that stays
-// L2 resident.  The line search is speculative: lane a rolls out step size alpha_a, so one serial
-// pass over the horizon produces all eleven candidates of ilqr_optimizer.cc:246-265; their costs
-// are then evaluated in the reference's order (lane == knot) until the first one is accepted.  All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>);
-// B200 has a full-rate FP64 pipe (64 lanes/clk/SM), no tensor cores are involved.
+// One warp solves one trajectory phase at a time.  A persistent grid of one CTA per SM (W warps)
+// owns C > W scenario CONTEXTS that live in a global workspace (L2 / HBM): shrunk corridor planes,
+// five trajectory slots (the iterate and four line-search candidates), feedback gains, lane
+// segments, nearest-segment indices and a small header with the solver scalars.  The solve of a
+// scenario is cut into PHASES -- INIT (load, shrink, LQR gains), BACK (linearise + Riccati), ROLL
+// (speculative rollout of four step sizes), EVAL (cost of one candidate + accept/reject logic) --
+// and in every round the CTA runs ONE phase type: the type with the most waiting contexts is chosen
+// and each warp takes one of them.  Reason (measured): a B200 SM feeds
+// unaligned instruction streams at full rate only while their combined hot code fits ~32 KB; the
+// whole solver is ~75 KB of fp64 code, so free-running warps at different phases are
+// instruction-fetch bound at 1 warp per scheduler (issue 20 %, identical from 4 to 12 warps/SM),
+// while warps that run the same phase together scale (2.7x at 12 warps/SM).  With contexts in global
+// memory the shared-memory stage per warp is only what the running phase needs (lane segments +
+// heading table for EVAL, a linearisation window + Riccati scratch for BACK, a cp.async ring of
+// gains / nominal trajectory for ROLL), so 12-16 warps fit at any horizon.
+//
+// All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>); no tensor cores.
 //
 // Reference functions re-created here (file:line relative to the reference root):
 //   ShrinkConstraints / NormalizeHalfPlane   algorithm/ilqr/ilqr_optimizer.cc:438-495
@@ -34,16 +41,34 @@ constexpr int kNX = 6;
 constexpr int kNU = 2;
 constexpr int kDisc = 5;
 constexpr int kNAlpha = 11;
-constexpr int kLinStride = 37;  // doubles per knot in the linearisation window
-constexpr int kSegStride = 10;  // sx sy ex ey ux uy len a b c
-constexpr int kGroup = 8;       // lane segments per bounding-circle group of the pruned nearest search
-constexpr int kScratch = 192;   // doubles of per-warp scratch
+constexpr int kSpec = 4;          // step sizes rolled out speculatively per ROLL phase
+constexpr int kTrajSlots = kSpec + 1;  // iterate + candidates
+constexpr int kLinStride = 37;    // doubles per knot in the linearisation window
+constexpr int kSegStride = 10;    // sx sy ex ey ux uy len a b c
+constexpr int kGainStride = 16;   // K (2x6), k (2), pad (2): one 128-byte record per knot
+constexpr int kRollChunk = 4;     // knots per cp.async stage of the rollout ring
+constexpr int kRingDoubles = 2 * (8 * kRollChunk + kGainStride * kRollChunk);
+#ifndef CILQR_GROUP
+#define CILQR_GROUP 4
+#endif
+constexpr int kGroup = CILQR_GROUP;  // lane segments per bounding-circle group of the pruned nearest search
+constexpr int kScratch = 192;     // doubles of per-warp Riccati scratch
+constexpr int kPlaneKnots = 8;    // knots per staged tile of corridor planes
+constexpr int kPlaneTile = 3 * kPlaneKnots;  // doubles per plane (a, b, c rows) in a tile; x M_max per buffer
+constexpr int kHdrDoubles = 24;   // sizeof(CtxHdr) / 8
+constexpr int kMaxCtx = 64;       // contexts per CTA (two ballots)
+constexpr unsigned kFull = 0xffffffffu;
 #ifndef CILQR_LIN_WINDOW
-#define CILQR_LIN_WINDOW 32
+#define CILQR_LIN_WINDOW 16
 #endif
 constexpr int kWin = CILQR_LIN_WINDOW;  // knots per linearisation window (<= 32: lane == knot inside a window)
 static_assert(kWin >= 1 && kWin <= 32, "linearisation window is at most one knot per lane");
-constexpr unsigned kFull = 0xffffffffu;
+#ifndef CILQR_CTA_WARPS
+#define CILQR_CTA_WARPS 12
+#endif
+constexpr int kCtaWarps = CILQR_CTA_WARPS;  // warps per CTA (one CTA per SM)
+
+enum Phase : int { PH_INIT = 0, PH_BACK = 1, PH_ROLL = 2, PH_EVAL = 3, PH_DONE = 4 };
 
 // linearisation record offsets
 constexpr int LA = 0;    // A02 A03 A04 A05 A12 A13 A14 A15 A23 A24 A25
@@ -56,11 +81,11 @@ constexpr int LZ = 31;   // constants 0, 1, dt, dt^2/2 so that A, B, H can be ga
 constexpr int LO = 32;
 constexpr int LDT = 33;
 constexpr int LB30 = 34;
-constexpr int LSN = 35;   // sin, cos of the heading (consumed by linearize_discs)
+constexpr int LSN = 35;  // sin, cos of the heading (consumed by linearize_discs)
 constexpr int LCS = 36;
 
 struct DevParams {
-  double dt, L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
+  double dt, L, inv_L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
   double vmax, amin, amax, dmin, dmax, jmin, jmax, drmin, drmax;
   double wx, wy, wth, wv, wa, wd, wj, wdr;
   double abs_tol, rel_tol;
@@ -69,11 +94,38 @@ struct DevParams {
   int max_iter;
 };
 
-struct SmemLayout {  // offsets in doubles from the start of dynamic shared memory
-  int X, U, Kg, kg, lin, seg, grp, scr, nidx;  // nidx: two byte arrays of nidx_bytes each
-  int nidx_bytes;
+// Per-warp shared-memory stage, offsets in doubles.  Phases alias each other's regions:
+//   EVAL: seg, grp, trig, pl_e   BACK: lin, scr, pl_b   ROLL: ring   INIT: seg, grp (built here), scr
+// pl_*: two buffers of M_max * kPlaneTile doubles, the cp.async double buffer of corridor-plane tiles
+struct SmemLayout {
+  int seg, grp, trig, lin, scr, ring, pl_e, pl_b;
   int total_bytes;
 };
+
+// One scenario context in the global workspace, offsets in doubles from the context base.
+struct CtxLayout {
+  int planes;  // [M_max][3][Kc]    shrunk + normalised half-planes, knot-minor
+  int slots;   // [5][8][Kc]        trajectories x0..x5,u0,u1 component-major (lane == knot coalesces)
+  int gains;   // [Npad][16]        K (2x6 row-major), k (2), pad
+  int seg;     // [S_left+S_right][10]
+  int grp;     // [groups][3]       bounding circles cx, cy, r
+  int nidx;    // 2 byte arrays [K][5][2] of nearest-segment indices
+  int hdr;     // CtxHdr
+  int nidx_bytes;
+  int stride;  // doubles per context
+};
+
+// Solver scalars of one context (the locals of IlqrOptimizer::Optimize, ilqr_optimizer.cc:182-199).
+struct CtxHdr {
+  double lambda, dlambda, cost_old, dV0, dV1;
+  double cost_acc[5];
+  double g0[6];              // goals_[0] = (x0, y0, theta0, v0, 0, 0)     :151
+  unsigned int b, ahash;     // scenario id, FNV-1a over the line-search outcome per iteration
+  int iter, status, cur, nflip, ai, gb, rmode, emode, n_cost, n_iter_traj;
+  unsigned int retired, deferred;  // line-search lanes whose rollout blew up / needs the general wrap
+  int pad_[2];
+};
+static_assert(sizeof(CtxHdr) == kHdrDoubles * 8, "CtxHdr size");
 
 struct DebugPtrs {
   double *corridor, *lanes, *X0, *U0, *cost0, *A11, *Jx, *Ju, *Hx, *Hu, *Kg, *kg, *dV, *Xn, *Un, *costn;
@@ -83,8 +135,9 @@ struct DebugPtrs {
 struct KernelArgs {
   DevParams P;
   SmemLayout sm;
-  int B, N, M_max, S_left, S_right, Kp, Kc;  // Kp / Kc: knot pitch of the plane / candidate arrays
-  size_t ws_stride;  // doubles of workspace per CTA: M_max*3*Kp planes + kNAlpha*8*Kc candidates
+  CtxLayout cl;
+  int B, N, M_max, S_left, S_right, Kc;  // Kc: knot pitch of the plane / trajectory arrays
+  int ctx_per_cta;
   const double* start;
   const double* coarse;
   const double* corridor;
@@ -102,10 +155,10 @@ struct KernelArgs {
   double* iter_controls;
   int32_t* hist_len;
   int hist_cap;
-  double* ws;           // [gridDim.x][ws_stride]
-  unsigned int* ticket; // scenario counter
+  double* ws;            // [gridDim.x][ctx_per_cta][cl.stride]
+  unsigned int* ticket;  // scenario counter
   DebugPtrs dbg;
-  int debug;            // 1: stop after the first iteration and dump stages
+  int debug;             // 1: stop after the first line-search evaluation and dump stages
 };
 
 __constant__ double kAlphaList[kNAlpha] = {1.0000, 0.5012, 0.2512, 0.1259, 0.0631, 0.0316,
@@ -156,17 +209,19 @@ __device__ __forceinline__ double normalize_angle(double angle) {
 }
 
 // vehicle_model.cc:88-138: midpoint RK2, same control at both stages, wrap theta and delta.
+// Division by the wheel base is a multiplication by its reciprocal (bit-identical for the
+// reference's L_w = 1.0, vehicle_param.h:30; <= 1 ulp otherwise).
 // (theta enters k1 only through k1x, k1y, which the midpoint step never uses.)
 __device__ __forceinline__ void rollout_step(const DevParams& P, double* x, double u0, double u1, bool allow_general,
                                              bool& slow) {
   const double de = wrap_angle(x[5], allow_general, slow);
-  const double k1t = x[3] * nt_tan(de) / P.L;
+  const double k1t = x[3] * nt_tan(de) * P.inv_L;
   const double h = 0.5 * P.dt;
   const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
   const double thm = wrap_angle(m2, allow_general, slow);
   const double dem = wrap_angle(m5, allow_general, slow);
   const double2 sc = nt_sincos(thm);
-  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * nt_tan(dem) / P.L;
+  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * nt_tan(dem) * P.inv_L;
   x[0] = x[0] + P.dt * k2x;
   x[1] = x[1] + P.dt * k2y;
   x[2] = wrap_angle(x[2] + P.dt * k2t, allow_general, slow);
@@ -178,13 +233,13 @@ __device__ __forceinline__ void rollout_step(const DevParams& P, double* x, doub
 // vehicle_model.cc:21-86.  Writes the 11 state-dependent entries of A and B(2,1).
 __device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double* x, double u1,
                                                double* A11, double* b21) {
-  const double L = P.L, dt = P.dt;
+  const double iL = P.inv_L, dt = P.dt;
   const double v = x[3];
   const double theta = normalize_angle(x[2]);
   const double delta = normalize_angle(x[5]);
   const double a = x[4];
   const double tan_delta = nt_tan(delta);
-  const double theta_mid = theta + 0.5 * dt * v * tan_delta / L;
+  const double theta_mid = theta + 0.5 * dt * v * tan_delta * iL;
   const double tan_dr = nt_tan(delta + 0.5 * dt * u1);
   const double2 scm = nt_sincos(theta_mid);
   const double sm = scm.x, cm = scm.y;
@@ -192,17 +247,17 @@ __device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double*
   const double tr2 = tan_dr * tan_dr;
   const double vm = 0.5 * a * dt + v;
   A11[0] = -dt * vm * sm;
-  A11[1] = dt * cm - 0.5 * dt * dt * vm * sm * tan_delta / L;
+  A11[1] = dt * cm - 0.5 * dt * dt * vm * sm * tan_delta * iL;
   A11[2] = 0.5 * dt * dt * cm;
-  A11[3] = -0.5 * dt * dt * v * vm * (td2 + 1) * sm / L;
+  A11[3] = -0.5 * dt * dt * v * vm * (td2 + 1) * sm * iL;
   A11[4] = dt * vm * cm;
-  A11[5] = dt * sm + 0.5 * dt * dt * vm * cm * tan_delta / L;
+  A11[5] = dt * sm + 0.5 * dt * dt * vm * cm * tan_delta * iL;
   A11[6] = 0.5 * dt * dt * sm;
-  A11[7] = 0.5 * dt * dt * v * vm * (td2 + 1) * cm / L;
-  A11[8] = dt * tan_dr / L;
-  A11[9] = 0.5 * dt * dt * tan_dr / L;
-  A11[10] = dt * (v * (tr2 + 1)) / L;
-  *b21 = 0.5 * dt * dt * v * (tr2 + 1) / L;
+  A11[7] = 0.5 * dt * dt * v * vm * (td2 + 1) * cm * iL;
+  A11[8] = dt * tan_dr * iL;
+  A11[9] = 0.5 * dt * dt * tan_dr * iL;
+  A11[10] = dt * (v * (tr2 + 1)) * iL;
+  *b21 = 0.5 * dt * dt * v * (tr2 + 1) * iL;
 }
 
 // Barrier value accumulator: sum of -rt*log(-g) over the log branch is -rt*log(prod(-g)).
@@ -248,19 +303,66 @@ __device__ __forceinline__ double seg_dist2(const double* sg, double px, double 
   return d;
 }
 
+// ---- cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass registers and L1
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// What one warp needs to run one phase of one context.
 struct Ctx {
   const KernelArgs& a;
-  double* sm;
+  double* sm;   // this warp's shared-memory stage
+  double* cx;   // this context in the global workspace
+  CtxHdr* h;
   int lane;
-  // scenario
-  const double* goals;  // global [K][6] (row 0 is replaced by g0)
-  double g0[6];
+  bool seg_staged;      // this warp's stage already holds the context's lane segments (chained EVALs)
+  const double* goals;  // global [K][6] (row 0 is replaced by h->g0)
   const int32_t* cnt;   // global [K]
-  double* ws;           // global workspace of this CTA: planes [M_max][3][Kp]
-  double* cand;         // ... followed by the candidates [kNAlpha][8][Kc]: x0..x5, u0, u1
-  __device__ Ctx(const KernelArgs& a_, double* s) : a(a_), sm(s) {}
-  __device__ __forceinline__ double goal(int k, int c) const { return k == 0 ? g0[c] : goals[k * 6 + c]; }
+  __device__ Ctx(const KernelArgs& a_, double* s, double* c, int l)
+      : a(a_), sm(s), cx(c), h(reinterpret_cast<CtxHdr*>(c + a_.cl.hdr)), lane(l), seg_staged(false), goals(nullptr), cnt(nullptr) {}
+  __device__ __forceinline__ void bind(unsigned b) {
+    goals = a.coarse + (size_t)b * (a.N + 1) * 6;
+    cnt = a.corridor_cnt + (size_t)b * (a.N + 1);
+  }
+  __device__ __forceinline__ double goal(int k, int c) const { return k == 0 ? h->g0[c] : goals[k * 6 + c]; }
+  __device__ __forceinline__ double* planes() const { return cx + a.cl.planes; }
+  __device__ __forceinline__ double* slot(int i) const { return cx + a.cl.slots + i * 8 * a.Kc; }
+  __device__ __forceinline__ double* gains() const { return cx + a.cl.gains; }
+  __device__ __forceinline__ double* gseg() const { return cx + a.cl.seg; }
+  __device__ __forceinline__ double* ggrp() const { return cx + a.cl.grp; }
+  __device__ __forceinline__ unsigned char* nidx(int i) const {
+    return reinterpret_cast<unsigned char*>(cx + a.cl.nidx) + i * a.cl.nidx_bytes;
+  }
 };
+// physical trajectory slot of line-search candidate `ai` while slot `cur` holds the iterate
+__device__ __forceinline__ int cand_slot(int cur, int ai) {
+  const int s = cur + 1 + (ai & (kSpec - 1));
+  return s >= kTrajSlots ? s - kTrajSlots : s;
+}
+
+// Corridor planes of knots [k_lo, k_lo + nk), planes m < Mrows: context (global, [m][a|b|c][knot]) ->
+// shared tile buf[(m * 3 + comp) * kPlaneKnots + knot - k_lo] by cp.async, one commit group.  The
+// consumer overlaps the copy of the next tile with the arithmetic of the current one, so the inner
+// loops never wait on L2 / HBM.
+__device__ __forceinline__ void stage_planes(const Ctx& c, double* buf, int k_lo, int nk, int Mrows) {
+  const double* src = c.planes() + k_lo;
+  const int total = Mrows * kPlaneTile;
+  for (int e = c.lane; e < total; e += 32) {
+    const int row = e / kPlaneKnots, kk = e - row * kPlaneKnots;
+    if (kk < nk) cp_async8(buf + e, src + row * c.a.Kc + kk);
+  }
+  cp_async_commit();
+}
 
 // ------------------------------------------------------------------------------------------
 // Nearest lane segment of one disc centre (FindNeastLaneSegment, ilqr_optimizer.cc:605-618) without
@@ -296,20 +398,21 @@ __device__ __forceinline__ int nearest_segment(const double* sg0, const double* 
 }
 
 // ------------------------------------------------------------------------------------------
-// TotalCost of (Xs, Us) (ilqr_optimizer.cc:417-436) in two passes over the candidate block Xs of the
-// global workspace ([8][Kc]: x0..x5, u0, u1):
+// TotalCost of the trajectory in slot Xs (ilqr_optimizer.cc:417-436), [8][Kc]: x0..x5, u0, u1, in two
+// passes:
 //   pass 1, lane == knot:          JCost + DynamicsCost (:497-551), sin/cos of the heading -> trig
 //   pass 2, lane == (knot, disc):  CorridorCost + LaneBoundaryCost (:553-603) of ONE disc per lane
 // (one disc per lane keeps the code five times smaller than a disc-unrolled knot-per-lane body and
 // fills 505 of 512 lane slots at K = 101 instead of 101 of 128).  Also records the nearest lane
 // segment of every (knot, disc, side) in nidx for the linearisation that follows an accepted step.
+// The lane segments / group circles must have been staged in shared memory (stage_segments).
 __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const unsigned char* guess,
                                        unsigned char* nidx, double cost5[5]) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
   const double* seg = c.sm + a.sm.seg;
-  double* trig = c.sm + a.sm.lin;  // [K][2] sin, cos (the linearisation window is idle here)
+  double* trig = c.sm + a.sm.trig;  // [K][2] sin, cos
   double sum_j = 0.0, sum_d = 0.0, sum_c = 0.0, sum_l = 0.0;
 #pragma unroll 1
   for (int k = c.lane; k < K; k += 32) {
@@ -342,8 +445,35 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   const int items = K * kDisc;
   const int ngl = (a.S_left + kGroup - 1) / kGroup;
   const double* grp = c.sm + a.sm.grp;
+  double* pbuf = c.sm + a.sm.pl_e;
+  const int pstride = a.M_max * kPlaneTile;
+  // tile of chunk j0: knots j0/5 .. (j0+31)/5 (at most kPlaneKnots), planes below the chunk's largest count
+  auto chunk_M = [&](int j0) {
+    const int j = j0 + c.lane;
+    return j < items ? c.cnt[j / kDisc] : 0;
+  };
+  auto chunk_stage = [&](int j0, int Mw, int s) {
+    const int k_lo = j0 / kDisc;
+    int k_hi = (j0 + 31) / kDisc;
+    k_hi = k_hi < K ? k_hi : K - 1;
+    stage_planes(c, pbuf + s * pstride, k_lo, k_hi - k_lo + 1, Mw);
+  };
+  int M = chunk_M(0);
+  int Mw = __reduce_max_sync(kFull, M);
+  chunk_stage(0, Mw, 0);
+  int stage = 0;
 #pragma unroll 1
-  for (int j0 = 0; j0 < items; j0 += 32) {
+  for (int j0 = 0; j0 < items; j0 += 32, stage ^= 1) {
+    int M_next = 0, Mw_next = 0;
+    if (j0 + 32 < items) {
+      M_next = chunk_M(j0 + 32);
+      Mw_next = __reduce_max_sync(kFull, M_next);
+      chunk_stage(j0 + 32, Mw_next, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
     const int j = j0 + c.lane;
     const bool act = j < items;
     const int jj = act ? j : items - 1;
@@ -352,14 +482,12 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     const double xd = fma(o, trig[k * 2 + 1], Xs[k]);
     const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
     // corridor half-planes of this knot
-    const int M = act ? c.cnt[k] : 0;
-    const int Mw = __reduce_max_sync(kFull, M);
     BarAcc bc = {1.0, 0.0};
-    const double* w = c.ws + k;
+    const double* w = pbuf + stage * pstride + (k - j0 / kDisc);
 #pragma unroll 4
     for (int m = 0; m < Mw; ++m) {
       if (m < M) {
-        const double pa = w[(m * 3 + 0) * a.Kp], pb = w[(m * 3 + 1) * a.Kp], pc = w[(m * 3 + 2) * a.Kp];
+        const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
         bar_add(bc, fma(pb, yd, pa * xd) - pc, P);
       }
     }
@@ -379,6 +507,9 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
       sum_c += tc;
       sum_l += tl;
     }
+    __syncwarp();  // the tile is dead: the next iteration's prefetch may overwrite it
+    M = M_next;
+    Mw = Mw_next;
   }
   const double j = warp_sum(sum_j), d = warp_sum(sum_d), co = warp_sum(sum_c), la = warp_sum(sum_l);
   cost5[0] = j + d + co + la;
@@ -391,15 +522,18 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
 // ------------------------------------------------------------------------------------------
 // CostJacbian + CostHessian + DynamicsJacbian (ilqr_optimizer.cc:620-769, vehicle_model.cc:21-86) of one
 // window of knots -> 37-double records, in two passes:
-//   linearize_knot, lane == knot:        A, B, the running-cost and bound-barrier terms, sin/cos heading
+//   linearize_knot, lane == knot:          A, B, the running-cost and bound-barrier terms, sin/cos heading
 //   linearize_discs, lane == (disc, knot): corridor and lane-boundary barrier terms of ONE disc per lane,
-//                                        reduced over the five disc lanes of a knot by shuffles
-__device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const double* Us, double* rec) {
+//                                          reduced over the five disc lanes of a knot by shuffles
+// Xs is the iterate's slot ([8][Kc], component-major, global).
+__device__ void linearize_knot(const Ctx& c, int k, const double* Xs, double* rec) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int N = a.N;
-  const double* x = Xs + k * 6;
-  const double u0 = k < N ? Us[k * 2] : 0.0, u1 = k < N ? Us[k * 2 + 1] : 0.0;
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k];
+  const double u0 = k < N ? Xs[6 * a.Kc + k] : 0.0, u1 = k < N ? Xs[7 * a.Kc + k] : 0.0;
   if (k < N) {
     double A11[11], b21;
     dynamics_jacobian(P, x, u1, A11, &b21);
@@ -407,28 +541,30 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, const doub
     for (int i = 0; i < 11; ++i) rec[LA + i] = A11[i];
     rec[LB21] = b21;
   }
-  double cj0, cj1, co0, co1, cd;
   // DynamicsConsJacbian / Hessian: each state (control) component carries a pair of bounds
-  bar_coef(0.0 - x[3], P, cj0, co0, cd);
-  bar_coef(x[3] - P.vmax, P, cj1, co1, cd);
-  rec[LJX + 3] = cj1 - cj0;
-  rec[LHX + 6] = 2.0 * P.wv + (co0 + co1);
-  bar_coef(P.amin - x[4], P, cj0, co0, cd);
-  bar_coef(x[4] - P.amax, P, cj1, co1, cd);
-  rec[LJX + 4] = cj1 - cj0;
-  rec[LHX + 7] = 2.0 * P.wa + (co0 + co1);
-  bar_coef(P.dmin - x[5], P, cj0, co0, cd);
-  bar_coef(x[5] - P.dmax, P, cj1, co1, cd);
-  rec[LJX + 5] = cj1 - cj0;
-  rec[LHX + 8] = 2.0 * P.wd + (co0 + co1);
-  bar_coef(P.jmin - u0, P, cj0, co0, cd);
-  bar_coef(u0 - P.jmax, P, cj1, co1, cd);
-  rec[LJU + 0] = 2.0 * P.wj * u0 + (cj1 - cj0);
-  rec[LHU + 0] = 2.0 * P.wj + (co0 + co1);
-  bar_coef(P.drmin - u1, P, cj0, co0, cd);
-  bar_coef(u1 - P.drmax, P, cj1, co1, cd);
-  rec[LJU + 1] = 2.0 * P.wdr * u1 + (cj1 - cj0);
-  rec[LHU + 1] = 2.0 * P.wdr + (co0 + co1);
+  auto bound_pair = [&](double lo_g, double hi_g, double& dj, double& dh) {
+    double cj0, cj1, co0, co1, cd;
+    bar_coef(lo_g, P, cj0, co0, cd);
+    bar_coef(hi_g, P, cj1, co1, cd);
+    dj = cj1 - cj0;
+    dh = co0 + co1;
+  };
+  double dj, dh;
+  bound_pair(0.0 - x[3], x[3] - P.vmax, dj, dh);
+  rec[LJX + 3] = dj;
+  rec[LHX + 6] = 2.0 * P.wv + dh;
+  bound_pair(P.amin - x[4], x[4] - P.amax, dj, dh);
+  rec[LJX + 4] = dj;
+  rec[LHX + 7] = 2.0 * P.wa + dh;
+  bound_pair(P.dmin - x[5], x[5] - P.dmax, dj, dh);
+  rec[LJX + 5] = dj;
+  rec[LHX + 8] = 2.0 * P.wd + dh;
+  bound_pair(P.jmin - u0, u0 - P.jmax, dj, dh);
+  rec[LJU + 0] = 2.0 * P.wj * u0 + dj;
+  rec[LHU + 0] = 2.0 * P.wj + dh;
+  bound_pair(P.drmin - u1, u1 - P.drmax, dj, dh);
+  rec[LJU + 1] = 2.0 * P.wdr * u1 + dj;
+  rec[LHU + 1] = 2.0 * P.wdr + dh;
   const double2 scth = nt_sincos(x[2]);
   rec[LSN] = scth.x;
   rec[LCS] = scth.y;
@@ -456,17 +592,38 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
                                 double* lin) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
-  const double* seg = c.sm + a.sm.seg;
+  const double* seg = c.gseg();  // only (a, b, c) of ten segments per knot: read from the context
+  double* pbuf = c.sm + a.sm.pl_b;
+  const int pstride = a.M_max * kPlaneTile;
   const int d = c.lane / kKnotsPerPass, kl = c.lane - d * kKnotsPerPass;
+  auto pass_M = [&](int g0) { return (d < kDisc && g0 + kl < nk) ? c.cnt[k0 + g0 + kl] : 0; };
+  auto pass_stage = [&](int g0, int Mw, int s) {
+    const int n = nk - g0 < kKnotsPerPass ? nk - g0 : kKnotsPerPass;
+    stage_planes(c, pbuf + s * pstride, k0 + g0, n, Mw);
+  };
+  int M = pass_M(0);
+  int Mw = __reduce_max_sync(kFull, M);
+  pass_stage(0, Mw, 0);
+  int stage = 0;
 #pragma unroll 1
-  for (int g0 = 0; g0 < nk; g0 += kKnotsPerPass) {
+  for (int g0 = 0; g0 < nk; g0 += kKnotsPerPass, stage ^= 1) {
+    int M_next = 0, Mw_next = 0;
+    if (g0 + kKnotsPerPass < nk) {
+      M_next = pass_M(g0 + kKnotsPerPass);
+      Mw_next = __reduce_max_sync(kFull, M_next);
+      pass_stage(g0 + kKnotsPerPass, Mw_next, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
     const bool act = d < kDisc && g0 + kl < nk;
     const int ko = act ? g0 + kl : 0;  // knot inside the window
     const int k = k0 + ko;
     double* rec = lin + ko * kLinStride;
     const double sn = rec[LSN], cs = rec[LCS];
     const double o = P.off[act ? d : 0];
-    const double xd = fma(o, cs, Xs[k * 6]), yd = fma(o, sn, Xs[k * 6 + 1]);
+    const double xd = fma(o, cs, Xs[k]), yd = fma(o, sn, Xs[a.Kc + k]);
     double J0 = 0.0, J1 = 0.0, J2 = 0.0, H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
     auto plane = [&](double pa, double pb, double pc) {
       const double g = fma(pb, yd, pa * xd) - pc;
@@ -486,12 +643,10 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
       H22 = fma(to, to * co, H22);
       H22 = fma(wo, cdd, H22);
     };
-    const int M = act ? c.cnt[k] : 0;
-    const int Mw = __reduce_max_sync(kFull, M);
-    const double* w = c.ws + k;
+    const double* w = pbuf + stage * pstride + (act ? kl : 0);
 #pragma unroll 2
     for (int m = 0; m < Mw; ++m) {
-      if (m < M) plane(w[(m * 3 + 0) * a.Kp], w[(m * 3 + 1) * a.Kp], w[(m * 3 + 2) * a.Kp]);
+      if (m < M) plane(w[m * kPlaneTile], w[m * kPlaneTile + kPlaneKnots], w[m * kPlaneTile + 2 * kPlaneKnots]);
     }
     if (act) {
 #pragma unroll 1
@@ -528,7 +683,9 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
       rec[LHX + 4] += H12;
       rec[LHX + 5] += H22;
     }
-    __syncwarp();
+    __syncwarp();  // records updated; the tile is dead
+    M = M_next;
+    Mw = Mw_next;
   }
 }
 
@@ -589,15 +746,14 @@ constexpr int SQL = 162;  // 8   ql
 constexpr int SKH = 170;  // 14  Kh  [2][7]
 static_assert(SKH + 14 <= SK, "scratch overflow");
 
-__device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, const double* Us,
-                              const unsigned char* nidx, double dV[2], const DebugPtrs* dbg, int b) {
+__device__ __noinline__ void backward_pass(const Ctx& c, double lambda, const double* Xs, const unsigned char* nidx,
+                                           double dV[2], const DebugPtrs* dbg, int b) {
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
   double* lin = c.sm + a.sm.lin;
   double* scr = c.sm + a.sm.scr;
-  double* Kg = c.sm + a.sm.Kg;
-  double* kg = c.sm + a.sm.kg;
+  double* gains = c.gains();  // global: K, k of every knot are consumed by the next ROLL phase
   double* M = scr + SM_;
   double* G = scr + SG;
   double* Qh = scr + SQH;
@@ -656,7 +812,7 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
     const int k = k0 + lane;
     const bool lin_lane = lane < kWin && k < K;
     __syncwarp();
-    if (lin_lane) linearize_knot(c, k, Xs, Us, lin + lane * kLinStride);
+    if (lin_lane) linearize_knot(c, k, Xs, lin + lane * kLinStride);
     __syncwarp();
     linearize_discs(c, k0, (K - k0 < kWin ? K - k0 : kWin), Xs, nidx, lin);
     if (dbg) {
@@ -734,8 +890,7 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
         const double b1 = j < 6 ? Qh[j * 8 + 7] : ql[7];
         const double kv = fma(n1, b1, n0 * b0);
         Kh[lane] = kv;
-        if (j < 6) Kg[kn * 12 + rr * 6 + j] = kv;
-        else kg[kn * 2 + rr] = kv;
+        gains[kn * kGainStride + (j < 6 ? rr * 6 + j : 12 + rr)] = kv;
       }
       __syncwarp();
       // ---- S4: M' and the delta_V contributions
@@ -772,10 +927,12 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
   dV[1] = warp_sum(acc1);
 }
 
-// Rollout of the closed loop u_k = ubar_k + K_k (x - xbar_k) + alpha k_k for several step sizes of the
-// line search at once (Forward, ilqr_optimizer.cc:392-415): lane a with bit a of `want` set rolls out
-// alpha_a and writes its candidate to the global workspace (the other lanes shadow the highest
-// wanted lane and store nothing).  The same code produces the LQR initial guess (iqr,
+// Rollout of the closed loop u_k = ubar_k + K_k (x - xbar_k) + alpha k_k for up to four step sizes of
+// the line search at once (Forward, ilqr_optimizer.cc:392-415): lane a < 4 with bit a of `want` set
+// rolls out alpha_{gb+a} and writes its candidate to trajectory slot cand_slot(cur, a) (the other
+// lanes shadow the highest wanted lane and store nothing).  The nominal trajectory (slot `cur`) and
+// the gains stream from the context through a two-stage cp.async ring of kRollChunk knots, so the
+// serial loop only reads shared memory.  The same code produces the LQR initial guess (iqr,
 // ilqr_optimizer.cc:830-841) when called with iqr = true on (xbar, ubar, K, k) = (goals, 0, -K_lqr, 0):
 // the control is then clamped to its bounds instead of angle-wrapped.
 //  * A lane whose state stops being finite is RETIRED: every later state of that rollout would be
@@ -785,95 +942,107 @@ __device__ void backward_pass(const Ctx& c, double lambda, const double* Xs, con
 //    blown-up rollout -- is DEFERRED instead of dragging the whole warp through that branch at every
 //    step; the caller repeats deferred step sizes with allow_general = true only if the line search
 //    gets to them.
-// Returns retired | deferred << 16.
-__device__ __noinline__ unsigned rollout(const Ctx& c, const double* Xs, const double* Us, unsigned want,
-                                         bool allow_general, bool iqr) {
+// Returns retired | deferred << 16 (bit a = candidate a of this group).
+__device__ __noinline__ unsigned rollout(const Ctx& c, int cur, unsigned want, int gb, bool allow_general, bool iqr) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
-  const double* Kg = c.sm + a.sm.Kg;
-  const double* kg = c.sm + a.sm.kg;
-  const bool owner = (want >> c.lane) & 1u;
-  const int slot = owner ? c.lane : 31 - __clz(want);
-  const double alpha = kAlphaList[slot];
-  double* out = c.cand + (size_t)slot * 8 * a.Kc;
+  const int lane = c.lane;
+  const double* Xs = c.slot(cur);
+  const double* gains = c.gains();
+  double* ring = c.sm + a.sm.ring;
+  constexpr int kStage = 8 * kRollChunk + kGainStride * kRollChunk;  // doubles per ring stage
+  const bool owner = (want >> lane) & 1u;
+  const int ca = owner ? lane : 31 - __clz(want);
+  const double alpha = kAlphaList[gb + ca];
+  double* out = c.slot(cand_slot(cur, ca));
   double x[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = c.g0[i];
+  for (int i = 0; i < 6; ++i) x[i] = c.h->g0[i];
   if (owner) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) out[i * a.Kc] = x[i];
   }
+  // stage s of the ring: [8][kRollChunk] nominal x0..x5,u0,u1 then [kRollChunk][16] gain records
+  auto prefetch = [&](int k0, int s) {
+    double* st = ring + s * kStage;
+    if (lane < 4 * kRollChunk) {  // 8 components x kRollChunk doubles = 4*kRollChunk 16-byte pieces
+      const int comp = lane / (kRollChunk / 2), part = lane - comp * (kRollChunk / 2);
+      cp_async16(st + comp * kRollChunk + part * 2, Xs + comp * a.Kc + k0 + part * 2);
+    }
+#pragma unroll
+    for (int i = lane; i < kGainStride * kRollChunk / 2; i += 32)
+      cp_async16(st + 8 * kRollChunk + i * 2, gains + (size_t)k0 * kGainStride + i * 2);
+    cp_async_commit();
+  };
   bool dead = false, defer = false, slow = false;
-  for (int k = 0; k < a.N; ++k) {
-    const double* Kk = Kg + k * 12;
-    const double* xb = Xs + k * 6;
-    double dx[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dx[i] = x[i] - xb[i];
-    double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
-#pragma unroll
-    for (int i = 1; i < 6; ++i) {
-      s0 = fma(Kk[i], dx[i], s0);
-      s1 = fma(Kk[6 + i], dx[i], s1);
-    }
-    double u0 = Us[k * 2] + s0 + alpha * kg[k * 2];
-    double u1 = Us[k * 2 + 1] + s1 + alpha * kg[k * 2 + 1];
-    if (iqr) {
-      u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
-      u1 = fmin(P.drmax, fmax(u1, P.drmin));
+  prefetch(0, 0);
+  int stage = 0;
+  for (int k0 = 0; k0 < a.N; k0 += kRollChunk, stage ^= 1) {
+    if (k0 + kRollChunk < a.N) {
+      prefetch(k0 + kRollChunk, stage ^ 1);
+      cp_async_wait<1>();
     } else {
-      u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
+      cp_async_wait<0>();
     }
-    rollout_step(P, x, u0, u1, allow_general, slow);
-    if (!iqr && !dead && !defer) {
-      const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
-      if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
-      else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
-    }
-    if (dead || defer) {
-      // park the lane on the nominal trajectory: benign operands for the remaining steps
+    __syncwarp();
+    const double* st = ring + stage * kStage;
+    const int kn = a.N - k0 < kRollChunk ? a.N - k0 : kRollChunk;
+    for (int kk = 0; kk < kn; ++kk) {
+      const int k = k0 + kk;
+      const double* Kk = st + 8 * kRollChunk + kk * kGainStride;
+      double dx[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = Xs[(k + 1) * 6 + i];
-      slow = false;
-    } else if (owner) {
-      out[6 * a.Kc + k] = u0;
-      out[7 * a.Kc + k] = u1;
+      for (int i = 0; i < 6; ++i) dx[i] = x[i] - st[i * kRollChunk + kk];
+      double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
+      for (int i = 1; i < 6; ++i) {
+        s0 = fma(Kk[i], dx[i], s0);
+        s1 = fma(Kk[6 + i], dx[i], s1);
+      }
+      double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
+      double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
+      if (iqr) {
+        u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
+        u1 = fmin(P.drmax, fmax(u1, P.drmin));
+      } else {
+        u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
+      }
+      rollout_step(P, x, u0, u1, allow_general, slow);
+      if (!iqr && !dead && !defer) {
+        const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
+        if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
+        else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
+      }
+      if (dead || defer) {
+        // park the lane on the nominal trajectory: benign operands for the remaining steps
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k + 1];
+        slow = false;
+      } else if (owner) {
+        out[6 * a.Kc + k] = u0;
+        out[7 * a.Kc + k] = u1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
+      }
     }
+    __syncwarp();
   }
-  __syncwarp();
   const unsigned retired = __ballot_sync(kFull, dead) & want;
   const unsigned deferred = __ballot_sync(kFull, defer) & want;
   return retired | (deferred << 16);
 }
 
-// Candidate `slot` of the workspace becomes the iterate in shared memory.
-__device__ __forceinline__ void adopt(const Ctx& c, int slot, double* X, double* U) {
-  const KernelArgs& a = c.a;
-  const double* cd = c.cand + (size_t)slot * 8 * a.Kc;
-  for (int k = c.lane; k <= a.N; k += 32) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) X[k * 6 + i] = cd[i * a.Kc + k];
-    if (k < a.N) {
-      U[k * 2] = cd[6 * a.Kc + k];
-      U[k * 2 + 1] = cd[7 * a.Kc + k];
-    }
-  }
-  __syncwarp();
-}
-
 // iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control).  Leaves the
-// NEGATED gains -K_k in the gain stage (k_k = 0) and (xbar, ubar) = (goals, 0) in (Xs, Us), so that
-// rollout(..., iqr = true) evaluates u_k = clamp(-K_k (x - goal_k)) and the RK2 rollout of :830-841.
-__device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
+// NEGATED gains -K_k in the context's gain records (k_k = 0) and (xbar, ubar) = (goals, 0) in slot
+// Xs, so that rollout(..., iqr = true) evaluates u_k = clamp(-K_k (x - goal_k)) and the RK2 rollout
+// of :830-841.  A_k, B_k about the goals are parked in the gain records until the sweep consumes them.
+__device__ void iqr_gains(const Ctx& c, double* Xs) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int N = a.N, lane = c.lane;
-  double* Kg = c.sm + a.sm.Kg;
+  double* Kg = c.gains();
   double* scr = c.sm + a.sm.scr;
   const double B30 = 0.5 * P.dt * P.dt, B40 = P.dt, B51 = P.dt;
-  // A_k, B_k about the goals with zero control; parked in the gain slots until consumed
   for (int k = lane; k < N; k += 32) {
     double g[6];
 #pragma unroll
@@ -881,8 +1050,8 @@ __device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
     double A11[11], b21;
     dynamics_jacobian(P, g, 0.0, A11, &b21);
 #pragma unroll
-    for (int i = 0; i < 11; ++i) Kg[k * 12 + i] = A11[i];
-    Kg[k * 12 + 11] = b21;
+    for (int i = 0; i < 11; ++i) Kg[k * kGainStride + i] = A11[i];
+    Kg[k * kGainStride + 11] = b21;
   }
   const double Qd[6] = {0.001, 0.001, 0.001, 0.001, 0.01, 0.005};
   for (int e = lane; e < 36; e += 32) scr[SV + e] = (e / 6 == e % 6) ? Qd[e / 6] : 0.0;
@@ -894,10 +1063,11 @@ __device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
   double* Cm = scr + SQXX;   // A - B K
   double* G = scr + SQUX;    // B^T P A
   double* S4 = scr + SQUU;   // R + B^T P B
+  double* Kl = scr + ST;     // K of this knot, 2x6
   for (int k = N - 1; k >= 0; --k) {
     double rec[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) rec[i] = Kg[k * 12 + i];
+    for (int i = 0; i < 12; ++i) rec[i] = Kg[k * kGainStride + i];
     const double b21 = rec[11];
     __syncwarp();
     if (lane < 24) {
@@ -941,7 +1111,11 @@ __device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
       const double i00 = S4[3] * invdet, i01 = -S4[1] * invdet, i10 = -S4[2] * invdet, i11 = S4[0] * invdet;
       if (lane < 12) {
         const int rr = lane / 6, cc = lane % 6;
-        Kg[k * 12 + lane] = rr == 0 ? fma(i01, G[6 + cc], i00 * G[cc]) : fma(i11, G[6 + cc], i10 * G[cc]);
+        const double kv = rr == 0 ? fma(i01, G[6 + cc], i00 * G[cc]) : fma(i11, G[6 + cc], i10 * G[cc]);
+        Kl[lane] = kv;
+        Kg[k * kGainStride + lane] = -kv;  // the rollout adds K (x - xbar): store -K_lqr
+      } else if (lane < 14) {
+        Kg[k * kGainStride + lane] = 0.0;  // k_k = 0
       }
     }
     __syncwarp();
@@ -950,10 +1124,10 @@ __device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
       const int r = e / 6, j = e % 6;
       double av = (r == j ? 1.0 : 0.0) + (r < 4 ? Nf[r * 6 + j] : 0.0);
       double bk = 0.0;
-      if (r == 2) bk = b21 * Kg[k * 12 + 6 + j];
-      else if (r == 3) bk = B30 * Kg[k * 12 + j];
-      else if (r == 4) bk = B40 * Kg[k * 12 + j];
-      else if (r == 5) bk = B51 * Kg[k * 12 + 6 + j];
+      if (r == 2) bk = b21 * Kl[6 + j];
+      else if (r == 3) bk = B30 * Kl[j];
+      else if (r == 4) bk = B40 * Kl[j];
+      else if (r == 5) bk = B51 * Kl[6 + j];
       Cm[e] = av - bk;
     }
     __syncwarp();
@@ -978,384 +1152,565 @@ __device__ void iqr_gains(const Ctx& c, double* Xs, double* Us) {
     if (lane < 4) Pm[32 + lane] = pn1;
   }
   __syncwarp();
-  for (int i = lane; i < N * 12; i += 32) Kg[i] = -Kg[i];
-  double* kg = c.sm + a.sm.kg;
-  for (int i = lane; i < N * 2; i += 32) {
-    kg[i] = 0.0;
-    Us[i] = 0.0;
+  // (xbar, ubar) = (goals, 0)
+  for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Xs[i * a.Kc + k] = c.goal(k, i);
+    Xs[6 * a.Kc + k] = 0.0;
+    Xs[7 * a.Kc + k] = 0.0;
   }
-  for (int i = lane; i < (N + 1) * 6; i += 32) Xs[i] = c.goal(i / 6, i % 6);
   __syncwarp();
 }
 
 __device__ __forceinline__ unsigned fnv1a(unsigned h, unsigned byte) { return (h ^ (byte & 0xffu)) * 16777619u; }
 
-__device__ __noinline__ void copy_out(double* dst, const double* src, int n, int lane) {
+// trajectory slot ([8][Kc], component-major) -> states [K][6] and controls [N][2] (knot-major)
+__device__ __noinline__ void copy_traj(const Ctx& c, const double* Xs, double* states, double* controls) {
+  const int N = c.a.N, Kc = c.a.Kc;
 #pragma unroll 1
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  for (int k = c.lane; k <= N; k += 32) {
+    if (states) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) states[k * 6 + i] = Xs[i * Kc + k];
+    }
+    if (controls && k < N) {
+      controls[k * 2] = Xs[6 * Kc + k];
+      controls[k * 2 + 1] = Xs[7 * Kc + k];
+    }
+  }
+}
+
+// lane segments + group circles of the context -> this warp's shared-memory stage
+__device__ __forceinline__ void stage_segments(Ctx& c) {
+  const KernelArgs& a = c.a;
+  if (c.seg_staged) return;
+  c.seg_staged = true;
+  const int n16 = ((a.S_left + a.S_right) * kSegStride + 1) / 2;
+  const double* src = c.gseg();
+  double* dst = c.sm + a.sm.seg;
+  for (int i = c.lane; i < n16; i += 32) cp_async16(dst + i * 2, src + i * 2);
+  const int ng = (a.S_left + kGroup - 1) / kGroup + (a.S_right + kGroup - 1) / kGroup;
+  const int g16 = (ng * 3 + 1) / 2;
+  const double* gs = c.ggrp();
+  double* gd = c.sm + a.sm.grp;
+  for (int i = c.lane; i < g16; i += 32) cp_async16(gd + i * 2, gs + i * 2);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+}
+
+// ---- exits of Optimize (ilqr_optimizer.cc:225,238,285,303,319): results of the context -> outputs
+__device__ __noinline__ void finish_scenario(const Ctx& c) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N, K = N + 1, lane = c.lane;
+  const CtxHdr* h = c.h;
+  const size_t b = h->b;
+  const double* Xs = c.slot(h->cur);
+  copy_traj(c, Xs, a.states + b * K * 6, a.controls + b * N * 2);
+  if (lane == 0) {
+    double* st = a.status + b * 8;
+    st[0] = h->status;
+    st[1] = h->iter;
+    for (int i = 0; i < 5; ++i) st[2 + i] = h->cost_acc[i];
+    st[7] = (double)h->ahash;
+    if (a.hist_len) {
+      a.hist_len[b * 2] = h->n_cost;
+      a.hist_len[b * 2 + 1] = h->n_iter_traj;
+    }
+  }
+  if (a.trajectory) {
+    // TransformToTrajectory (:771-791): time, s, x, y, theta, kappa, velocity, a, jerk, delta, delta_rate, lb, rb
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+      double* tp = a.trajectory + (b * K + k) * 13;
+      const double de = Xs[5 * a.Kc + k];
+      tp[0] = k * P.dt;
+      tp[1] = 0.0;
+      tp[2] = Xs[k];
+      tp[3] = Xs[a.Kc + k];
+      tp[4] = Xs[2 * a.Kc + k];
+      tp[5] = nt_tan(de) / P.L;
+      tp[6] = Xs[3 * a.Kc + k];
+      tp[7] = Xs[4 * a.Kc + k];
+      tp[8] = k < N ? Xs[6 * a.Kc + k] : 0.0;
+      tp[9] = de;
+      tp[10] = k < N ? Xs[7 * a.Kc + k] : 0.0;
+      tp[11] = 0.0;
+      tp[12] = 0.0;
+    }
+  }
+}
+
+// iter_trajs.push_back (ilqr_optimizer.cc:170,294) and cost_.push_back (:173,283,296) when requested
+__device__ __forceinline__ void push_traj(const Ctx& c, const double* Xs) {
+  const KernelArgs& a = c.a;
+  CtxHdr* h = c.h;
+  const int n = h->n_iter_traj;
+  if (a.iter_states && n < a.hist_cap) {
+    const size_t o = (size_t)h->b * a.hist_cap + n;
+    copy_traj(c, Xs, a.iter_states + o * (a.N + 1) * 6, a.iter_controls ? a.iter_controls + o * a.N * 2 : nullptr);
+  }
+  __syncwarp();
+  if (c.lane == 0) h->n_iter_traj = n + 1;
+}
+__device__ __forceinline__ void push_cost(const Ctx& c, const double cost5[5]) {
+  const KernelArgs& a = c.a;
+  CtxHdr* h = c.h;
+  const int n = h->n_cost;
+  __syncwarp();
+  if (c.lane == 0) {
+    if (a.cost_hist && n < a.hist_cap)
+      for (int i = 0; i < 5; ++i) a.cost_hist[((size_t)h->b * a.hist_cap + n) * 5 + i] = cost5[i];
+    for (int i = 0; i < 5; ++i) h->cost_acc[i] = cost5[i];
+    h->n_cost = n + 1;
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
-#ifndef CILQR_MIN_BLOCKS
-#define CILQR_MIN_BLOCKS 1
-#endif
-#ifndef CILQR_CTA_WARPS
-#define CILQR_CTA_WARPS 1
-#endif
-constexpr int kCtaWarps = CILQR_CTA_WARPS;  // warps (= concurrently solved scenarios) per CTA
-__global__ void __launch_bounds__(32 * kCtaWarps, CILQR_MIN_BLOCKS) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
+// INIT: next scenario of the batch -> context.  TransformGoals (:141-152), ShrinkConstraints +
+// NormalizeHalfPlane (:438-495), LineSegment2d construction (line_segment2d.cpp:40-49), group circles,
+// LQR gains of the initial guess (:793-824).
+__device__ __noinline__ int phase_init(Ctx& c) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N, K = N + 1, lane = c.lane;
+  const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
+  unsigned int b = 0;
+  if (lane == 0) b = atomicAdd(a.ticket, 1u);
+  b = __shfl_sync(kFull, b, 0);
+  if (b >= (unsigned)a.B) return PH_DONE;
+  c.bind(b);
+  CtxHdr* h = c.h;
+  if (lane == 0) {
+    const double* st = a.start + (size_t)b * 4;
+    h->g0[0] = st[0];
+    h->g0[1] = st[1];
+    h->g0[2] = st[2];
+    h->g0[3] = st[3];
+    h->g0[4] = 0.0;
+    h->g0[5] = 0.0;
+    h->b = b;
+    h->ahash = 2166136261u;
+    h->lambda = 1.0;
+    h->dlambda = 1.0;
+    h->iter = 0;
+    h->status = 4;
+    h->cur = 0;
+    h->nflip = 0;
+    h->n_cost = 0;
+    h->n_iter_traj = 0;
+    h->rmode = 0;
+    h->emode = 0;
+    h->retired = 0;
+    h->deferred = 0;
+  }
+  __syncwarp();
+  {
+    const double* raw = a.corridor + (size_t)b * K * a.M_max * 3;
+    double* planes = c.planes();
+    const int total = K * a.M_max;
+#pragma unroll 1
+    for (int idx = lane; idx < total; idx += 32) {
+      const int k = idx / a.M_max, m = idx - k * a.M_max;
+      if (m < c.cnt[k]) {
+        const double e0 = raw[idx * 3], e1 = raw[idx * 3 + 1];
+        double e2 = raw[idx * 3 + 2];
+        e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+        const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
+        planes[(m * 3 + 0) * a.Kc + k] = e0 / nrm;
+        planes[(m * 3 + 1) * a.Kc + k] = e1 / nrm;
+        planes[(m * 3 + 2) * a.Kc + k] = e2 / nrm;
+        if (dbg && dbg->corridor) {
+          double* o = dbg->corridor + ((size_t)b * total + idx) * 3;
+          o[0] = e0 / nrm;
+          o[1] = e1 / nrm;
+          o[2] = e2 / nrm;
+        }
+      }
+    }
+    const int ST_ = a.S_left + a.S_right;
+    double* seg = c.sm + a.sm.seg;
+    double* gsg = c.gseg();
+#pragma unroll 1
+    for (int s = lane; s < ST_; s += 32) {
+      const double* ln = s < a.S_left ? a.lane_left + ((size_t)b * a.S_left + s) * 7
+                                      : a.lane_right + ((size_t)b * a.S_right + (s - a.S_left)) * 7;
+      const double e0 = ln[0], e1 = ln[1];
+      double e2 = ln[2];
+      e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+      const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
+      const double dx = ln[5] - ln[3], dy = ln[6] - ln[4];
+      const double len = nt_hypot(dx, dy);
+      double r[kSegStride];
+      r[0] = ln[3];
+      r[1] = ln[4];
+      r[2] = ln[5];
+      r[3] = ln[6];
+      r[4] = len <= 1e-10 ? 0.0 : dx / len;  // line_segment2d.cpp:40-49
+      r[5] = len <= 1e-10 ? 0.0 : dy / len;
+      r[6] = len;
+      r[7] = e0 / nrm;
+      r[8] = e1 / nrm;
+      r[9] = e2 / nrm;
+#pragma unroll
+      for (int q = 0; q < kSegStride; ++q) {
+        seg[s * kSegStride + q] = r[q];
+        gsg[s * kSegStride + q] = r[q];
+      }
+      if (dbg && dbg->lanes) {
+        double* o = dbg->lanes + ((size_t)b * ST_ + s) * 3;
+        o[0] = r[7];
+        o[1] = r[8];
+        o[2] = r[9];
+      }
+    }
+    __syncwarp();
+    // bounding circles of the segment groups (see nearest_segment)
+    const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
+    double* grp = c.ggrp();
+#pragma unroll 1
+    for (int g = lane; g < ngl + ngr; g += 32) {
+      const int side = g < ngl ? 0 : 1;
+      const int S = side == 0 ? a.S_left : a.S_right;
+      const int s_lo = (side == 0 ? g : g - ngl) * kGroup;
+      const int s_hi = s_lo + kGroup < S ? s_lo + kGroup : S;
+      const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+      double xmin = 1.7976931348623157e308, xmax = -xmin, ymin = xmin, ymax = -xmin;
+#pragma unroll 1
+      for (int s2 = s_lo; s2 < s_hi; ++s2) {
+        const double* sg = sg0 + s2 * kSegStride;
+        xmin = fmin(xmin, fmin(sg[0], sg[2]));
+        xmax = fmax(xmax, fmax(sg[0], sg[2]));
+        ymin = fmin(ymin, fmin(sg[1], sg[3]));
+        ymax = fmax(ymax, fmax(sg[1], sg[3]));
+      }
+      const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+      double r2 = 0.0;
+#pragma unroll 1
+      for (int s2 = s_lo; s2 < s_hi; ++s2) {
+        const double* sg = sg0 + s2 * kSegStride;
+        const double ax = sg[0] - cx, ay = sg[1] - cy, bx = sg[2] - cx, by = sg[3] - cy;
+        r2 = fmax(r2, fmax(ax * ax + ay * ay, bx * bx + by * by));
+      }
+      grp[g * 3] = cx;
+      grp[g * 3 + 1] = cy;
+      // radius, inflated so that rounding can only make the pruning test more conservative
+      grp[g * 3 + 2] = sqrt(r2) * (1.0 + 1e-9) + 1e-9;
+    }
+  }
+  __syncwarp();
+  iqr_gains(c, c.slot(0));
+  // no previous iterate: any valid index is an upper bound for the nearest-segment search
+  unsigned char* n0 = c.nidx(0);
+#pragma unroll 1
+  for (int i = lane; i < a.cl.nidx_bytes; i += 32) n0[i] = 0;
+  __syncwarp();
+  return PH_ROLL;
+}
+
+// ROLL: the initial-guess rollout (:830-841), the speculative rollout of one group of four step sizes
+// (:246-252), or the faithful repeat of deferred ones.
+__device__ __noinline__ int phase_roll(Ctx& c) {
+  const KernelArgs& a = c.a;
+  CtxHdr* h = c.h;
+  c.bind(h->b);
+  const int cur = h->cur, rmode = h->rmode, gb = h->gb;
+  if (rmode == 0) {
+    rollout(c, cur, 1u, 0, true, true);
+    const int ns = cand_slot(cur, 0);
+    if (a.init_states || a.init_controls) {
+      __syncwarp();
+      copy_traj(c, c.slot(ns), a.init_states ? a.init_states + (size_t)h->b * (a.N + 1) * 6 : nullptr,
+                a.init_controls ? a.init_controls + (size_t)h->b * a.N * 2 : nullptr);
+    }
+    __syncwarp();
+    if (c.lane == 0) {
+      h->cur = ns;
+      h->emode = 0;
+    }
+    return PH_EVAL;
+  }
+  if (rmode == 1) {
+    const int n = kNAlpha - gb < kSpec ? kNAlpha - gb : kSpec;
+    const unsigned fw = rollout(c, cur, (1u << n) - 1u, gb, false, false);
+    if (c.lane == 0) {
+      h->retired |= (fw & 0xffffu) << gb;
+      h->deferred |= (fw >> 16) << gb;
+      h->ai = gb;
+      h->emode = 1;
+    }
+    return PH_EVAL;
+  }
+  // rmode == 2: the search reached a step size whose rollout needs the general NormalizeAngle branch:
+  // repeat all deferred ones of this group faithfully (lanes = deferred step sizes)
+  const unsigned def = (h->deferred >> gb) & ((1u << kSpec) - 1u);
+  const unsigned fw = rollout(c, cur, def, gb, true, false);
+  if (c.lane == 0) {
+    h->retired |= (fw & 0xffffu) << gb;
+    h->deferred &= ~(((1u << kSpec) - 1u) << gb);
+  }
+  return PH_EVAL;
+}
+
+// BACK: linearise + quadratise + Riccati sweep (:203-233), gradient-norm exit (:235-241).
+__device__ __noinline__ int phase_back(Ctx& c) {
+  const KernelArgs& a = c.a;
+  const int N = a.N, lane = c.lane;
+  CtxHdr* h = c.h;
+  const unsigned b = h->b;
+  c.bind(b);
+  const DebugPtrs* dbg = (a.debug && h->iter == 0) ? &a.dbg : nullptr;
+  const double lambda = h->lambda;
+  const double* Xs = c.slot(h->cur);
+  double dV[2];
+  backward_pass(c, lambda, Xs, c.nidx(h->nflip), dV, dbg, (int)b);
+  __syncwarp();
+  const double* gains = c.gains();
+  if (dbg) {
+    for (int k = lane; k < N; k += 32) {
+      if (dbg->Kg) for (int i = 0; i < 12; ++i) dbg->Kg[((size_t)b * N + k) * 12 + i] = gains[k * kGainStride + i];
+      if (dbg->kg) for (int i = 0; i < 2; ++i) dbg->kg[((size_t)b * N + k) * 2 + i] = gains[k * kGainStride + 12 + i];
+    }
+    if (dbg->dV && lane == 0) {
+      dbg->dV[(size_t)b * 2] = dV[0];
+      dbg->dV[(size_t)b * 2 + 1] = dV[1];
+    }
+  }
+  // CalGradientNorm (:322-332)
+  double acc = 0.0;
+#pragma unroll 1
+  for (int k = lane; k < N; k += 32) {
+    const double v0 = fabs(gains[k * kGainStride + 12]) / (fabs(Xs[6 * a.Kc + k]) + 1.0);
+    const double v1 = fabs(gains[k * kGainStride + 13]) / (fabs(Xs[7 * a.Kc + k]) + 1.0);
+    acc += fmax(v0, v1);
+  }
+  const double gnorm = warp_sum(acc) / N;
+  if (gnorm < 1e-6 && lambda < 1e-5) {
+    if (lane == 0) h->status = 2;
+    __syncwarp();
+    finish_scenario(c);
+    return PH_INIT;
+  }
+  if (lane == 0) {
+    h->dV0 = dV[0];
+    h->dV1 = dV[1];
+    h->gb = 0;
+    h->rmode = 1;
+    h->retired = 0;
+    h->deferred = 0;
+  }
+  return PH_ROLL;
+}
+
+// EVAL: TotalCost of the initial guess (:172) or of ONE line-search candidate, followed by the
+// accept / reject / lambda / convergence logic of Optimize (:253-309).
+__device__ __noinline__ int phase_eval(Ctx& c) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int N = a.N, K = N + 1, lane = c.lane;
+  CtxHdr* h = c.h;
+  const unsigned b = h->b;
+  c.bind(b);
+  const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
+  const double reg_ratio = 1.6, reg_min = 1e-8, reg_max = 1e11, beta_min = 1e-4, beta_max = 10.0;
+  double cost5[5];
+  const int cur = h->cur, nflip = h->nflip;
+  if (h->emode == 0) {
+    // ---- cost of the initial guess; iter_trajs[0], cost_[0]
+    stage_segments(c);
+    const double* Xs = c.slot(cur);
+    eval_cost(c, Xs, c.nidx(nflip), c.nidx(nflip), cost5);
+    __syncwarp();
+    push_cost(c, cost5);
+    push_traj(c, Xs);
+    if (lane == 0) h->cost_old = cost5[0];
+    if (dbg) {
+      copy_traj(c, Xs, dbg->X0 ? dbg->X0 + (size_t)b * K * 6 : nullptr, dbg->U0 ? dbg->U0 + (size_t)b * N * 2 : nullptr);
+      if (dbg->cost0 && lane == 0) for (int i = 0; i < 5; ++i) dbg->cost0[(size_t)b * 5 + i] = cost5[i];
+      if (dbg->nearest) {
+        const unsigned char* nn = c.nidx(nflip);
+#pragma unroll 1
+        for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nn[i];
+      }
+    }
+    return PH_BACK;
+  }
+  // ---- line search (:246-265): candidates in the reference's order until the first accept
+  int ai = h->ai;
+  const int gb = h->gb;
+  const unsigned retired = h->retired, deferred = h->deferred;
+  while (ai < kNAlpha && ai < gb + kSpec && ((retired >> ai) & 1u)) ++ai;  // non-finite rollout: rejected
+  bool all_rejected = ai >= kNAlpha;
+  if (!all_rejected) {
+    if (ai >= gb + kSpec) {  // next group of step sizes
+      if (lane == 0) {
+        h->gb = gb + kSpec;
+        h->rmode = 1;
+      }
+      return PH_ROLL;
+    }
+    if ((deferred >> ai) & 1u) {
+      if (lane == 0) {
+        h->ai = ai;
+        h->rmode = 2;
+      }
+      return PH_ROLL;
+    }
+    stage_segments(c);
+    const double* cd = c.slot(cand_slot(cur, ai));
+    eval_cost(c, cd, c.nidx(nflip), c.nidx(nflip ^ 1), cost5);
+    __syncwarp();
+    if (dbg && h->iter == 0 && ai == 0) {
+      copy_traj(c, cd, dbg->Xn ? dbg->Xn + (size_t)b * K * 6 : nullptr, dbg->Un ? dbg->Un + (size_t)b * N * 2 : nullptr);
+      if (dbg->costn && lane == 0) for (int i = 0; i < 5; ++i) dbg->costn[(size_t)b * 5 + i] = cost5[i];
+    }
+    if (a.debug) {  // stage dump mode: one backward + one forward only; the initial guess is returned
+      __syncwarp();
+      finish_scenario(c);
+      return PH_INIT;
+    }
+    const double alpha = kAlphaList[ai];
+    const double cost_old = h->cost_old;
+    const double dcost = cost_old - cost5[0];
+    const double expected = -alpha * (h->dV0 + alpha * h->dV1);
+    const double z = dcost / expected;
+    if ((z > beta_min && z < beta_max) && dcost > 0.0) {
+      // ---- accepted (:266-296): the candidate becomes the iterate
+      const double dl = fmin(h->dlambda / reg_ratio, 1.0 / reg_ratio);
+      const double lam = h->lambda;
+      int status = -1;
+      if (dcost < P.abs_tol || dcost / cost_old < P.rel_tol) status = dcost < P.abs_tol ? 0 : 1;
+      const int iter = h->iter;
+      __syncwarp();
+      if (lane == 0) {
+        h->ahash = fnv1a(h->ahash, (unsigned)ai);
+        h->cur = cand_slot(cur, ai);
+        h->nflip = nflip ^ 1;
+        h->dlambda = dl;
+        h->lambda = lam * dl * (lam > reg_min ? 1.0 : 0.0);
+        h->cost_old = cost5[0];
+        if (status >= 0) h->status = status;
+      }
+      push_cost(c, cost5);
+      if (status >= 0) {
+        finish_scenario(c);
+        return PH_INIT;
+      }
+      push_traj(c, cd);
+      if (iter + 1 >= P.max_iter) {  // loop exhausted (:312-319)
+        if (lane == 0) h->iter = iter + 1;
+        __syncwarp();
+        finish_scenario(c);
+        return PH_INIT;
+      }
+      if (lane == 0) h->iter = iter + 1;
+      return PH_BACK;
+    }
+    // rejected: next step size
+    ++ai;
+    while (ai < kNAlpha && ai < gb + kSpec && ((retired >> ai) & 1u)) ++ai;
+    if (ai < kNAlpha) {
+      if (lane == 0) h->ai = ai;
+      return PH_EVAL;  // (a group change / deferred repeat is resolved at the top of the next EVAL)
+    }
+    all_rejected = true;
+  }
+  // ---- every step size rejected (:297-308)
+  {
+    const double dl = fmax(h->dlambda * reg_ratio, reg_ratio);
+    const double lam = fmax(h->lambda * dl, reg_min);
+    const int iter = h->iter;
+    const bool overflow = lam > reg_max;
+    const bool exhausted = iter + 1 >= P.max_iter;
+    __syncwarp();
+    if (lane == 0) {
+      h->ahash = fnv1a(h->ahash, (unsigned)kNAlpha);
+      h->dlambda = dl;
+      h->lambda = lam;
+      if (overflow) h->status = 3;
+      else h->iter = iter + 1;
+    }
+    __syncwarp();
+    if (overflow || exhausted) {
+      finish_scenario(c);
+      return PH_INIT;
+    }
+    return PH_BACK;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent kernel: one CTA per SM, kCtaWarps warps, ctx_per_cta contexts.  Every round all warps
+// compute the same schedule from the shared phase table: the phase type with the largest
+// (waiting contexts capped at W) x (typical duration) + age is run by the first min(W, count)
+// contexts waiting for it; the other warps idle for the round.
+__global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) double smem_cta[];
+  __shared__ unsigned char s_phase[kMaxCtx];
+  __shared__ int s_claim;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int C = a.ctx_per_cta;
   double* smem = smem_cta + (size_t)warp * (a.sm.total_bytes / 8);
-  const DevParams& P = a.P;
-  const int N = a.N, K = N + 1;
-  Ctx c(a, smem);
-  c.lane = lane;
-  c.ws = a.ws + ((size_t)blockIdx.x * kCtaWarps + warp) * a.ws_stride;
-  c.cand = c.ws + (size_t)a.M_max * 3 * a.Kp;
-  double* seg = smem + a.sm.seg;
-  unsigned char* nidx_base = reinterpret_cast<unsigned char*>(smem + a.sm.nidx);
-  const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
-
-  while (true) {
-    unsigned int b = 0;
-#if defined(CILQR_LOCKSTEP_TEST) && CILQR_LOCKSTEP_TEST == 2
-    // experiment: the warps of one scheduler (warp & 3) solve the SAME scenario side by side
-    __shared__ unsigned int s_bg[4];
-    {
-      const int grp = warp & 3, gthreads = (kCtaWarps / 4) * 32;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
-      if (warp == grp && lane == 0) s_bg[grp] = atomicAdd(a.ticket, 1u);
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
-      b = s_bg[grp];
-    }
-#elif defined(CILQR_LOCKSTEP_TEST)
-    // experiment: all warps of the CTA solve the SAME scenario side by side (aligned instruction streams)
-    __shared__ unsigned int s_b;
-    __syncthreads();
-    if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    b = s_b;
-#else
-    if (lane == 0) b = atomicAdd(a.ticket, 1u);
-    b = __shfl_sync(kFull, b, 0);
-#endif
-    if (b >= (unsigned)a.B) break;
-
-    // ---- load scenario, TransformGoals (:141-152)
-    c.goals = a.coarse + (size_t)b * K * 6;
-    c.cnt = a.corridor_cnt + (size_t)b * K;
-    {
-      const double* st = a.start + (size_t)b * 4;
-      c.g0[0] = st[0];
-      c.g0[1] = st[1];
-      c.g0[2] = st[2];
-      c.g0[3] = st[3];
-      c.g0[4] = 0.0;
-      c.g0[5] = 0.0;
-    }
-    // ---- ShrinkConstraints + NormalizeHalfPlane (:438-495)
-    {
-      const double* raw = a.corridor + (size_t)b * K * a.M_max * 3;
-      const int total = K * a.M_max;
-#pragma unroll 1
-      for (int idx = lane; idx < total; idx += 32) {
-        const int k = idx / a.M_max, m = idx - k * a.M_max;
-        if (m < c.cnt[k]) {
-          const double e0 = raw[idx * 3], e1 = raw[idx * 3 + 1];
-          double e2 = raw[idx * 3 + 2];
-          e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
-          const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
-          c.ws[(m * 3 + 0) * a.Kp + k] = e0 / nrm;
-          c.ws[(m * 3 + 1) * a.Kp + k] = e1 / nrm;
-          c.ws[(m * 3 + 2) * a.Kp + k] = e2 / nrm;
-          if (dbg && dbg->corridor) {
-            double* o = dbg->corridor + ((size_t)b * total + idx) * 3;
-            o[0] = e0 / nrm;
-            o[1] = e1 / nrm;
-            o[2] = e2 / nrm;
-          }
-        }
-      }
-      const int ST_ = a.S_left + a.S_right;
-#pragma unroll 1
-      for (int s = lane; s < ST_; s += 32) {
-        const double* ln = s < a.S_left ? a.lane_left + ((size_t)b * a.S_left + s) * 7
-                                        : a.lane_right + ((size_t)b * a.S_right + (s - a.S_left)) * 7;
-        const double e0 = ln[0], e1 = ln[1];
-        double e2 = ln[2];
-        e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
-        const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
-        double* sg = seg + s * kSegStride;
-        const double dx = ln[5] - ln[3], dy = ln[6] - ln[4];
-        const double len = nt_hypot(dx, dy);
-        sg[0] = ln[3];
-        sg[1] = ln[4];
-        sg[2] = ln[5];
-        sg[3] = ln[6];
-        sg[4] = len <= 1e-10 ? 0.0 : dx / len;  // line_segment2d.cpp:40-49
-        sg[5] = len <= 1e-10 ? 0.0 : dy / len;
-        sg[6] = len;
-        sg[7] = e0 / nrm;
-        sg[8] = e1 / nrm;
-        sg[9] = e2 / nrm;
-        if (dbg && dbg->lanes) {
-          double* o = dbg->lanes + ((size_t)b * ST_ + s) * 3;
-          o[0] = sg[7];
-          o[1] = sg[8];
-          o[2] = sg[9];
-        }
-      }
-    }
-    __syncwarp();
-    {
-      // bounding circles of the segment groups (see eval_cost)
-      double offmax = 0.0;
+  double* cta_ws = a.ws + (size_t)blockIdx.x * C * a.cl.stride;
+  for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) s_phase[i] = i < C ? PH_INIT : PH_DONE;
+  if (threadIdx.x == 0) s_claim = 0;
+  __syncthreads();
+  int age[4] = {0, 0, 0, 0};
+  for (;;) {
+    const int p0 = s_phase[lane], p1 = s_phase[lane + 32];
+    unsigned long long m[4];
+    int cnt[4];
 #pragma unroll
-      for (int d = 0; d < kDisc; ++d) offmax = fmax(offmax, fabs(P.off[d]));
-      const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
-      double* grp = smem + a.sm.grp;
-#pragma unroll 1
-      for (int g = lane; g < ngl + ngr; g += 32) {
-        const int side = g < ngl ? 0 : 1;
-        const int S = side == 0 ? a.S_left : a.S_right;
-        const int s_lo = (side == 0 ? g : g - ngl) * kGroup;
-        const int s_hi = s_lo + kGroup < S ? s_lo + kGroup : S;
-        const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
-        double xmin = 1.7976931348623157e308, xmax = -xmin, ymin = xmin, ymax = -xmin;
-#pragma unroll 1
-        for (int s2 = s_lo; s2 < s_hi; ++s2) {
-          const double* sg = sg0 + s2 * kSegStride;
-          xmin = fmin(xmin, fmin(sg[0], sg[2]));
-          xmax = fmax(xmax, fmax(sg[0], sg[2]));
-          ymin = fmin(ymin, fmin(sg[1], sg[3]));
-          ymax = fmax(ymax, fmax(sg[1], sg[3]));
-        }
-        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
-        double r2 = 0.0;
-#pragma unroll 1
-        for (int s2 = s_lo; s2 < s_hi; ++s2) {
-          const double* sg = sg0 + s2 * kSegStride;
-          const double ax = sg[0] - cx, ay = sg[1] - cy, bx = sg[2] - cx, by = sg[3] - cy;
-          r2 = fmax(r2, fmax(ax * ax + ay * ay, bx * bx + by * by));
-        }
-        grp[g * 3] = cx;
-        grp[g * 3 + 1] = cy;
-        // radius + largest disc offset, inflated so that rounding can only make the test more conservative
-        grp[g * 3 + 2] = (sqrt(r2) + offmax) * (1.0 + 1e-9) + 1e-9;
-      }
+    for (int p = 0; p < 4; ++p) {
+      m[p] = (unsigned long long)__ballot_sync(kFull, p0 == p) | ((unsigned long long)__ballot_sync(kFull, p1 == p) << 32);
+      cnt[p] = __popcll(m[p]);
     }
-    __syncwarp();
-    __threadfence_block();
-
-    double* X = smem + a.sm.X;
-    double* U = smem + a.sm.U;
-    unsigned char* nidx = nidx_base;
-    unsigned char* nidx_c = nidx_base + a.sm.nidx_bytes;
-
-    // ---- initial guess (:169) and its cost (:172)
-    iqr_gains(c, X, U);
-    rollout(c, X, U, 1u, true, true);
-    __threadfence_block();
-    adopt(c, 0, X, U);
-    if (a.init_states) copy_out(a.init_states + (size_t)b * K * 6, X, K * 6, lane);
-    if (a.init_controls) copy_out(a.init_controls + (size_t)b * N * 2, U, N * 2, lane);
-    double cost_acc[5], cost_new5[5];
-#pragma unroll 1
-    for (int i = lane; i < a.sm.nidx_bytes; i += 32) nidx[i] = 0;  // no previous iterate: any valid index is a bound
-    __syncwarp();
-    eval_cost(c, c.cand, nidx, nidx, cost_acc);
-    __syncwarp();
-    double cost_old = cost_acc[0];
-    int n_cost = 0, n_iter_traj = 0;
-    auto push_traj = [&](const double* Xs, const double* Us) {
-      if (a.iter_states && n_iter_traj < a.hist_cap) {
-        copy_out(a.iter_states + ((size_t)b * a.hist_cap + n_iter_traj) * K * 6, Xs, K * 6, lane);
-        if (a.iter_controls) copy_out(a.iter_controls + ((size_t)b * a.hist_cap + n_iter_traj) * N * 2, Us, N * 2, lane);
-      }
-      ++n_iter_traj;
-    };
-    {
-      // cost5 values live in registers indexed by compile-time constants; spill through scratch for the lane-indexed store
-      double* t5 = smem + a.sm.scr + SK;
-      if (lane == 0) for (int i = 0; i < 5; ++i) t5[i] = cost_acc[i];
-      __syncwarp();
-      if (a.cost_hist && 0 < a.hist_cap && lane < 5) a.cost_hist[((size_t)b * a.hist_cap) * 5 + lane] = t5[lane];
-      n_cost = 1;
-      push_traj(X, U);
-      if (dbg) {
-        if (dbg->X0) copy_out(dbg->X0 + (size_t)b * K * 6, X, K * 6, lane);
-        if (dbg->U0) copy_out(dbg->U0 + (size_t)b * N * 2, U, N * 2, lane);
-        if (dbg->cost0 && lane < 5) dbg->cost0[(size_t)b * 5 + lane] = t5[lane];
-        if (dbg->nearest)
-#pragma unroll 1
-          for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nidx[i];
-      }
-      __syncwarp();
-    }
-
-    // ---- Optimize main loop (:182-320)
-    double dcost = 0.0, lambda = 1.0, dlambda = 1.0;
-    const double reg_ratio = 1.6, reg_min = 1e-8, reg_max = 1e11, gnorm_min = 1e-6, beta_min = 1e-4, beta_max = 10.0;
-    int status = 4;
-    unsigned ahash = 2166136261u;
-    int iter = 0;
-#ifdef CILQR_PHASE_TEST
-    // experiment: hammer ONE phase (1 rollout, 2 cost evaluation, 3 linearise + backward) to see how
-    // unaligned warps scale when they all run the same code
-    {
-      double dVt[2];
-      backward_pass(c, lambda, X, U, nidx, dVt, nullptr, (int)b);
-      rollout(c, X, U, (1u << kNAlpha) - 1u, true, false);
-      __threadfence_block();
-      for (int rep = 0; rep < 50; ++rep) {
-        if (CILQR_PHASE_TEST == 1) rollout(c, X, U, (1u << kNAlpha) - 1u, true, false);
-        if (CILQR_PHASE_TEST == 2) eval_cost(c, c.cand + (size_t)(rep % 3 + 1) * 8 * a.Kc, nidx, nidx_c, cost_new5);
-        if (CILQR_PHASE_TEST == 3) backward_pass(c, lambda, X, U, nidx, dVt, nullptr, (int)b);
-        __syncwarp();
-      }
-      cost_acc[0] += cost_new5[0] + dVt[0];
-      iter = P.max_iter;
-    }
-#endif
-    for (; iter < P.max_iter; ++iter) {
-      double dV[2];
-      backward_pass(c, lambda, X, U, nidx, dV, iter == 0 ? dbg : nullptr, (int)b);
-      if (dbg && iter == 0) {
-        if (dbg->Kg) copy_out(dbg->Kg + (size_t)b * N * 12, smem + a.sm.Kg, N * 12, lane);
-        if (dbg->kg) copy_out(dbg->kg + (size_t)b * N * 2, smem + a.sm.kg, N * 2, lane);
-        if (dbg->dV && lane == 0) {
-          dbg->dV[(size_t)b * 2] = dV[0];
-          dbg->dV[(size_t)b * 2 + 1] = dV[1];
-        }
-      }
-      // CalGradientNorm (:322-332)
-      {
-        const double* kgp = smem + a.sm.kg;
-        double acc = 0.0;
-#pragma unroll 1
-        for (int k = lane; k < N; k += 32) {
-          const double v0 = fabs(kgp[k * 2]) / (fabs(U[k * 2]) + 1.0);
-          const double v1 = fabs(kgp[k * 2 + 1]) / (fabs(U[k * 2 + 1]) + 1.0);
-          acc += fmax(v0, v1);
-        }
-        const double gnorm = warp_sum(acc) / N;
-        if (gnorm < gnorm_min && lambda < 1e-5) {
-          status = 2;
-          break;
-        }
-      }
-      // line search (:246-265): all candidates in one rollout, then costs in the reference's order
-      bool done = false;
-      int alpha_idx = kNAlpha;
-      unsigned fw = rollout(c, X, U, (1u << kNAlpha) - 1u, false, false);
-      unsigned retired = fw & 0xffffu, deferred = fw >> 16;
-      __threadfence_block();
-      for (int ai = 0; ai < kNAlpha; ++ai) {
-        if ((deferred >> ai) & 1u) {
-          // the search reached a step size whose rollout needs the general NormalizeAngle branch:
-          // repeat all deferred ones faithfully (one extra pass, lanes = deferred step sizes)
-          fw = rollout(c, X, U, deferred, true, false);
-          retired |= fw & 0xffffu;
-          deferred = 0;
-          __threadfence_block();
-        }
-        if ((retired >> ai) & 1u) continue;  // non-finite rollout: rejected (see forward_all)
-        const double alpha = kAlphaList[ai];
-        const double* cd = c.cand + (size_t)ai * 8 * a.Kc;
-        eval_cost(c, cd, nidx, nidx_c, cost_new5);
-        __syncwarp();
-        if (dbg && iter == 0 && ai == 0) {
-          for (int k = lane; k < K; k += 32) {
-            if (dbg->Xn) for (int i = 0; i < 6; ++i) dbg->Xn[((size_t)b * K + k) * 6 + i] = cd[i * a.Kc + k];
-            if (dbg->Un && k < N) for (int i = 0; i < 2; ++i) dbg->Un[((size_t)b * N + k) * 2 + i] = cd[(6 + i) * a.Kc + k];
-          }
-          if (dbg->costn && lane == 0) for (int i = 0; i < 5; ++i) dbg->costn[(size_t)b * 5 + i] = cost_new5[i];
-        }
-        dcost = cost_old - cost_new5[0];
-        const double expected = -alpha * (dV[0] + alpha * dV[1]);
-        const double z = dcost / expected;
-        if ((z > beta_min && z < beta_max) && dcost > 0.0) {
-          done = true;
-          alpha_idx = ai;
-          break;
-        }
-      }
-      ahash = fnv1a(ahash, (unsigned)alpha_idx);
-      if (a.debug) {
-        // stage dump mode: one backward + one forward only
-        break;
-      }
-      if (done) {
-        // accept: the candidate becomes the iterate (workspace -> shared memory)
-        adopt(c, alpha_idx, X, U);
-        unsigned char* tn = nidx; nidx = nidx_c; nidx_c = tn;
-        dlambda = fmin(dlambda / reg_ratio, 1.0 / reg_ratio);
-        lambda = lambda * dlambda * (lambda > reg_min ? 1.0 : 0.0);
+    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) break;
+    // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
+    const int wt[4] = {5, 4, 5, 3};
+    int best = 0, best_score = -1;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) cost_acc[i] = cost_new5[i];
-        {
-          double* t5 = smem + a.sm.scr + SK;
-          __syncwarp();
-          if (lane == 0) for (int i = 0; i < 5; ++i) t5[i] = cost_acc[i];
-          __syncwarp();
-          if (a.cost_hist && n_cost < a.hist_cap && lane < 5) a.cost_hist[((size_t)b * a.hist_cap + n_cost) * 5 + lane] = t5[lane];
-          ++n_cost;
-        }
-        if (dcost < P.abs_tol || dcost / cost_old < P.rel_tol) {
-          status = dcost < P.abs_tol ? 0 : 1;
-          cost_old = cost_new5[0];
-          break;
-        }
-        push_traj(X, U);
-        cost_old = cost_new5[0];
-      } else {
-        dlambda = fmax(dlambda * reg_ratio, reg_ratio);
-        lambda = fmax(lambda * dlambda, reg_min);
-        if (lambda > reg_max) {
-          status = 3;
-          break;
-        }
+    for (int p = 0; p < 4; ++p) {
+      const int score = cnt[p] ? cnt[p] * wt[p] + 2 * age[p] : -1;
+      if (score > best_score) {
+        best_score = score;
+        best = p;
       }
     }
-    __syncwarp();
-    // ---- outputs
-    copy_out(a.states + (size_t)b * K * 6, X, K * 6, lane);
-    copy_out(a.controls + (size_t)b * N * 2, U, N * 2, lane);
-    if (lane == 0) {
-      double* st = a.status + (size_t)b * 8;
-      st[0] = status;
-      st[1] = iter;
-      for (int i = 0; i < 5; ++i) st[2 + i] = cost_acc[i];
-      st[7] = (double)ahash;
-      if (a.hist_len) {
-        a.hist_len[(size_t)b * 2] = n_cost;
-        a.hist_len[(size_t)b * 2 + 1] = n_iter_traj;
-      }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) age[p] = (p == best || cnt[p] == 0) ? 0 : age[p] + 1;
+    unsigned long long mm = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) mm = p == best ? m[p] : mm;
+    const int n_best = __popcll(mm);
+    __syncthreads();  // every warp has read the phase table (and s_claim is zero)
+    // the waiting contexts of the chosen type are claimed one at a time, so a warp that finishes early
+    // takes the next one; a context whose next phase is again the chosen type (EVAL -> EVAL: the next
+    // step size of the line search) keeps its warp
+    for (;;) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(&s_claim, 1);
+      idx = __shfl_sync(kFull, idx, 0);
+      if (idx >= n_best) break;
+      unsigned long long t = mm;
+      for (int i = 0; i < idx; ++i) t &= t - 1;
+      const int mine = __ffsll((long long)t) - 1;
+      Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
+      int next;
+      do {
+        if (best == PH_INIT) next = phase_init(c);
+        else if (best == PH_BACK) next = phase_back(c);
+        else if (best == PH_ROLL) next = phase_roll(c);
+        else next = phase_eval(c);
+        __syncwarp();
+      } while (next == best && best == PH_EVAL);
+      if (lane == 0) s_phase[mine] = (unsigned char)next;
     }
-    if (a.trajectory) {
-      // TransformToTrajectory (:771-791): time, s, x, y, theta, kappa, velocity, a, jerk, delta, delta_rate, lb, rb
-#pragma unroll 1
-      for (int k = lane; k < K; k += 32) {
-        double* tp = a.trajectory + ((size_t)b * K + k) * 13;
-        const double* x = X + k * 6;
-        tp[0] = k * P.dt;
-        tp[1] = 0.0;
-        tp[2] = x[0];
-        tp[3] = x[1];
-        tp[4] = x[2];
-        tp[5] = nt_tan(x[5]) / P.L;
-        tp[6] = x[3];
-        tp[7] = x[4];
-        tp[8] = k < N ? U[k * 2] : 0.0;
-        tp[9] = x[5];
-        tp[10] = k < N ? U[k * 2 + 1] : 0.0;
-        tp[11] = 0.0;
-        tp[12] = 0.0;
-      }
-    }
-    __syncwarp();
+    __syncthreads();  // phase results (context state in global memory, phase table) visible to all warps
+    if (threadIdx.x == 0) s_claim = 0;
   }
 }
 

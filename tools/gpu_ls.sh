@@ -1,4 +1,3 @@
 #!/bin/bash
-V=cilqr_b200/lib/variants
-CILQR_B200_SMEM_PAD=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cilqr_solve -c 1 -f -o gpurun_out/v5_occ12 \
-    python tools/occ_sweep.py --child --lib $V/libcilqr_b200_w16_b12.so --horizon 20 --batch 8192 --reps 0 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for c in 16 24 36; do CILQR_B200_CTX=$c timeout 300 python tools/occ_sweep.py --horizon 100 --batch 65536 --pads 0 --reps 1; done
