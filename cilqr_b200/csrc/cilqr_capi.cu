@@ -25,7 +25,7 @@ using cilqr::CtxLayout;
 namespace {
 
 constexpr int kSlots = 2;           // double buffering of the host path
-constexpr int kDefaultChunk = 8192; // scenarios per pipelined chunk on the host path
+constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granularity) on the host path
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -37,6 +37,13 @@ struct Slot {
   char* out_buf = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host path: H2D copies run on copy_stream ahead of the solve kernel, which only takes scenarios
+  // below the watermark *ready (written by the copy stream after every chunk)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_reset = nullptr;
+  unsigned int* ready = nullptr;       // device
+  unsigned int* ready_host = nullptr;  // pinned, one entry per chunk
+  int ready_cap = 0;
 };
 
 }  // namespace
@@ -172,7 +179,7 @@ int plan_launch(cilqr_handle* h, int B, int N, int M_max, int S_left, int S_righ
   CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes * W));
   // persistent grid: one CTA (W warps) per SM, each owning `ctx` scenario contexts
   L.grid = std::max(1, std::min(B, h->num_sms));
-  int ctx = 2 * W;
+  int ctx = cilqr::kMaxCtx;  // measured best at N = 100 (profiles/): more waiting contexts -> fewer idle warps
   if (const char* e = getenv("CILQR_B200_CTX")) ctx = atoi(e);  // development knob
   ctx = std::max(1, std::min(ctx, cilqr::kMaxCtx));
   L.ctx = std::max(1, std::min(ctx, (B + L.grid - 1) / L.grid));
@@ -206,7 +213,7 @@ int validate(const cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut*
 }
 
 int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatchIn* in, const CilqrBatchOut* out,
-                 const CilqrDebugOut* dbg) {
+                 const CilqrDebugOut* dbg, const unsigned int* ready = nullptr) {
   if (in->B == 0) return CILQR_OK;
   Launch L;
   int rc = plan_launch(h, in->B, in->N, in->M_max, in->S_left, in->S_right, &L);
@@ -244,6 +251,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.hist_cap = out->hist_cap;
   a.ws = s->ws;
   a.ticket = s->ticket;
+  a.ready = ready;
   a.debug = 0;
   if (dbg) {
     a.debug = 1;
@@ -372,6 +380,9 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaMalloc(&s->ticket, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaEventCreateWithFlags(&s->ev_reset, cudaEventDisableTiming) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->ready, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
   }
   *out = h;
   return CILQR_OK;
@@ -389,6 +400,13 @@ void cilqr_destroy(cilqr_handle* h) {
     if (s->out_buf) cudaFree(s->out_buf);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->copy_stream) {
+      cudaStreamSynchronize(s->copy_stream);
+      cudaStreamDestroy(s->copy_stream);
+    }
+    if (s->ev_reset) cudaEventDestroy(s->ev_reset);
+    if (s->ready) cudaFree(s->ready);
+    if (s->ready_host) cudaFreeHost(s->ready_host);
     if (s->stream) cudaStreamDestroy(s->stream);
   }
   delete h;
@@ -432,15 +450,20 @@ int cilqr_synchronize(cilqr_handle* h) {
   return CILQR_OK;
 }
 
-// Host path: chunks of `chunk` scenarios are pipelined over two streams, each doing
-// H2D(inputs) -> solve -> D2H(outputs); copies of one chunk overlap the solve of the other.
+// Host path: ONE solve launch for the whole batch.  The inputs travel host -> device in chunks on a copy
+// stream; after every chunk the copy stream bumps a device watermark, and the kernel's INIT phase only
+// takes scenarios below it, so the solve starts as soon as the first chunk has landed and the rest of the
+// transfer hides behind it (a persistent kernel fed by a stream, instead of one launch -- and one drain
+// tail -- per chunk).  The outputs return in one D2H pass after the kernel.
 int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out) {
   int rc = validate(h, in, out);
   if (rc != CILQR_OK) return rc;
   if (in->B > h->B_max) return CILQR_E_CAPACITY;
+  if (in->B == 0) return CILQR_OK;
   CK(cudaSetDevice(h->device));
-  const size_t K = in->N + 1, N = in->N, M = in->M_max;
+  const size_t K = in->N + 1, N = in->N, M = in->M_max, B = in->B;
   const int chunk = std::max(1, std::min(h->chunk, in->B));
+  const int n_chunks = (in->B + chunk - 1) / chunk;
   const int H = out->hist_cap;
   // per-scenario byte counts
   const size_t b_start = 4 * 8, b_coarse = K * 6 * 8, b_corr = K * M * 3 * 8, b_cnt = K * 4;
@@ -448,99 +471,127 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   const size_t b_st = K * 6 * 8, b_ct = N * 2 * 8, b_status = 8 * 8, b_traj = K * 13 * 8;
   const size_t b_ch = (size_t)H * 5 * 8, b_is = (size_t)H * K * 6 * 8, b_ic = (size_t)H * N * 2 * 8, b_hl = 2 * 4;
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t in_need = up(b_start * chunk) + up(b_coarse * chunk) + up(b_corr * chunk) + up(b_cnt * chunk) +
-                         up(b_ll * chunk) + up(b_lr * chunk);
-  size_t out_need = up(b_st * chunk) + up(b_ct * chunk) + up(b_status * chunk);
-  if (out->trajectory) out_need += up(b_traj * chunk);
-  if (out->init_states) out_need += up(b_st * chunk);
-  if (out->init_controls) out_need += up(b_ct * chunk);
-  if (out->cost_hist) out_need += up(b_ch * chunk);
-  if (out->iter_states) out_need += up(b_is * chunk);
-  if (out->iter_controls) out_need += up(b_ic * chunk);
-  if (out->hist_len) out_need += up(b_hl * chunk);
-  for (int i = 0; i < kSlots; ++i) {
-    Slot* s = &h->slots[i];
-    if (s->in_bytes < in_need) {
-      CK(cudaStreamSynchronize(s->stream));
-      if (s->in_buf) CK(cudaFree(s->in_buf));
-      s->in_buf = nullptr;
-      s->in_bytes = 0;
-      CK(cudaMalloc(&s->in_buf, in_need));
-      s->in_bytes = in_need;
-    }
-    if (s->out_bytes < out_need) {
-      CK(cudaStreamSynchronize(s->stream));
-      if (s->out_buf) CK(cudaFree(s->out_buf));
-      s->out_buf = nullptr;
-      s->out_bytes = 0;
-      CK(cudaMalloc(&s->out_buf, out_need));
-      s->out_bytes = out_need;
-    }
+  const size_t in_need = up(b_start * B) + up(b_coarse * B) + up(b_corr * B) + up(b_cnt * B) + up(b_ll * B) + up(b_lr * B);
+  size_t out_need = up(b_st * B) + up(b_ct * B) + up(b_status * B);
+  if (out->trajectory) out_need += up(b_traj * B);
+  if (out->init_states) out_need += up(b_st * B);
+  if (out->init_controls) out_need += up(b_ct * B);
+  if (out->cost_hist) out_need += up(b_ch * B);
+  if (out->iter_states) out_need += up(b_is * B);
+  if (out->iter_controls) out_need += up(b_ic * B);
+  if (out->hist_len) out_need += up(b_hl * B);
+  Slot* s = &h->slots[0];
+  if (s->in_bytes < in_need) {
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->in_buf) CK(cudaFree(s->in_buf));
+    s->in_buf = nullptr;
+    s->in_bytes = 0;
+    CK(cudaMalloc(&s->in_buf, in_need));
+    s->in_bytes = in_need;
   }
-  int ci = 0;
-  for (int b0 = 0; b0 < in->B; b0 += chunk, ++ci) {
-    const int nb = std::min(chunk, in->B - b0);
-    Slot* s = &h->slots[ci % kSlots];
-    char* p = s->in_buf;
-    auto h2d = [&](const void* src, size_t per, char** dev) -> cudaError_t {
-      *dev = p;
-      p += up(per * chunk);
-      return cudaMemcpyAsync(*dev, (const char*)src + per * b0, per * nb, cudaMemcpyHostToDevice, s->stream);
-    };
-    char *d_start, *d_coarse, *d_corr, *d_cnt, *d_ll, *d_lr;
-    CK(h2d(in->start, b_start, &d_start));
-    CK(h2d(in->coarse, b_coarse, &d_coarse));
-    CK(h2d(in->corridor, b_corr, &d_corr));
-    CK(h2d(in->corridor_cnt, b_cnt, &d_cnt));
-    CK(h2d(in->lane_left, b_ll, &d_ll));
-    CK(h2d(in->lane_right, b_lr, &d_lr));
-    CilqrBatchIn din = *in;
-    din.B = nb;
-    din.start = (const double*)d_start;
-    din.coarse = (const double*)d_coarse;
-    din.corridor = (const double*)d_corr;
-    din.corridor_cnt = (const int32_t*)d_cnt;
-    din.lane_left = (const double*)d_ll;
-    din.lane_right = (const double*)d_lr;
-    char* q = s->out_buf;
-    auto carve = [&](bool want, size_t per) -> char* {
-      if (!want) return nullptr;
-      char* r = q;
-      q += up(per * chunk);
-      return r;
-    };
-    CilqrBatchOut dout;
-    memset(&dout, 0, sizeof(dout));
-    dout.hist_cap = H;
-    dout.states = (double*)carve(true, b_st);
-    dout.controls = (double*)carve(true, b_ct);
-    dout.status = (double*)carve(true, b_status);
-    dout.trajectory = (double*)carve(out->trajectory != nullptr, b_traj);
-    dout.init_states = (double*)carve(out->init_states != nullptr, b_st);
-    dout.init_controls = (double*)carve(out->init_controls != nullptr, b_ct);
-    dout.cost_hist = (double*)carve(out->cost_hist != nullptr, b_ch);
-    dout.iter_states = (double*)carve(out->iter_states != nullptr, b_is);
-    dout.iter_controls = (double*)carve(out->iter_controls != nullptr, b_ic);
-    dout.hist_len = (int32_t*)carve(out->hist_len != nullptr, b_hl);
-    if (dout.cost_hist) CK(cudaMemsetAsync(dout.cost_hist, 0, b_ch * nb, s->stream));
-    rc = launch_solve(h, s, s->stream, &din, &dout, nullptr);
-    if (rc != CILQR_OK) return rc;
-    auto d2h = [&](void* dst, const void* dev, size_t per) -> cudaError_t {
-      if (!dst) return cudaSuccess;
-      return cudaMemcpyAsync((char*)dst + per * b0, dev, per * nb, cudaMemcpyDeviceToHost, s->stream);
-    };
-    CK(d2h(out->states, dout.states, b_st));
-    CK(d2h(out->controls, dout.controls, b_ct));
-    CK(d2h(out->status, dout.status, b_status));
-    CK(d2h(out->trajectory, dout.trajectory, b_traj));
-    CK(d2h(out->init_states, dout.init_states, b_st));
-    CK(d2h(out->init_controls, dout.init_controls, b_ct));
-    CK(d2h(out->cost_hist, dout.cost_hist, b_ch));
-    CK(d2h(out->iter_states, dout.iter_states, b_is));
-    CK(d2h(out->iter_controls, dout.iter_controls, b_ic));
-    CK(d2h(out->hist_len, dout.hist_len, b_hl));
+  if (s->out_bytes < out_need) {
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->out_buf) CK(cudaFree(s->out_buf));
+    s->out_buf = nullptr;
+    s->out_bytes = 0;
+    CK(cudaMalloc(&s->out_buf, out_need));
+    s->out_bytes = out_need;
   }
-  for (int i = 0; i < kSlots; ++i) CK(cudaStreamSynchronize(h->slots[i].stream));
+  if (s->ready_cap < n_chunks) {
+    if (s->ready_host) CK(cudaFreeHost(s->ready_host));
+    s->ready_host = nullptr;
+    s->ready_cap = 0;
+    CK(cudaHostAlloc((void**)&s->ready_host, sizeof(unsigned int) * n_chunks, cudaHostAllocDefault));
+    s->ready_cap = n_chunks;
+  }
+  // device arrays of the whole batch
+  char* p = s->in_buf;
+  auto carve_in = [&](size_t per) {
+    char* r = p;
+    p += up(per * B);
+    return r;
+  };
+  char* d_start = carve_in(b_start);
+  char* d_coarse = carve_in(b_coarse);
+  char* d_corr = carve_in(b_corr);
+  char* d_cnt = carve_in(b_cnt);
+  char* d_ll = carve_in(b_ll);
+  char* d_lr = carve_in(b_lr);
+  CilqrBatchIn din = *in;
+  din.start = (const double*)d_start;
+  din.coarse = (const double*)d_coarse;
+  din.corridor = (const double*)d_corr;
+  din.corridor_cnt = (const int32_t*)d_cnt;
+  din.lane_left = (const double*)d_ll;
+  din.lane_right = (const double*)d_lr;
+  char* q = s->out_buf;
+  auto carve = [&](bool want, size_t per) -> char* {
+    if (!want) return nullptr;
+    char* r = q;
+    q += up(per * B);
+    return r;
+  };
+  CilqrBatchOut dout;
+  memset(&dout, 0, sizeof(dout));
+  dout.hist_cap = H;
+  dout.states = (double*)carve(true, b_st);
+  dout.controls = (double*)carve(true, b_ct);
+  dout.status = (double*)carve(true, b_status);
+  dout.trajectory = (double*)carve(out->trajectory != nullptr, b_traj);
+  dout.init_states = (double*)carve(out->init_states != nullptr, b_st);
+  dout.init_controls = (double*)carve(out->init_controls != nullptr, b_ct);
+  dout.cost_hist = (double*)carve(out->cost_hist != nullptr, b_ch);
+  dout.iter_states = (double*)carve(out->iter_states != nullptr, b_is);
+  dout.iter_controls = (double*)carve(out->iter_controls != nullptr, b_ic);
+  dout.hist_len = (int32_t*)carve(out->hist_len != nullptr, b_hl);
+  // watermark = 0, then the kernel (which waits for the watermark), then the copies that raise it
+  CK(cudaMemsetAsync(s->ready, 0, sizeof(unsigned int), s->copy_stream));
+  CK(cudaEventRecord(s->ev_reset, s->copy_stream));
+  CK(cudaStreamWaitEvent(s->stream, s->ev_reset, 0));
+  if (dout.cost_hist) CK(cudaMemsetAsync(dout.cost_hist, 0, b_ch * B, s->stream));
+  rc = launch_solve(h, s, s->stream, &din, &dout, nullptr, s->ready);
+  if (rc != CILQR_OK) return rc;
+  cudaError_t ce = cudaSuccess;
+  for (int ci = 0; ci < n_chunks && ce == cudaSuccess; ++ci) {
+    const size_t b0 = (size_t)ci * chunk, nb = std::min<size_t>(chunk, B - b0);
+    auto h2d = [&](char* dev, const void* src, size_t per) {
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(dev + per * b0, (const char*)src + per * b0, per * nb, cudaMemcpyHostToDevice, s->copy_stream);
+    };
+    h2d(d_start, in->start, b_start);
+    h2d(d_coarse, in->coarse, b_coarse);
+    h2d(d_corr, in->corridor, b_corr);
+    h2d(d_cnt, in->corridor_cnt, b_cnt);
+    h2d(d_ll, in->lane_left, b_ll);
+    h2d(d_lr, in->lane_right, b_lr);
+    s->ready_host[ci] = (unsigned int)(b0 + nb);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(s->ready, &s->ready_host[ci], sizeof(unsigned int), cudaMemcpyHostToDevice, s->copy_stream);
+  }
+  if (ce != cudaSuccess) {
+    // release the kernel (it would otherwise wait for its watchdog), then report
+    s->ready_host[0] = 0xffffffffu;
+    cudaMemcpyAsync(s->ready, &s->ready_host[0], sizeof(unsigned int), cudaMemcpyHostToDevice, s->copy_stream);
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamSynchronize(s->stream);
+    return fail_cuda(h, ce, "host-to-device copy");
+  }
+  auto d2h = [&](void* dst, const void* dev, size_t per) -> cudaError_t {
+    if (!dst) return cudaSuccess;
+    return cudaMemcpyAsync(dst, dev, per * B, cudaMemcpyDeviceToHost, s->stream);
+  };
+  CK(d2h(out->states, dout.states, b_st));
+  CK(d2h(out->controls, dout.controls, b_ct));
+  CK(d2h(out->status, dout.status, b_status));
+  CK(d2h(out->trajectory, dout.trajectory, b_traj));
+  CK(d2h(out->init_states, dout.init_states, b_st));
+  CK(d2h(out->init_controls, dout.init_controls, b_ct));
+  CK(d2h(out->cost_hist, dout.cost_hist, b_ch));
+  CK(d2h(out->iter_states, dout.iter_states, b_is));
+  CK(d2h(out->iter_controls, dout.iter_controls, b_ic));
+  CK(d2h(out->hist_len, dout.hist_len, b_hl));
+  CK(cudaStreamSynchronize(s->copy_stream));
+  CK(cudaStreamSynchronize(s->stream));
   return CILQR_OK;
 }
 

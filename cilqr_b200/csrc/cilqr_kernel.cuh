@@ -157,6 +157,7 @@ struct KernelArgs {
   int hist_cap;
   double* ws;            // [gridDim.x][ctx_per_cta][cl.stride]
   unsigned int* ticket;  // scenario counter
+  const unsigned int* ready;  // host path: scenarios below *ready have arrived on the device (NULL: all)
   DebugPtrs dbg;
   int debug;             // 1: stop after the first line-search evaluation and dump stages
 };
@@ -1281,6 +1282,15 @@ __device__ __noinline__ int phase_init(Ctx& c) {
   if (lane == 0) b = atomicAdd(a.ticket, 1u);
   b = __shfl_sync(kFull, b, 0);
   if (b >= (unsigned)a.B) return PH_DONE;
+  if (a.ready) {
+    // the host path streams the inputs in behind the running kernel: wait for this scenario's chunk
+    unsigned naps = 0;
+    while (b >= *(const volatile unsigned int*)a.ready) {
+      __nanosleep(2000);
+      if (++naps > 2000000u) return PH_DONE;  // (watchdog ~4 s: the transfer died; the host reports the error)
+    }
+    __threadfence();
+  }
   c.bind(b);
   CtxHdr* h = c.h;
   if (lane == 0) {
@@ -1642,25 +1652,40 @@ __device__ __noinline__ int phase_eval(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent kernel: one CTA per SM, kCtaWarps warps, ctx_per_cta contexts.  Every round all warps
-// compute the same schedule from the shared phase table: the phase type with the largest
-// (waiting contexts capped at W) x (typical duration) + age is run by the first min(W, count)
-// contexts waiting for it; the other warps idle for the round.
+// Persistent kernel: one CTA per SM, up to kCtaWarps warps, ctx_per_cta contexts (> warps).
+//
+// Scheduling is CTA-local and barrier-free.  s_state[c] holds the phase context c waits for (or BUSY
+// while a warp runs it, DONE after the last scenario); s_type is the phase type the CTA currently
+// runs.  A warp looking for work claims (shared-memory CAS) a free context that waits for s_type; only
+// when none is left does it move s_type to the type with the most waiting work, so at any moment the
+// SM executes one phase body (two while stragglers of the previous type finish) and its hot code stays
+// inside the ~32 KB the instruction cache can feed to unaligned warps.  A context whose next phase is
+// again s_type (EVAL -> EVAL: the next step size of the line search) keeps its warp.  Warps never wait
+// for each other; they only nap when every live context is being run by another warp.
+constexpr int ST_BUSY = 5;
 __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) double smem_cta[];
-  __shared__ unsigned char s_phase[kMaxCtx];
-  __shared__ int s_claim;
+  __shared__ int s_state[kMaxCtx];
+  __shared__ int s_iter[kMaxCtx];  // iterations run so far by the scenario in each context (claim priority)
+  __shared__ int s_type;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int C = a.ctx_per_cta;
   double* smem = smem_cta + (size_t)warp * (a.sm.total_bytes / 8);
   double* cta_ws = a.ws + (size_t)blockIdx.x * C * a.cl.stride;
-  for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) s_phase[i] = i < C ? PH_INIT : PH_DONE;
-  if (threadIdx.x == 0) s_claim = 0;
+  for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
+    s_state[i] = i < C ? PH_INIT : PH_DONE;
+    s_iter[i] = 0;
+  }
+  if (threadIdx.x == 0) s_type = PH_INIT;
   __syncthreads();
-  int age[4] = {0, 0, 0, 0};
+  // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
+  const int wt[4] = {5, 4, 5, 3};
+  unsigned naps = 0;
   for (;;) {
-    const int p0 = s_phase[lane], p1 = s_phase[lane + 32];
+    // ---- snapshot of the context table (all lanes, identical result)
+    const volatile int* st = s_state;
+    const int p0 = st[lane], p1 = st[lane + 32];
     unsigned long long m[4];
     int cnt[4];
 #pragma unroll
@@ -1668,49 +1693,62 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       m[p] = (unsigned long long)__ballot_sync(kFull, p0 == p) | ((unsigned long long)__ballot_sync(kFull, p1 == p) << 32);
       cnt[p] = __popcll(m[p]);
     }
-    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) break;
-    // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
-    const int wt[4] = {5, 4, 5, 3};
-    int best = 0, best_score = -1;
+    const unsigned busy = __ballot_sync(kFull, p0 == ST_BUSY) | __ballot_sync(kFull, p1 == ST_BUSY);
+    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) {
+      if (busy == 0) break;  // every context is DONE
+      // the remaining contexts are all being run by other warps: back off (up to ~4 us between polls)
+      ++naps;
+      __nanosleep(naps < 16 ? 250 : 4000);
+      if (naps > (1u << 22)) break;  // (watchdog: never spin forever)
+      continue;
+    }
+    naps = 0;
+    int type = *(const volatile int*)&s_type;
+    if (cnt[type] == 0) {
+      int best = 0, best_score = -1;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int score = cnt[p] ? cnt[p] * wt[p] + 2 * age[p] : -1;
-      if (score > best_score) {
-        best_score = score;
-        best = p;
+      for (int p = 0; p < 4; ++p) {
+        const int score = cnt[p] ? cnt[p] * wt[p] : -1;
+        if (score > best_score) {
+          best_score = score;
+          best = p;
+        }
       }
+      type = best;
+      if (lane == 0) s_type = type;
     }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) age[p] = (p == best || cnt[p] == 0) ? 0 : age[p] + 1;
-    unsigned long long mm = 0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) mm = p == best ? m[p] : mm;
-    const int n_best = __popcll(mm);
-    __syncthreads();  // every warp has read the phase table (and s_claim is zero)
-    // the waiting contexts of the chosen type are claimed one at a time, so a warp that finishes early
-    // takes the next one; a context whose next phase is again the chosen type (EVAL -> EVAL: the next
-    // step size of the line search) keeps its warp
-    for (;;) {
-      int idx = 0;
-      if (lane == 0) idx = atomicAdd(&s_claim, 1);
-      idx = __shfl_sync(kFull, idx, 0);
-      if (idx >= n_best) break;
-      unsigned long long t = mm;
-      for (int i = 0; i < idx; ++i) t &= t - 1;
-      const int mine = __ffsll((long long)t) - 1;
-      Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
-      int next;
-      do {
-        if (best == PH_INIT) next = phase_init(c);
-        else if (best == PH_BACK) next = phase_back(c);
-        else if (best == PH_ROLL) next = phase_roll(c);
-        else next = phase_eval(c);
-        __syncwarp();
-      } while (next == best && best == PH_EVAL);
-      if (lane == 0) s_phase[mine] = (unsigned char)next;
+    // claim the waiting context of that type that has run the most iterations: scenarios with long
+    // iteration counts (the batch has a few with 10x the mean) must not idle in the pool, or they finish
+    // long after everything else and the SM drains
+    int key = -1;
+    if (p0 == type) key = (s_iter[lane] << 6) | lane;
+    if (p1 == type) {
+      const int k1 = (s_iter[lane + 32] << 6) | (lane + 32);
+      key = k1 > key ? k1 : key;
     }
-    __syncthreads();  // phase results (context state in global memory, phase table) visible to all warps
-    if (threadIdx.x == 0) s_claim = 0;
+    key = __reduce_max_sync(kFull, key);
+    const int mine = key & 63;
+    int got = 0;
+    if (lane == 0) got = atomicCAS(&s_state[mine], type, ST_BUSY) == type;
+    got = __shfl_sync(kFull, got, 0);
+    if (!got) continue;
+    __threadfence();  // acquire: the context was last written by another warp (plain stores, read back by cp.async too)
+    Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
+    int next = type;
+    do {
+      if (next != PH_EVAL) c.seg_staged = false;  // the other phases reuse the segment region of the stage
+      if (next == PH_INIT) next = phase_init(c);
+      else if (next == PH_BACK) next = phase_back(c);
+      else if (next == PH_ROLL) next = phase_roll(c);
+      else next = phase_eval(c);
+      __syncwarp();
+    } while (next < PH_DONE && next == *(const volatile int*)&s_type);
+    __threadfence();  // release
+    if (lane == 0) {
+      s_iter[mine] = next == PH_INIT || next == PH_DONE ? 0 : c.h->iter;
+      *(volatile int*)&s_state[mine] = next;
+    }
+    __syncwarp();
   }
 }
 

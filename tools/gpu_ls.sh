@@ -1,3 +1,4 @@
 #!/bin/bash
+mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for c in 16 24 36; do CILQR_B200_CTX=$c timeout 300 python tools/occ_sweep.py --horizon 100 --batch 65536 --pads 0 --reps 1; done
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
