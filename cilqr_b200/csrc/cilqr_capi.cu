@@ -128,12 +128,12 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   L.grp = S * cilqr::kSegStride;
   L.trig = even(L.grp + ng * 3);
   L.pl_e = even(L.trig + 2 * K);
-  const int e_end = L.pl_e + 2 * M_max * cilqr::kPlaneTile;
+  const int e_end = L.pl_e + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
   // BACK: lin, scr; INIT builds seg/grp while iqr uses scr, so scr lies behind both
   L.lin = 0;
   L.scr = std::max(even(cilqr::kWin * cilqr::kLinStride), L.trig);
   L.pl_b = L.scr + cilqr::kScratch;
-  const int b_end = L.pl_b + 2 * M_max * cilqr::kPlaneTile;
+  const int b_end = L.pl_b + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
   // ROLL: ring
   L.ring = 0;
   const int total = std::max(std::max(e_end, b_end), cilqr::kRingDoubles);

@@ -55,6 +55,12 @@ constexpr int kGroup = CILQR_GROUP;  // lane segments per bounding-circle group 
 constexpr int kScratch = 192;     // doubles of per-warp Riccati scratch
 constexpr int kPlaneKnots = 8;    // knots per staged tile of corridor planes
 constexpr int kPlaneTile = 3 * kPlaneKnots;  // doubles per plane (a, b, c rows) in a tile; x M_max per buffer
+#ifndef CILQR_TILE_BUFS
+#define CILQR_TILE_BUFS 1
+#endif
+// 2: the next tile is copied while the whole current chunk is processed; 1: (less shared memory, for 16
+// warps per SM) the next tile is copied into the same buffer behind the lane-boundary part of the chunk
+constexpr int kTileBufs = CILQR_TILE_BUFS;
 constexpr int kHdrDoubles = 24;   // sizeof(CtxHdr) / 8
 constexpr int kMaxCtx = 64;       // contexts per CTA (two ballots)
 constexpr unsigned kFull = 0xffffffffu;
@@ -64,7 +70,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWin = CILQR_LIN_WINDOW;  // knots per linearisation window (<= 32: lane == knot inside a window)
 static_assert(kWin >= 1 && kWin <= 32, "linearisation window is at most one knot per lane");
 #ifndef CILQR_CTA_WARPS
-#define CILQR_CTA_WARPS 12
+#define CILQR_CTA_WARPS 16
 #endif
 constexpr int kCtaWarps = CILQR_CTA_WARPS;  // warps per CTA (one CTA per SM)
 
@@ -176,6 +182,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Inlined at every call site they made the kernel ~300 KB of SASS, which thrashed the instruction
 // cache (ncu: stall_no_instruction 5.4 cycles per issued instruction); see DESIGN.md.
 __device__ __noinline__ double nt_tan(double x) { return tan(x); }
+// two independent tangents in one call: the two polynomial chains interleave (the rollout is a serial
+// dependency chain, so instruction-level parallelism inside a step is all there is)
+__device__ __noinline__ double2 nt_tan2(double x, double y) { return make_double2(tan(x), tan(y)); }
 __device__ __noinline__ double nt_log(double x) { return log(x); }
 __device__ __noinline__ double nt_hypot(double x, double y) { return hypot(x, y); }
 __device__ __noinline__ double2 nt_sincos(double x) {
@@ -215,14 +224,16 @@ __device__ __forceinline__ double normalize_angle(double angle) {
 // (theta enters k1 only through k1x, k1y, which the midpoint step never uses.)
 __device__ __forceinline__ void rollout_step(const DevParams& P, double* x, double u0, double u1, bool allow_general,
                                              bool& slow) {
-  const double de = wrap_angle(x[5], allow_general, slow);
-  const double k1t = x[3] * nt_tan(de) * P.inv_L;
   const double h = 0.5 * P.dt;
-  const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0, m5 = x[5] + h * u1;
-  const double thm = wrap_angle(m2, allow_general, slow);
+  const double m5 = x[5] + h * u1;
+  const double de = wrap_angle(x[5], allow_general, slow);
   const double dem = wrap_angle(m5, allow_general, slow);
+  const double2 tt = nt_tan2(de, dem);
+  const double k1t = x[3] * tt.x * P.inv_L;
+  const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0;
+  const double thm = wrap_angle(m2, allow_general, slow);
   const double2 sc = nt_sincos(thm);
-  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * nt_tan(dem) * P.inv_L;
+  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * tt.y * P.inv_L;
   x[0] = x[0] + P.dt * k2x;
   x[1] = x[1] + P.dt * k2y;
   x[2] = wrap_angle(x[2] + P.dt * k2t, allow_general, slow);
@@ -239,9 +250,9 @@ __device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double*
   const double theta = normalize_angle(x[2]);
   const double delta = normalize_angle(x[5]);
   const double a = x[4];
-  const double tan_delta = nt_tan(delta);
+  const double2 tt = nt_tan2(delta, delta + 0.5 * dt * u1);
+  const double tan_delta = tt.x, tan_dr = tt.y;
   const double theta_mid = theta + 0.5 * dt * v * tan_delta * iL;
-  const double tan_dr = nt_tan(delta + 0.5 * dt * u1);
   const double2 scm = nt_sincos(theta_mid);
   const double sm = scm.x, cm = scm.y;
   const double td2 = tan_delta * tan_delta;
@@ -265,11 +276,14 @@ __device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double*
 struct BarAcc {
   double prod, quad;
 };
-__device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P) {
-  const bool lg = g < -P.eps;
+// quadratic extension of the barrier for g >= -eps (barrier_function.h:108-112): rare, kept out of line
+__device__ __noinline__ double bar_quad(double g, const DevParams& P) {
   const double q = (-g - 2.0 * P.eps) * P.inv_eps;
-  a.prod *= lg ? -g : 1.0;
-  a.quad += lg ? 0.0 : fma(0.5 * P.rt * q, q, P.relax_c);
+  return fma(0.5 * P.rt * q, q, P.relax_c);
+}
+__device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P) {
+  if (g < -P.eps) a.prod *= -g;
+  else a.quad += bar_quad(g, P);
 }
 __device__ __forceinline__ double bar_value(const BarAcc& a, const DevParams& P) {
   return a.quad - P.rt * nt_log(a.prod);
@@ -466,7 +480,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
 #pragma unroll 1
   for (int j0 = 0; j0 < items; j0 += 32, stage ^= 1) {
     int M_next = 0, Mw_next = 0;
-    if (j0 + 32 < items) {
+    if (kTileBufs == 2 && j0 + 32 < items) {
       M_next = chunk_M(j0 + 32);
       Mw_next = __reduce_max_sync(kFull, M_next);
       chunk_stage(j0 + 32, Mw_next, stage ^ 1);
@@ -484,13 +498,19 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
     // corridor half-planes of this knot
     BarAcc bc = {1.0, 0.0};
-    const double* w = pbuf + stage * pstride + (k - j0 / kDisc);
+    const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (k - j0 / kDisc);
 #pragma unroll 4
     for (int m = 0; m < Mw; ++m) {
       if (m < M) {
         const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
         bar_add(bc, fma(pb, yd, pa * xd) - pc, P);
       }
+    }
+    if (kTileBufs == 1 && j0 + 32 < items) {
+      __syncwarp();  // every lane is done with the tile
+      M_next = chunk_M(j0 + 32);
+      Mw_next = __reduce_max_sync(kFull, M_next);
+      chunk_stage(j0 + 32, Mw_next, 0);
     }
     // nearest lane segment per side (strict '<': first minimum wins)
     BarAcc bl = {1.0, 0.0};
@@ -609,7 +629,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
 #pragma unroll 1
   for (int g0 = 0; g0 < nk; g0 += kKnotsPerPass, stage ^= 1) {
     int M_next = 0, Mw_next = 0;
-    if (g0 + kKnotsPerPass < nk) {
+    if (kTileBufs == 2 && g0 + kKnotsPerPass < nk) {
       M_next = pass_M(g0 + kKnotsPerPass);
       Mw_next = __reduce_max_sync(kFull, M_next);
       pass_stage(g0 + kKnotsPerPass, Mw_next, stage ^ 1);
@@ -644,10 +664,16 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
       H22 = fma(to, to * co, H22);
       H22 = fma(wo, cdd, H22);
     };
-    const double* w = pbuf + stage * pstride + (act ? kl : 0);
+    const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (act ? kl : 0);
 #pragma unroll 2
     for (int m = 0; m < Mw; ++m) {
       if (m < M) plane(w[m * kPlaneTile], w[m * kPlaneTile + kPlaneKnots], w[m * kPlaneTile + 2 * kPlaneKnots]);
+    }
+    if (kTileBufs == 1 && g0 + kKnotsPerPass < nk) {
+      __syncwarp();  // every lane is done with the tile
+      M_next = pass_M(g0 + kKnotsPerPass);
+      Mw_next = __reduce_max_sync(kFull, M_next);
+      pass_stage(g0 + kKnotsPerPass, Mw_next, 0);
     }
     if (act) {
 #pragma unroll 1
@@ -1065,10 +1091,17 @@ __device__ void iqr_gains(const Ctx& c, double* Xs) {
   double* G = scr + SQUX;    // B^T P A
   double* S4 = scr + SQUU;   // R + B^T P B
   double* Kl = scr + ST;     // K of this knot, 2x6
+  double nxt[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) nxt[i] = Kg[(N - 1) * kGainStride + i];
   for (int k = N - 1; k >= 0; --k) {
     double rec[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) rec[i] = Kg[k * kGainStride + i];
+    for (int i = 0; i < 12; ++i) rec[i] = nxt[i];
+    if (k > 0) {  // the parked record of the next knot travels from L2 while this knot is processed
+#pragma unroll
+      for (int i = 0; i < 12; ++i) nxt[i] = Kg[(k - 1) * kGainStride + i];
+    }
     const double b21 = rec[11];
     __syncwarp();
     if (lane < 24) {

@@ -1,4 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
+V=cilqr_b200/lib/variants
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+timeout 300 python tools/occ_sweep.py --horizon 100 --batch 65536 --pads 0 --reps 1
+timeout 300 python tools/occ_sweep.py --lib $V/libcilqr_b200_w18.so --horizon 100 --batch 65536 --pads 0 --reps 1
