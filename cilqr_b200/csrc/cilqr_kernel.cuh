@@ -62,7 +62,12 @@ constexpr int kPlaneTile = 3 * kPlaneKnots;  // doubles per plane (a, b, c rows)
 // warps per SM) the next tile is copied into the same buffer behind the lane-boundary part of the chunk
 constexpr int kTileBufs = CILQR_TILE_BUFS;
 constexpr int kHdrDoubles = 24;   // sizeof(CtxHdr) / 8
-constexpr int kMaxCtx = 64;       // contexts per CTA (two ballots)
+#ifndef CILQR_MAX_CTX
+#define CILQR_MAX_CTX 128
+#endif
+constexpr int kMaxCtx = CILQR_MAX_CTX;  // contexts per CTA (power of two, multiple of 32)
+constexpr int kCtxWords = kMaxCtx / 32;
+static_assert(kMaxCtx % 32 == 0 && (kMaxCtx & (kMaxCtx - 1)) == 0 && kMaxCtx <= 256, "context table size");
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef CILQR_LIN_WINDOW
 #define CILQR_LIN_WINDOW 16
@@ -370,11 +375,18 @@ __device__ __forceinline__ int cand_slot(int cur, int ai) {
 // consumer overlaps the copy of the next tile with the arithmetic of the current one, so the inner
 // loops never wait on L2 / HBM.
 __device__ __forceinline__ void stage_planes(const Ctx& c, double* buf, int k_lo, int nk, int Mrows) {
-  const double* src = c.planes() + k_lo;
-  const int total = Mrows * kPlaneTile;
-  for (int e = c.lane; e < total; e += 32) {
-    const int row = e / kPlaneKnots, kk = e - row * kPlaneKnots;
-    if (kk < nk) cp_async8(buf + e, src + row * c.a.Kc + kk);
+  static_assert(32 % kPlaneKnots == 0, "a lane keeps its knot column");
+  constexpr int kRowsPerIter = 32 / kPlaneKnots;
+  const int kk = c.lane % kPlaneKnots, r0 = c.lane / kPlaneKnots;
+  if (kk < nk) {
+    const double* src = c.planes() + k_lo + kk + (size_t)r0 * c.a.Kc;
+    unsigned dst = (unsigned)__cvta_generic_to_shared(buf + c.lane);
+    const size_t sstep = (size_t)kRowsPerIter * c.a.Kc;
+    for (int row = r0; row < Mrows * 3; row += kRowsPerIter) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      src += sstep;
+      dst += 32 * 8;
+    }
   }
   cp_async_commit();
 }
@@ -497,15 +509,22 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     const double xd = fma(o, trig[k * 2 + 1], Xs[k]);
     const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
     // corridor half-planes of this knot
-    BarAcc bc = {1.0, 0.0};
+    BarAcc bc = {1.0, 0.0}, bc2 = {1.0, 0.0};  // two running products: two independent multiply chains
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (k - j0 / kDisc);
-#pragma unroll 4
-    for (int m = 0; m < Mw; ++m) {
+#pragma unroll 2
+    for (int m = 0; m < Mw; m += 2) {
       if (m < M) {
         const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
         bar_add(bc, fma(pb, yd, pa * xd) - pc, P);
       }
+      if (m + 1 < M) {
+        const double* w1 = w + kPlaneTile;
+        const double pa = w1[m * kPlaneTile], pb = w1[m * kPlaneTile + kPlaneKnots], pc = w1[m * kPlaneTile + 2 * kPlaneKnots];
+        bar_add(bc2, fma(pb, yd, pa * xd) - pc, P);
+      }
     }
+    bc.prod *= bc2.prod;
+    bc.quad += bc2.quad;
     if (kTileBufs == 1 && j0 + 32 < items) {
       __syncwarp();  // every lane is done with the tile
       M_next = chunk_M(j0 + 32);
@@ -1718,17 +1737,22 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   for (;;) {
     // ---- snapshot of the context table (all lanes, identical result)
     const volatile int* st = s_state;
-    const int p0 = st[lane], p1 = st[lane + 32];
-    unsigned long long m[4];
+    int sl[kCtxWords];
+#pragma unroll
+    for (int w = 0; w < kCtxWords; ++w) sl[w] = st[lane + 32 * w];
     int cnt[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      m[p] = (unsigned long long)__ballot_sync(kFull, p0 == p) | ((unsigned long long)__ballot_sync(kFull, p1 == p) << 32);
-      cnt[p] = __popcll(m[p]);
+      int n = 0;
+#pragma unroll
+      for (int w = 0; w < kCtxWords; ++w) n += __popc(__ballot_sync(kFull, sl[w] == p));
+      cnt[p] = n;
     }
-    const unsigned busy = __ballot_sync(kFull, p0 == ST_BUSY) | __ballot_sync(kFull, p1 == ST_BUSY);
     if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) {
-      if (busy == 0) break;  // every context is DONE
+      bool b = false;
+#pragma unroll
+      for (int w = 0; w < kCtxWords; ++w) b |= sl[w] == ST_BUSY;
+      if (!__any_sync(kFull, b)) break;  // every context is DONE
       // the remaining contexts are all being run by other warps: back off (up to ~4 us between polls)
       ++naps;
       __nanosleep(naps < 16 ? 250 : 4000);
@@ -1752,19 +1776,28 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     }
     // claim the waiting context of that type that has run the most iterations: scenarios with long
     // iteration counts (the batch has a few with 10x the mean) must not idle in the pool, or they finish
-    // long after everything else and the SM drains
+    // long after everything else and the SM drains.  Priority in buckets of four iterations; inside a
+    // bucket every warp prefers a different context, so warps that look for work at the same moment do
+    // not all go for the same one.
+    const int rot = warp * 5;
     int key = -1;
-    if (p0 == type) key = (s_iter[lane] << 6) | lane;
-    if (p1 == type) {
-      const int k1 = (s_iter[lane + 32] << 6) | (lane + 32);
-      key = k1 > key ? k1 : key;
+#pragma unroll
+    for (int w = 0; w < kCtxWords; ++w) {
+      if (sl[w] == type) {
+        const int idx = lane + 32 * w;
+        const int k1 = ((s_iter[idx] >> 2) << 8) | ((idx + rot) & (kMaxCtx - 1));
+        key = k1 > key ? k1 : key;
+      }
     }
     key = __reduce_max_sync(kFull, key);
-    const int mine = key & 63;
+    const int mine = ((key & 255) - rot) & (kMaxCtx - 1);
     int got = 0;
     if (lane == 0) got = atomicCAS(&s_state[mine], type, ST_BUSY) == type;
     got = __shfl_sync(kFull, got, 0);
-    if (!got) continue;
+    if (!got) {
+      __nanosleep(100);
+      continue;
+    }
     __threadfence();  // acquire: the context was last written by another warp (plain stores, read back by cp.async too)
     Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
     int next = type;
