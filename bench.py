@@ -13,7 +13,7 @@ result blocks).  Prints ONE JSON line (rank 0).
 
 value     : converged trajectories / s, inputs resident in HBM, CUDA events around the K steps
 e2e       : same metric through the host C ABI (cilqr_plan_batch): pinned host buffers in, H2D +
-            solve + D2H inside the timed region
+            solve + D2H inside the timed region (one launch fed by chunked copies behind a watermark)
 roofline  : algorithmic HBM bytes of the solve kernel / its CUDA-event time vs MEASURED_PEAKS.json
 cpu_baseline: the oracle (a port: the reference cannot be built here) on a bounded sample
 """
@@ -263,7 +263,8 @@ def main():
         e2e = {"value": float(ce[0]) * n_e2e / float(te[0]), "unit": UNIT,
                "h2d_bytes_per_step": int(batch.input_bytes()) * world,
                "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) * world,
-               "steps": n_e2e, "api": "cilqr_plan_batch (C ABI, host pointers, chunked H2D/solve/D2H pipeline)"}
+               "steps": n_e2e, "api": "cilqr_plan_batch (C ABI, host pointers): one solve launch fed by chunked H2D copies through a "
+                      "device watermark, then one D2H pass"}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -290,8 +291,9 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "cilqr_solve_kernel",
                          "kernel_ms": kmean_ms, "kernel_ms_library_events": lib_kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "latency/FP64-issue bound by construction: the horizon is staged on chip, "
-                                 "compulsory HBM traffic is inputs once + outputs once (DESIGN.md)"},
+                         "note": "fp64 issue/latency bound, not HBM bound: compulsory traffic is inputs once + "
+                                 "outputs once; `traffic` (ncu dram bytes per launch) is larger because the "
+                                 "scenario contexts live in L2/HBM between solver phases (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches),
             "kernel_ms_per_step": k_ms, "allgather_ms_per_step": g_ms if world > 1 else None,
         }
