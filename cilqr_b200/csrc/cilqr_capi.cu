@@ -30,6 +30,7 @@ constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granul
 struct Slot {
   cudaStream_t stream = nullptr;
   unsigned int* ticket = nullptr;
+  unsigned long long* stats = nullptr;  // scheduler counters of the last launch (cilqr_debug_stats)
   double* ws = nullptr;
   size_t ws_bytes = 0;
   // device staging for the host API
@@ -252,6 +253,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.ws = s->ws;
   a.ticket = s->ticket;
   a.ready = ready;
+  a.stats = s->stats;
+  CK(cudaMemsetAsync(s->stats, 0, 8 * sizeof(unsigned long long), stream));
   a.debug = 0;
   if (dbg) {
     a.debug = 1;
@@ -379,6 +382,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
     Slot* s = &h->slots[i];
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaMalloc(&s->ticket, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreateWithFlags(&s->ev_reset, cudaEventDisableTiming) != cudaSuccess) return bail(CILQR_E_CUDA);
@@ -395,6 +399,7 @@ void cilqr_destroy(cilqr_handle* h) {
     Slot* s = &h->slots[i];
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ticket) cudaFree(s->ticket);
+    if (s->stats) cudaFree(s->stats);
     if (s->ws) cudaFree(s->ws);
     if (s->in_buf) cudaFree(s->in_buf);
     if (s->out_buf) cudaFree(s->out_buf);
@@ -592,6 +597,15 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   CK(d2h(out->hist_len, dout.hist_len, b_hl));
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(s->stream));
+  return CILQR_OK;
+}
+
+int cilqr_debug_stats(cilqr_handle* h, uint64_t out[8]) {
+  if (!h || !out || !h->timed) return CILQR_E_INVALID;
+  Slot* s = &h->slots[h->last_slot];
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(s->ev1));
+  CK(cudaMemcpy(out, s->stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return CILQR_OK;
 }
 

@@ -169,6 +169,7 @@ struct KernelArgs {
   double* ws;            // [gridDim.x][ctx_per_cta][cl.stride]
   unsigned int* ticket;  // scenario counter
   const unsigned int* ready;  // host path: scenarios below *ready have arrived on the device (NULL: all)
+  unsigned long long* stats;  // optional [8]: scheduler passes, idle polls, failed claims, phases run by type (4), type switches
   DebugPtrs dbg;
   int debug;             // 1: stop after the first line-search evaluation and dump stages
 };
@@ -505,6 +506,9 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     const bool act = j < items;
     const int jj = act ? j : items - 1;
     const int k = jj / kDisc, d = jj - k * kDisc;
+    // issued now, consumed after the corridor loop: the next chunk's plane count and this item's guesses
+    const int M_pre = (kTileBufs == 1 && j0 + 32 < items) ? chunk_M(j0 + 32) : 0;
+    const unsigned short g2 = *reinterpret_cast<const unsigned short*>(guess + jj * 2);
     const double o = P.off[d];
     const double xd = fma(o, trig[k * 2 + 1], Xs[k]);
     const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
@@ -527,7 +531,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     bc.quad += bc2.quad;
     if (kTileBufs == 1 && j0 + 32 < items) {
       __syncwarp();  // every lane is done with the tile
-      M_next = chunk_M(j0 + 32);
+      M_next = M_pre;
       Mw_next = __reduce_max_sync(kFull, M_next);
       chunk_stage(j0 + 32, Mw_next, 0);
     }
@@ -537,7 +541,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     for (int side = 0; side < 2; ++side) {
       const int S = side == 0 ? a.S_left : a.S_right;
       const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
-      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, S, guess[jj * 2 + side], xd, yd);
+      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, S, side == 0 ? (g2 & 0xff) : (g2 >> 8), xd, yd);
       const double* sg = sg0 + bi * kSegStride;
       bar_add(bl, fma(sg[8], yd, sg[7] * xd) - sg[9], P);
       if (act) nidx[jj * 2 + side] = (unsigned char)bi;
@@ -657,6 +661,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
       cp_async_wait<0>();
     }
     __syncwarp();
+    const int M_pre = (kTileBufs == 1 && g0 + kKnotsPerPass < nk) ? pass_M(g0 + kKnotsPerPass) : 0;  // used after the plane loop
     const bool act = d < kDisc && g0 + kl < nk;
     const int ko = act ? g0 + kl : 0;  // knot inside the window
     const int k = k0 + ko;
@@ -690,7 +695,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     }
     if (kTileBufs == 1 && g0 + kKnotsPerPass < nk) {
       __syncwarp();  // every lane is done with the tile
-      M_next = pass_M(g0 + kKnotsPerPass);
+      M_next = M_pre;
       Mw_next = __reduce_max_sync(kFull, M_next);
       pass_stage(g0 + kKnotsPerPass, Mw_next, 0);
     }
@@ -1734,7 +1739,9 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
   const int wt[4] = {5, 4, 5, 3};
   unsigned naps = 0;
+  unsigned st_pass = 0, st_poll = 0, st_fail = 0, st_ph[4] = {0, 0, 0, 0}, st_sw = 0;
   for (;;) {
+    ++st_pass;
     // ---- snapshot of the context table (all lanes, identical result)
     const volatile int* st = s_state;
     int sl[kCtxWords];
@@ -1755,6 +1762,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       if (!__any_sync(kFull, b)) break;  // every context is DONE
       // the remaining contexts are all being run by other warps: back off (up to ~4 us between polls)
       ++naps;
+      ++st_poll;
       __nanosleep(naps < 16 ? 250 : 4000);
       if (naps > (1u << 22)) break;  // (watchdog: never spin forever)
       continue;
@@ -1772,6 +1780,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
         }
       }
       type = best;
+      ++st_sw;
       if (lane == 0) s_type = type;
     }
     // claim the waiting context of that type that has run the most iterations: scenarios with long
@@ -1795,6 +1804,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     if (lane == 0) got = atomicCAS(&s_state[mine], type, ST_BUSY) == type;
     got = __shfl_sync(kFull, got, 0);
     if (!got) {
+      ++st_fail;
       __nanosleep(100);
       continue;
     }
@@ -1803,6 +1813,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     int next = type;
     do {
       if (next != PH_EVAL) c.seg_staged = false;  // the other phases reuse the segment region of the stage
+      ++st_ph[next];
       if (next == PH_INIT) next = phase_init(c);
       else if (next == PH_BACK) next = phase_back(c);
       else if (next == PH_ROLL) next = phase_roll(c);
@@ -1815,6 +1826,13 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       *(volatile int*)&s_state[mine] = next;
     }
     __syncwarp();
+  }
+  if (a.stats && lane == 0) {
+    atomicAdd(a.stats + 0, (unsigned long long)st_pass);
+    atomicAdd(a.stats + 1, (unsigned long long)st_poll);
+    atomicAdd(a.stats + 2, (unsigned long long)st_fail);
+    for (int p = 0; p < 4; ++p) atomicAdd(a.stats + 3 + p, (unsigned long long)st_ph[p]);
+    atomicAdd(a.stats + 7, (unsigned long long)st_sw);
   }
 }
 

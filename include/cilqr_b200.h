@@ -137,6 +137,9 @@ int cilqr_kernel_launches(const cilqr_handle* h, int64_t* solve_launches);
 int cilqr_last_kernel_ms(cilqr_handle* h, float* ms);      /* CUDA-event time of the last solve kernel */
 int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* warps_per_sm,
                     int* smem_bytes_per_warp);
+/* Scheduler counters of the last solve launch (development aid): scheduler passes, idle polls, failed
+ * context claims, phases run {INIT, BACK, ROLL, EVAL}, phase-type switches -- summed over all warps. */
+int cilqr_debug_stats(cilqr_handle* h, uint64_t out[8]);
 const char* cilqr_strerror(int code);
 const char* cilqr_last_cuda_error(const cilqr_handle* h);
 int cilqr_abi_version(void);

@@ -41,6 +41,10 @@ def child(a):
         solver.synchronize()
         ms.append(solver.last_kernel_ms())
     w, smem = solver.occupancy(N, batch.S, batch.S)
+    try:
+        print("stats", solver.debug_stats(), flush=True)
+    except Exception as e:  # older variant libraries
+        print("stats unavailable", e, flush=True)
     conv = int((ss[:, 0] <= 2).sum().item())
     best = min(ms[1:] or ms)
     print(json.dumps({"lib": os.path.basename(a.lib or "default"), "pad": int(os.environ.get("CILQR_B200_SMEM_PAD", "0")),
@@ -66,6 +70,9 @@ def main():
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--lib", a.lib, "--horizon", str(a.horizon),
                "--batch", str(a.batch), "--reps", str(a.reps)]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        for l in r.stdout.splitlines():
+            if l.startswith("stats"):
+                print(l, flush=True)
         out = [l for l in r.stdout.splitlines() if l.startswith("{")]
         print(out[-1] if out else f"FAILED pad={pad}: {r.stderr[-400:]}", flush=True)
 
