@@ -130,11 +130,14 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   L.trig = even(L.grp + ng * 3);
   L.pl_e = even(L.trig + 2 * K);
   const int e_end = L.pl_e + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
-  // BACK: lin, scr; INIT builds seg/grp while iqr uses scr, so scr lies behind both
+  // LIN: lin window, plane tiles.  BACK: record ring, scr.  INIT builds seg/grp while iqr uses scr, so scr
+  // lies behind both
   L.lin = 0;
-  L.scr = std::max(even(cilqr::kWin * cilqr::kLinStride), L.trig);
-  L.pl_b = L.scr + cilqr::kScratch;
-  const int b_end = L.pl_b + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
+  L.pl_b = even(cilqr::kWin * cilqr::kLinStride);
+  const int l_end = L.pl_b + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
+  L.bring = 0;
+  L.scr = std::max(even(2 * cilqr::kBackChunk * cilqr::kRecStride), L.trig);
+  const int b_end = std::max(L.scr + cilqr::kScratch, l_end);
   // ROLL: ring
   L.ring = 0;
   const int total = std::max(std::max(e_end, b_end), cilqr::kRingDoubles);
@@ -150,7 +153,8 @@ CtxLayout make_ctx_layout(int N, int M_max, int S_left, int S_right) {
   C.planes = 0;
   C.slots = M_max * 3 * Kc;
   C.gains = C.slots + cilqr::kTrajSlots * 8 * Kc;
-  C.seg = C.gains + (N + cilqr::kRollChunk - 1) / cilqr::kRollChunk * cilqr::kRollChunk * cilqr::kGainStride;
+  C.lin = C.gains + (N + cilqr::kRollChunk - 1) / cilqr::kRollChunk * cilqr::kRollChunk * cilqr::kGainStride;
+  C.seg = C.lin + (K + cilqr::kBackChunk - 1) / cilqr::kBackChunk * cilqr::kBackChunk * cilqr::kRecStride;
   C.grp = C.seg + S * cilqr::kSegStride;
   C.nidx = even(C.grp + ng * 3);
   C.nidx_bytes = (K * 10 + 7) / 8 * 8;

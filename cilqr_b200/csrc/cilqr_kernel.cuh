@@ -47,6 +47,8 @@ constexpr int kLinStride = 37;    // doubles per knot in the linearisation windo
 constexpr int kSegStride = 10;    // sx sy ex ey ux uy len a b c
 constexpr int kGainStride = 16;   // K (2x6), k (2), pad (2): one 128-byte record per knot
 constexpr int kRollChunk = 4;     // knots per cp.async stage of the rollout ring
+constexpr int kRecStride = 40;    // doubles per knot of the linearisation records in the context (16-byte pieces)
+constexpr int kBackChunk = 4;     // knots per cp.async stage of the Riccati ring
 constexpr int kRingDoubles = 2 * (8 * kRollChunk + kGainStride * kRollChunk);
 #ifndef CILQR_GROUP
 #define CILQR_GROUP 4
@@ -79,7 +81,8 @@ static_assert(kWin >= 1 && kWin <= 32, "linearisation window is at most one knot
 #endif
 constexpr int kCtaWarps = CILQR_CTA_WARPS;  // warps per CTA (one CTA per SM)
 
-enum Phase : int { PH_INIT = 0, PH_BACK = 1, PH_ROLL = 2, PH_EVAL = 3, PH_DONE = 4 };
+enum Phase : int { PH_INIT = 0, PH_BACK = 1, PH_ROLL = 2, PH_EVAL = 3, PH_LIN = 4, PH_DONE = 5 };
+constexpr int kNumTypes = 5;
 
 // linearisation record offsets
 constexpr int LA = 0;    // A02 A03 A04 A05 A12 A13 A14 A15 A23 A24 A25
@@ -109,7 +112,7 @@ struct DevParams {
 //   EVAL: seg, grp, trig, pl_e   BACK: lin, scr, pl_b   ROLL: ring   INIT: seg, grp (built here), scr
 // pl_*: two buffers of M_max * kPlaneTile doubles, the cp.async double buffer of corridor-plane tiles
 struct SmemLayout {
-  int seg, grp, trig, lin, scr, ring, pl_e, pl_b;
+  int seg, grp, trig, lin, scr, ring, pl_e, pl_b, bring;
   int total_bytes;
 };
 
@@ -118,6 +121,7 @@ struct CtxLayout {
   int planes;  // [M_max][3][Kc]    shrunk + normalised half-planes, knot-minor
   int slots;   // [5][8][Kc]        trajectories x0..x5,u0,u1 component-major (lane == knot coalesces)
   int gains;   // [Npad][16]        K (2x6 row-major), k (2), pad
+  int lin;     // [Kpad][40]        linearisation records of the iterate (LIN -> BACK)
   int seg;     // [S_left+S_right][10]
   int grp;     // [groups][3]       bounding circles cx, cy, r
   int nidx;    // 2 byte arrays [K][5][2] of nearest-segment indices
@@ -359,6 +363,7 @@ struct Ctx {
   __device__ __forceinline__ double* planes() const { return cx + a.cl.planes; }
   __device__ __forceinline__ double* slot(int i) const { return cx + a.cl.slots + i * 8 * a.Kc; }
   __device__ __forceinline__ double* gains() const { return cx + a.cl.gains; }
+  __device__ __forceinline__ double* linrec() const { return cx + a.cl.lin; }
   __device__ __forceinline__ double* gseg() const { return cx + a.cl.seg; }
   __device__ __forceinline__ double* ggrp() const { return cx + a.cl.grp; }
   __device__ __forceinline__ unsigned char* nidx(int i) const {
@@ -797,13 +802,54 @@ constexpr int SQL = 162;  // 8   ql
 constexpr int SKH = 170;  // 14  Kh  [2][7]
 static_assert(SKH + 14 <= SK, "scratch overflow");
 
-__device__ __noinline__ void backward_pass(const Ctx& c, double lambda, const double* Xs, const unsigned char* nidx,
-                                           double dV[2], const DebugPtrs* dbg, int b) {
+// LIN phase body: linearise + quadratise every knot of the iterate in windows of kWin knots (shared
+// memory), and flush the records to the context, where the Riccati sweep of the BACK phase streams
+// them from.  (One phase for both was 57 KB of code -- more than the ~32 KB an SM's instruction cache
+// feeds to unaligned warps -- and spilled at 128 registers.)
+__device__ __noinline__ void linearize_all(const Ctx& c, const double* Xs, const unsigned char* nidx,
+                                           const DebugPtrs* dbg, int b) {
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
   double* lin = c.sm + a.sm.lin;
+  double* R = c.linrec();
+  for (int k0 = 0; k0 < K; k0 += kWin) {
+    const int k = k0 + lane;
+    const int nk = K - k0 < kWin ? K - k0 : kWin;
+    const bool lin_lane = lane < kWin && k < K;
+    __syncwarp();
+    if (lin_lane) linearize_knot(c, k, Xs, lin + lane * kLinStride);
+    __syncwarp();
+    linearize_discs(c, k0, nk, Xs, nidx, lin);
+    if (dbg) {
+      if (lin_lane) {
+        const double* rec = lin + lane * kLinStride;
+        if (k < N) {
+          if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
+          if (dbg->Ju) for (int i = 0; i < 2; ++i) dbg->Ju[((size_t)b * N + k) * 2 + i] = rec[LJU + i];
+          if (dbg->Hu) for (int i = 0; i < 2; ++i) dbg->Hu[((size_t)b * N + k) * 2 + i] = rec[LHU + i];
+        }
+        if (dbg->Jx) for (int i = 0; i < 6; ++i) dbg->Jx[((size_t)b * K + k) * 6 + i] = rec[LJX + i];
+        if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
+      }
+    }
+    // window -> context, coalesced (record stride 37 in shared memory, 40 in the context)
+#pragma unroll 1
+    for (int idx = lane; idx < nk * kRecStride; idx += 32) {
+      const int kk = idx / kRecStride, i = idx - kk * kRecStride;
+      R[(size_t)(k0 + kk) * kRecStride + i] = i < kLinStride ? lin[kk * kLinStride + i] : 0.0;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double dV[2]) {
+  const KernelArgs& a = c.a;
+  const int N = a.N;
+  const int lane = c.lane;
   double* scr = c.sm + a.sm.scr;
+  double* ring = c.sm + a.sm.bring;  // two stages of kBackChunk records
+  const double* R = c.linrec();
   double* gains = c.gains();  // global: K, k of every knot are consumed by the next ROLL phase
   double* M = scr + SM_;
   double* G = scr + SG;
@@ -857,40 +903,38 @@ __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, const do
   const double wsym = vi == vj ? 0.5 : 1.0;  // 0.5 * (1 or 2) y_i V_ij y_j
 
   double acc0 = 0.0, acc1 = 0.0;
-  const int last_chunk = (K - 1) / kWin;
-  for (int ch = last_chunk; ch >= 0; --ch) {
-    const int k0 = ch * kWin;
-    const int k = k0 + lane;
-    const bool lin_lane = lane < kWin && k < K;
-    __syncwarp();
-    if (lin_lane) linearize_knot(c, k, Xs, lin + lane * kLinStride);
-    __syncwarp();
-    linearize_discs(c, k0, (K - k0 < kWin ? K - k0 : kWin), Xs, nidx, lin);
-    if (dbg) {
-      if (lin_lane) {
-        const double* rec = lin + lane * kLinStride;
-        if (k < N) {
-          if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
-          if (dbg->Ju) for (int i = 0; i < 2; ++i) dbg->Ju[((size_t)b * N + k) * 2 + i] = rec[LJU + i];
-          if (dbg->Hu) for (int i = 0; i < 2; ++i) dbg->Hu[((size_t)b * N + k) * 2 + i] = rec[LHU + i];
-        }
-        if (dbg->Jx) for (int i = 0; i < 6; ++i) dbg->Jx[((size_t)b * K + k) * 6 + i] = rec[LJX + i];
-        if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
-      }
+  // Vx = cost_Jx.back(), Vxx = cost_Hx.back()    (:343-344): the terminal record straight from the context
+  {
+    const double* rec = R + (size_t)N * kRecStride;
+    for (int e = lane; e < 42; e += 32) {
+      const int i = e / 6, j = e % 6;
+      M[e] = i == 6 ? rec[LJX + j] : rec[h_off(i < j ? i : j, i < j ? j : i)];
     }
-    int kend = k0 + kWin - 1;
+  }
+  constexpr int kStageD = kBackChunk * kRecStride;
+  auto prefetch = [&](int q, int s) {  // records of knots [4q, 4q+4) -> stage s (the context pads to whole chunks)
+    const double* src = R + (size_t)q * kStageD;
+    double* dst = ring + s * kStageD;
+    for (int i = lane; i < kStageD / 2; i += 32) cp_async16(dst + i * 2, src + i * 2);
+    cp_async_commit();
+  };
+  const int q_last = (N - 1) / kBackChunk;
+  prefetch(q_last, 0);
+  int stage = 0;
+  for (int q = q_last; q >= 0; --q, stage ^= 1) {
+    if (q > 0) {
+      prefetch(q - 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const int k0 = q * kBackChunk;
+    int kend = k0 + kBackChunk - 1;
     if (kend > N - 1) kend = N - 1;
-    if (ch == last_chunk) {
-      // Vx = cost_Jx.back(), Vxx = cost_Hx.back()    (:343-344)
-      const double* rec = lin + (N - k0) * kLinStride;
-      for (int e = lane; e < 42; e += 32) {
-        const int i = e / 6, j = e % 6;
-        M[e] = i == 6 ? rec[LJX + j] : rec[h_off(i < j ? i : j, i < j ? j : i)];
-      }
-      __syncwarp();
-    }
+    const double* lin = ring + stage * kStageD;
     for (int kn = kend; kn >= k0; --kn) {
-      const double* rec = lin + (kn - k0) * kLinStride;
+      const double* rec = lin + (kn - k0) * kRecStride;
       // ---- S1: G = M F
       {
         double f[6];
@@ -1521,7 +1565,18 @@ __device__ __noinline__ int phase_roll(Ctx& c) {
   return PH_EVAL;
 }
 
-// BACK: linearise + quadratise + Riccati sweep (:203-233), gradient-norm exit (:235-241).
+// LIN: linearise + quadratise the iterate (:203-214) -> records in the context.
+__device__ __noinline__ int phase_lin(Ctx& c) {
+  const KernelArgs& a = c.a;
+  CtxHdr* h = c.h;
+  const unsigned b = h->b;
+  c.bind(b);
+  const DebugPtrs* dbg = (a.debug && h->iter == 0) ? &a.dbg : nullptr;
+  linearize_all(c, c.slot(h->cur), c.nidx(h->nflip), dbg, (int)b);
+  return PH_BACK;
+}
+
+// BACK: Riccati sweep (:216-233), gradient-norm exit (:235-241).
 __device__ __noinline__ int phase_back(Ctx& c) {
   const KernelArgs& a = c.a;
   const int N = a.N, lane = c.lane;
@@ -1532,7 +1587,7 @@ __device__ __noinline__ int phase_back(Ctx& c) {
   const double lambda = h->lambda;
   const double* Xs = c.slot(h->cur);
   double dV[2];
-  backward_pass(c, lambda, Xs, c.nidx(h->nflip), dV, dbg, (int)b);
+  backward_pass(c, lambda, dV);
   __syncwarp();
   const double* gains = c.gains();
   if (dbg) {
@@ -1602,7 +1657,7 @@ __device__ __noinline__ int phase_eval(Ctx& c) {
         for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nn[i];
       }
     }
-    return PH_BACK;
+    return PH_LIN;
   }
   // ---- line search (:246-265): candidates in the reference's order until the first accept
   int ai = h->ai;
@@ -1673,7 +1728,7 @@ __device__ __noinline__ int phase_eval(Ctx& c) {
         return PH_INIT;
       }
       if (lane == 0) h->iter = iter + 1;
-      return PH_BACK;
+      return PH_LIN;
     }
     // rejected: next step size
     ++ai;
@@ -1704,7 +1759,7 @@ __device__ __noinline__ int phase_eval(Ctx& c) {
       finish_scenario(c);
       return PH_INIT;
     }
-    return PH_BACK;
+    return PH_LIN;
   }
 }
 
@@ -1719,7 +1774,7 @@ __device__ __noinline__ int phase_eval(Ctx& c) {
 // inside the ~32 KB the instruction cache can feed to unaligned warps.  A context whose next phase is
 // again s_type (EVAL -> EVAL: the next step size of the line search) keeps its warp.  Warps never wait
 // for each other; they only nap when every live context is being run by another warp.
-constexpr int ST_BUSY = 5;
+constexpr int ST_BUSY = 6;
 __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) double smem_cta[];
   __shared__ int s_state[kMaxCtx];
@@ -1737,9 +1792,10 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   if (threadIdx.x == 0) s_type = PH_INIT;
   __syncthreads();
   // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
-  const int wt[4] = {5, 4, 5, 3};
+  // typical duration of the phases relative to one another: INIT 5, BACK 2, ROLL 5, EVAL 3, LIN 3
+  const int wt[kNumTypes] = {5, 2, 5, 3, 3};
   unsigned naps = 0;
-  unsigned st_pass = 0, st_poll = 0, st_fail = 0, st_ph[4] = {0, 0, 0, 0}, st_sw = 0;
+  unsigned st_pass = 0, st_poll = 0, st_fail = 0, st_ph[kNumTypes] = {0, 0, 0, 0, 0}, st_sw = 0;
   for (;;) {
     ++st_pass;
     // ---- snapshot of the context table (all lanes, identical result)
@@ -1747,15 +1803,15 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     int sl[kCtxWords];
 #pragma unroll
     for (int w = 0; w < kCtxWords; ++w) sl[w] = st[lane + 32 * w];
-    int cnt[4];
+    int cnt[kNumTypes];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < kNumTypes; ++p) {
       int n = 0;
 #pragma unroll
       for (int w = 0; w < kCtxWords; ++w) n += __popc(__ballot_sync(kFull, sl[w] == p));
       cnt[p] = n;
     }
-    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) {
+    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] == 0) {
       bool b = false;
 #pragma unroll
       for (int w = 0; w < kCtxWords; ++w) b |= sl[w] == ST_BUSY;
@@ -1772,7 +1828,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     if (cnt[type] == 0) {
       int best = 0, best_score = -1;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < kNumTypes; ++p) {
         const int score = cnt[p] ? cnt[p] * wt[p] : -1;
         if (score > best_score) {
           best_score = score;
@@ -1816,6 +1872,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       ++st_ph[next];
       if (next == PH_INIT) next = phase_init(c);
       else if (next == PH_BACK) next = phase_back(c);
+      else if (next == PH_LIN) next = phase_lin(c);
       else if (next == PH_ROLL) next = phase_roll(c);
       else next = phase_eval(c);
       __syncwarp();
@@ -1831,7 +1888,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     atomicAdd(a.stats + 0, (unsigned long long)st_pass);
     atomicAdd(a.stats + 1, (unsigned long long)st_poll);
     atomicAdd(a.stats + 2, (unsigned long long)st_fail);
-    for (int p = 0; p < 4; ++p) atomicAdd(a.stats + 3 + p, (unsigned long long)st_ph[p]);
+    for (int p = 0; p < 4; ++p) atomicAdd(a.stats + 3 + p, (unsigned long long)st_ph[p]);  // (LIN count == BACK count)
     atomicAdd(a.stats + 7, (unsigned long long)st_sw);
   }
 }
