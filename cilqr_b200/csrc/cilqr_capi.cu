@@ -134,7 +134,8 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   // lies behind both
   L.lin = 0;
   L.pl_b = even(cilqr::kWin * cilqr::kLinStride);
-  const int l_end = L.pl_b + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
+  L.red = L.pl_b + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;  // [9][32] disc-lane partial sums
+  const int l_end = L.red + 9 * 32;
   L.bring = 0;
   L.scr = std::max(even(2 * cilqr::kBackChunk * cilqr::kRecStride), L.trig);
   const int b_end = std::max(L.scr + cilqr::kScratch, l_end);

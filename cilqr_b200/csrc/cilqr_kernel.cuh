@@ -112,7 +112,7 @@ struct DevParams {
 //   EVAL: seg, grp, trig, pl_e   BACK: lin, scr, pl_b   ROLL: ring   INIT: seg, grp (built here), scr
 // pl_*: two buffers of M_max * kPlaneTile doubles, the cp.async double buffer of corridor-plane tiles
 struct SmemLayout {
-  int seg, grp, trig, lin, scr, ring, pl_e, pl_b, bring;
+  int seg, grp, trig, lin, scr, ring, pl_e, pl_b, bring, red;
   int total_bytes;
 };
 
@@ -711,33 +711,26 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
         plane(sg[7], sg[8], sg[9]);
       }
     }
-    // sum over the five disc lanes of each knot: (d0 + d3) + (d1 + d4), then + d2
-    auto red = [&](double v) {
-      const double hi = __shfl_down_sync(kFull, v, 3 * kKnotsPerPass);
-      v += c.lane < 2 * kKnotsPerPass ? hi : 0.0;
-      const double a1 = __shfl_down_sync(kFull, v, kKnotsPerPass);
-      const double a2 = __shfl_down_sync(kFull, v, 2 * kKnotsPerPass);
-      return (v + a1) + a2;
-    };
-    J0 = red(J0);
-    J1 = red(J1);
-    J2 = red(J2);
-    H00 = red(H00);
-    H01 = red(H01);
-    H02 = red(H02);
-    H11 = red(H11);
-    H12 = red(H12);
-    H22 = red(H22);
+    // sum over the five disc lanes of each knot through shared memory, in the fixed order
+    // ((d0 + d3) + (d1 + d4)) + d2
+    double* rb = c.sm + a.sm.red;  // [9][32]
+    rb[0 * 32 + c.lane] = J0;
+    rb[1 * 32 + c.lane] = J1;
+    rb[2 * 32 + c.lane] = J2;
+    rb[3 * 32 + c.lane] = H00;
+    rb[4 * 32 + c.lane] = H01;
+    rb[5 * 32 + c.lane] = H02;
+    rb[6 * 32 + c.lane] = H11;
+    rb[7 * 32 + c.lane] = H12;
+    rb[8 * 32 + c.lane] = H22;
+    __syncwarp();
     if (d == 0 && act) {
-      rec[LJX + 0] += J0;
-      rec[LJX + 1] += J1;
-      rec[LJX + 2] += J2;
-      rec[LHX + 0] += H00;
-      rec[LHX + 1] += H01;
-      rec[LHX + 2] += H02;
-      rec[LHX + 3] += H11;
-      rec[LHX + 4] += H12;
-      rec[LHX + 5] += H22;
+#pragma unroll 1
+      for (int v = 0; v < 9; ++v) {
+        const double* r = rb + v * 32 + kl;
+        const double sum = ((r[0] + r[3 * kKnotsPerPass]) + (r[kKnotsPerPass] + r[4 * kKnotsPerPass])) + r[2 * kKnotsPerPass];
+        rec[v < 3 ? LJX + v : LHX + v - 3] += sum;
+      }
     }
     __syncwarp();  // records updated; the tile is dead
     M = M_next;
