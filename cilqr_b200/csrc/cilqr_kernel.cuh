@@ -1276,7 +1276,7 @@ __device__ __noinline__ void copy_traj(const Ctx& c, const double* Xs, double* s
 }
 
 // lane segments + group circles of the context -> this warp's shared-memory stage
-__device__ __forceinline__ void stage_segments(Ctx& c) {
+__device__ __noinline__ void stage_segments(Ctx& c) {
   const KernelArgs& a = c.a;
   if (c.seg_staged) return;
   c.seg_staged = true;
@@ -1338,7 +1338,7 @@ __device__ __noinline__ void finish_scenario(const Ctx& c) {
 }
 
 // iter_trajs.push_back (ilqr_optimizer.cc:170,294) and cost_.push_back (:173,283,296) when requested
-__device__ __forceinline__ void push_traj(const Ctx& c, const double* Xs) {
+__device__ __noinline__ void push_traj(const Ctx& c, const double* Xs) {
   const KernelArgs& a = c.a;
   CtxHdr* h = c.h;
   const int n = h->n_iter_traj;
@@ -1349,7 +1349,7 @@ __device__ __forceinline__ void push_traj(const Ctx& c, const double* Xs) {
   __syncwarp();
   if (c.lane == 0) h->n_iter_traj = n + 1;
 }
-__device__ __forceinline__ void push_cost(const Ctx& c, const double cost5[5]) {
+__device__ __noinline__ void push_cost(const Ctx& c, const double cost5[5]) {
   const KernelArgs& a = c.a;
   CtxHdr* h = c.h;
   const int n = h->n_cost;
