@@ -138,7 +138,8 @@ struct CtxHdr {
   unsigned int b, ahash;     // scenario id, FNV-1a over the line-search outcome per iteration
   int iter, status, cur, nflip, ai, gb, rmode, emode, n_cost, n_iter_traj;
   unsigned int retired, deferred;  // line-search lanes whose rollout blew up / needs the general wrap
-  int pad_[2];
+  int imode;  // 1 while the context builds its initial guess (the BACK phase then runs the iqr sweep)
+  int pad_;
 };
 static_assert(sizeof(CtxHdr) == kHdrDoubles * 8, "CtxHdr size");
 
@@ -1120,135 +1121,50 @@ __device__ __noinline__ unsigned rollout(const Ctx& c, int cur, unsigned want, i
   return retired | (deferred << 16);
 }
 
-// iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control).  Leaves the
-// NEGATED gains -K_k in the context's gain records (k_k = 0) and (xbar, ubar) = (goals, 0) in slot
-// Xs, so that rollout(..., iqr = true) evaluates u_k = clamp(-K_k (x - goal_k)) and the RK2 rollout
-// of :830-841.  A_k, B_k about the goals are parked in the gain records until the sweep consumes them.
-__device__ void iqr_gains(const Ctx& c, double* Xs) {
+// iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control), Q = diag(1e-3, 1e-3,
+// 1e-3, 1e-3, 1e-2, 5e-3), R = diag(0.2, 0.05) (off-diagonals 0, quirk Q4).  It is the Riccati recursion of
+// Backward with Jx = Ju = 0, Hx = Q, Hu = R, lambda = 0 -- K_k = (R + B'PB)^-1 B'PA, P = Q + A'P(A - BK) is
+// algebraically the same value update -- so INIT only writes the "linearisation records" of that LQ problem
+// (A_k, B_k about goal_k with zero control) and the BACK phase does the sweep; its gains -(Quu)^-1 Qux are
+// the -K_lqr the rollout adds, k = 0 because the gradient stays zero.  (xbar, ubar) = (goals, 0) go to slot Xs.
+__device__ void iqr_records(const Ctx& c, double* Xs) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int N = a.N, lane = c.lane;
-  double* Kg = c.gains();
-  double* scr = c.sm + a.sm.scr;
-  const double B30 = 0.5 * P.dt * P.dt, B40 = P.dt, B51 = P.dt;
-  for (int k = lane; k < N; k += 32) {
-    double g[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) g[i] = c.goal(k, i);
-    double A11[11], b21;
-    dynamics_jacobian(P, g, 0.0, A11, &b21);
-#pragma unroll
-    for (int i = 0; i < 11; ++i) Kg[k * kGainStride + i] = A11[i];
-    Kg[k * kGainStride + 11] = b21;
-  }
+  double* R = c.linrec();
   const double Qd[6] = {0.001, 0.001, 0.001, 0.001, 0.01, 0.005};
-  for (int e = lane; e < 36; e += 32) scr[SV + e] = (e / 6 == e % 6) ? Qd[e / 6] : 0.0;
-  __syncwarp();
-  double* Pm = scr + SV;     // P
-  double* AtP = scr + SW;    // A^T P
-  double* Nf = scr + SN;
-  double* BtP = scr + SBV;   // 2x6
-  double* Cm = scr + SQXX;   // A - B K
-  double* G = scr + SQUX;    // B^T P A
-  double* S4 = scr + SQUU;   // R + B^T P B
-  double* Kl = scr + ST;     // K of this knot, 2x6
-  double nxt[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) nxt[i] = Kg[(N - 1) * kGainStride + i];
-  for (int k = N - 1; k >= 0; --k) {
-    double rec[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) rec[i] = nxt[i];
-    if (k > 0) {  // the parked record of the next knot travels from L2 while this knot is processed
-#pragma unroll
-      for (int i = 0; i < 12; ++i) nxt[i] = Kg[(k - 1) * kGainStride + i];
-    }
-    const double b21 = rec[11];
-    __syncwarp();
-    if (lane < 24) {
-      const int r = lane / 6, cc = lane % 6;
-      double v = 0.0;
-      if (r == 0 && cc >= 2) v = rec[cc - 2];
-      else if (r == 1 && cc >= 2) v = rec[4 + cc - 2];
-      else if (r == 2 && cc >= 3) v = rec[8 + cc - 3];
-      else if (r == 3 && cc == 4) v = P.dt;
-      Nf[lane] = v;
-    }
-    if (lane < 12) {
-      const int rr = lane / 6, j = lane % 6;
-      BtP[lane] = rr == 0 ? fma(B40, Pm[24 + j], B30 * Pm[18 + j]) : fma(B51, Pm[30 + j], b21 * Pm[12 + j]);
-    }
-    __syncwarp();
-    // AtP = P + Nf^T P ; G = BtP A ; S = R + BtP B
-    for (int e = lane; e < 36; e += 32) {
-      const int r = e / 6, j = e % 6;
-      double v = Pm[e];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v = fma(Nf[i * 6 + r], Pm[i * 6 + j], v);
-      AtP[e] = v;
-    }
-    if (lane < 12) {
-      const int rr = lane / 6, cc = lane % 6;
-      double q = BtP[lane];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) q = fma(BtP[rr * 6 + r], Nf[r * 6 + cc], q);
-      G[lane] = q;
-    } else if (lane < 16) {
-      const int e = lane - 12, ra = e / 2, cb = e % 2;
-      const double rdiag = ra == cb ? (ra == 0 ? 0.2 : 0.05) : 0.0;
-      S4[e] = rdiag + (cb == 0 ? fma(BtP[ra * 6 + 4], B40, BtP[ra * 6 + 3] * B30)
-                               : fma(BtP[ra * 6 + 5], B51, BtP[ra * 6 + 2] * b21));
-    }
-    __syncwarp();
-    {
-      const double det = S4[0] * S4[3] - S4[2] * S4[1];
-      const double invdet = 1.0 / det;
-      const double i00 = S4[3] * invdet, i01 = -S4[1] * invdet, i10 = -S4[2] * invdet, i11 = S4[0] * invdet;
-      if (lane < 12) {
-        const int rr = lane / 6, cc = lane % 6;
-        const double kv = rr == 0 ? fma(i01, G[6 + cc], i00 * G[cc]) : fma(i11, G[6 + cc], i10 * G[cc]);
-        Kl[lane] = kv;
-        Kg[k * kGainStride + lane] = -kv;  // the rollout adds K (x - xbar): store -K_lqr
-      } else if (lane < 14) {
-        Kg[k * kGainStride + lane] = 0.0;  // k_k = 0
-      }
-    }
-    __syncwarp();
-    // C = A - B K
-    for (int e = lane; e < 36; e += 32) {
-      const int r = e / 6, j = e % 6;
-      double av = (r == j ? 1.0 : 0.0) + (r < 4 ? Nf[r * 6 + j] : 0.0);
-      double bk = 0.0;
-      if (r == 2) bk = b21 * Kl[6 + j];
-      else if (r == 3) bk = B30 * Kl[j];
-      else if (r == 4) bk = B40 * Kl[j];
-      else if (r == 5) bk = B51 * Kl[6 + j];
-      Cm[e] = av - bk;
-    }
-    __syncwarp();
-    // P = Q + AtP C   (entry `lane`, and entry `lane + 32` on lanes 0..3)
-    double pn0, pn1 = 0.0;
-    {
-      const int r = lane / 6, j = lane % 6;
-      double v = AtP[r * 6] * Cm[j];
-#pragma unroll
-      for (int m = 1; m < 6; ++m) v = fma(AtP[r * 6 + m], Cm[m * 6 + j], v);
-      pn0 = (r == j ? Qd[r] : 0.0) + v;
-    }
-    if (lane < 4) {
-      const int j = lane + 2;
-      double v = AtP[30] * Cm[j];
-#pragma unroll
-      for (int m = 1; m < 6; ++m) v = fma(AtP[30 + m], Cm[m * 6 + j], v);
-      pn1 = (j == 5 ? Qd[5] : 0.0) + v;
-    }
-    __syncwarp();
-    Pm[lane] = pn0;
-    if (lane < 4) Pm[32 + lane] = pn1;
-  }
-  __syncwarp();
-  // (xbar, ubar) = (goals, 0)
   for (int k = lane; k <= N; k += 32) {
+    double* rec = R + (size_t)k * kRecStride;
+    if (k < N) {
+      double g[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g[i] = c.goal(k, i);
+      double A11[11], b21;
+      dynamics_jacobian(P, g, 0.0, A11, &b21);
+#pragma unroll
+      for (int i = 0; i < 11; ++i) rec[LA + i] = A11[i];
+      rec[LB21] = b21;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rec[LJX + i] = 0.0;
+    rec[LJU] = 0.0;
+    rec[LJU + 1] = 0.0;
+    rec[LHX + 0] = Qd[0];
+    rec[LHX + 1] = 0.0;
+    rec[LHX + 2] = 0.0;
+    rec[LHX + 3] = Qd[1];
+    rec[LHX + 4] = 0.0;
+    rec[LHX + 5] = Qd[2];
+    rec[LHX + 6] = Qd[3];
+    rec[LHX + 7] = Qd[4];
+    rec[LHX + 8] = Qd[5];
+    rec[LHU] = 0.2;
+    rec[LHU + 1] = 0.05;
+    rec[LZ] = 0.0;
+    rec[LO] = 1.0;
+    rec[LDT] = P.dt;
+    rec[LB30] = 0.5 * P.dt * P.dt;
+    // (xbar, ubar) = (goals, 0)
 #pragma unroll
     for (int i = 0; i < 6; ++i) Xs[i * a.Kc + k] = c.goal(k, i);
     Xs[6 * a.Kc + k] = 0.0;
@@ -1407,6 +1323,7 @@ __device__ __noinline__ int phase_init(Ctx& c) {
     h->n_iter_traj = 0;
     h->rmode = 0;
     h->emode = 0;
+    h->imode = 1;
     h->retired = 0;
     h->deferred = 0;
   }
@@ -1505,13 +1422,13 @@ __device__ __noinline__ int phase_init(Ctx& c) {
     }
   }
   __syncwarp();
-  iqr_gains(c, c.slot(0));
+  iqr_records(c, c.slot(0));
   // no previous iterate: any valid index is an upper bound for the nearest-segment search
   unsigned char* n0 = c.nidx(0);
 #pragma unroll 1
   for (int i = lane; i < a.cl.nidx_bytes; i += 32) n0[i] = 0;
   __syncwarp();
-  return PH_ROLL;
+  return PH_BACK;  // the iqr sweep
 }
 
 // ROLL: the initial-guess rollout (:830-841), the speculative rollout of one group of four step sizes
@@ -1577,11 +1494,19 @@ __device__ __noinline__ int phase_back(Ctx& c) {
   const unsigned b = h->b;
   c.bind(b);
   const DebugPtrs* dbg = (a.debug && h->iter == 0) ? &a.dbg : nullptr;
-  const double lambda = h->lambda;
+  const bool iqr = h->imode != 0;
+  const double lambda = iqr ? 0.0 : h->lambda;
   const double* Xs = c.slot(h->cur);
   double dV[2];
   backward_pass(c, lambda, dV);
   __syncwarp();
+  if (iqr) {  // gains of the LQR initial guess (:793-824) are in place: roll it out (:830-841)
+    if (lane == 0) {
+      h->imode = 0;
+      h->rmode = 0;
+    }
+    return PH_ROLL;
+  }
   const double* gains = c.gains();
   if (dbg) {
     for (int k = lane; k < N; k += 32) {
