@@ -299,11 +299,24 @@ __device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P)
 __device__ __forceinline__ double bar_value(const BarAcc& a, const DevParams& P) {
   return a.quad - P.rt * nt_log(a.prod);
 }
+// 1 / g for a normal, non-zero g (here g < -eps): hardware seed + three Newton steps.  Not correctly
+// rounded like the IEEE division (<= 1 ulp off), a third of its instructions, no slow-path call.
+__device__ __forceinline__ double fast_rcp(double g) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(g));
+  double e = fma(-g, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-g, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-g, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 // barrier_function.h:115-140: coefficient of dx in the Jacobian (cj), of dx dx^T (co) and of ddx (cd)
 __device__ __forceinline__ void bar_coef(double g, const DevParams& P, double& cj, double& co,
                                          double& cd) {
   if (g < -P.eps) {
-    const double inv = 1.0 / g;
+    const double inv = fast_rcp(g);
     const double q = P.rt * inv;
     cj = -q;
     co = q * inv;
