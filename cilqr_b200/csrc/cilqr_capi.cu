@@ -141,7 +141,7 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   const int b_end = std::max(L.scr + cilqr::kScratch, l_end);
   // ROLL: ring
   L.ring = 0;
-  const int total = std::max(std::max(e_end, b_end), cilqr::kRingDoubles);
+  const int total = std::max(std::max(e_end, b_end), cilqr::kRollGroups * cilqr::kRingDoubles);
   L.total_bytes = (total * 8 + 15) / 16 * 16;  // per-warp stages are packed back to back in the CTA
   return L;
 }

@@ -1029,111 +1029,6 @@ __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double d
   dV[1] = warp_sum(acc1);
 }
 
-// Rollout of the closed loop u_k = ubar_k + K_k (x - xbar_k) + alpha k_k for up to four step sizes of
-// the line search at once (Forward, ilqr_optimizer.cc:392-415): lane a < 4 with bit a of `want` set
-// rolls out alpha_{gb+a} and writes its candidate to trajectory slot cand_slot(cur, a) (the other
-// lanes shadow the highest wanted lane and store nothing).  The nominal trajectory (slot `cur`) and
-// the gains stream from the context through a two-stage cp.async ring of kRollChunk knots, so the
-// serial loop only reads shared memory.  The same code produces the LQR initial guess (iqr,
-// ilqr_optimizer.cc:830-841) when called with iqr = true on (xbar, ubar, K, k) = (goals, 0, -K_lqr, 0):
-// the control is then clamped to its bounds instead of angle-wrapped.
-//  * A lane whose state stops being finite is RETIRED: every later state of that rollout would be
-//    non-finite too, its cost NaN/inf, and the reference rejects such a step (the comparisons of
-//    ilqr_optimizer.cc:258 are false).
-//  * allow_general = false: a lane that would need the general (fmod) branch of NormalizeAngle -- a
-//    blown-up rollout -- is DEFERRED instead of dragging the whole warp through that branch at every
-//    step; the caller repeats deferred step sizes with allow_general = true only if the line search
-//    gets to them.
-// Returns retired | deferred << 16 (bit a = candidate a of this group).
-__device__ __noinline__ unsigned rollout(const Ctx& c, int cur, unsigned want, int gb, bool allow_general, bool iqr) {
-  const KernelArgs& a = c.a;
-  const DevParams& P = a.P;
-  const int lane = c.lane;
-  const double* Xs = c.slot(cur);
-  const double* gains = c.gains();
-  double* ring = c.sm + a.sm.ring;
-  constexpr int kStage = 8 * kRollChunk + kGainStride * kRollChunk;  // doubles per ring stage
-  const bool owner = (want >> lane) & 1u;
-  const int ca = owner ? lane : 31 - __clz(want);
-  const double alpha = kAlphaList[gb + ca];
-  double* out = c.slot(cand_slot(cur, ca));
-  double x[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = c.h->g0[i];
-  if (owner) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) out[i * a.Kc] = x[i];
-  }
-  // stage s of the ring: [8][kRollChunk] nominal x0..x5,u0,u1 then [kRollChunk][16] gain records
-  auto prefetch = [&](int k0, int s) {
-    double* st = ring + s * kStage;
-    if (lane < 4 * kRollChunk) {  // 8 components x kRollChunk doubles = 4*kRollChunk 16-byte pieces
-      const int comp = lane / (kRollChunk / 2), part = lane - comp * (kRollChunk / 2);
-      cp_async16(st + comp * kRollChunk + part * 2, Xs + comp * a.Kc + k0 + part * 2);
-    }
-#pragma unroll
-    for (int i = lane; i < kGainStride * kRollChunk / 2; i += 32)
-      cp_async16(st + 8 * kRollChunk + i * 2, gains + (size_t)k0 * kGainStride + i * 2);
-    cp_async_commit();
-  };
-  bool dead = false, defer = false, slow = false;
-  prefetch(0, 0);
-  int stage = 0;
-  for (int k0 = 0; k0 < a.N; k0 += kRollChunk, stage ^= 1) {
-    if (k0 + kRollChunk < a.N) {
-      prefetch(k0 + kRollChunk, stage ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncwarp();
-    const double* st = ring + stage * kStage;
-    const int kn = a.N - k0 < kRollChunk ? a.N - k0 : kRollChunk;
-    for (int kk = 0; kk < kn; ++kk) {
-      const int k = k0 + kk;
-      const double* Kk = st + 8 * kRollChunk + kk * kGainStride;
-      double dx[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) dx[i] = x[i] - st[i * kRollChunk + kk];
-      double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
-#pragma unroll
-      for (int i = 1; i < 6; ++i) {
-        s0 = fma(Kk[i], dx[i], s0);
-        s1 = fma(Kk[6 + i], dx[i], s1);
-      }
-      double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
-      double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
-      if (iqr) {
-        u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
-        u1 = fmin(P.drmax, fmax(u1, P.drmin));
-      } else {
-        u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
-      }
-      rollout_step(P, x, u0, u1, allow_general, slow);
-      if (!iqr && !dead && !defer) {
-        const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
-        if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
-        else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
-      }
-      if (dead || defer) {
-        // park the lane on the nominal trajectory: benign operands for the remaining steps
-#pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k + 1];
-        slow = false;
-      } else if (owner) {
-        out[6 * a.Kc + k] = u0;
-        out[7 * a.Kc + k] = u1;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
-      }
-    }
-    __syncwarp();
-  }
-  const unsigned retired = __ballot_sync(kFull, dead) & want;
-  const unsigned deferred = __ballot_sync(kFull, defer) & want;
-  return retired | (deferred << 16);
-}
-
 // iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control), Q = diag(1e-3, 1e-3,
 // 1e-3, 1e-3, 1e-2, 5e-3), R = diag(0.2, 0.05) (off-diagonals 0, quirk Q4).  It is the Riccati recursion of
 // Backward with Jx = Ju = 0, Hx = Q, Hu = R, lambda = 0 -- K_k = (R + B'PB)^-1 B'PA, P = Q + A'P(A - BK) is
@@ -1444,48 +1339,160 @@ __device__ __noinline__ int phase_init(Ctx& c) {
   return PH_BACK;  // the iqr sweep
 }
 
-// ROLL: the initial-guess rollout (:830-841), the speculative rollout of one group of four step sizes
-// (:246-252), or the faithful repeat of deferred ones.
-__device__ __noinline__ int phase_roll(Ctx& c) {
-  const KernelArgs& a = c.a;
-  CtxHdr* h = c.h;
-  c.bind(h->b);
-  const int cur = h->cur, rmode = h->rmode, gb = h->gb;
-  if (rmode == 0) {
-    rollout(c, cur, 1u, 0, true, true);
-    const int ns = cand_slot(cur, 0);
-    if (a.init_states || a.init_controls) {
-      __syncwarp();
-      copy_traj(c, c.slot(ns), a.init_states ? a.init_states + (size_t)h->b * (a.N + 1) * 6 : nullptr,
-                a.init_controls ? a.init_controls + (size_t)h->b * a.N * 2 : nullptr);
+// ROLL: rollout of the closed loop u_k = ubar_k + K_k (x - xbar_k) + alpha k_k (Forward,
+// ilqr_optimizer.cc:392-415) for up to EIGHT contexts per warp, four lanes each: lane a of a group rolls
+// out step size alpha_{gb+a} of its context's current line-search group and writes the candidate to
+// trajectory slot cand_slot(cur, a) (lanes without a wanted step size shadow the highest wanted lane of
+// their group and store nothing).  The rollout is a serial chain in which only the step sizes are
+// parallel, so one context alone would leave 28 lanes idle.  Every group streams its nominal trajectory
+// (slot `cur`) and gains from its context through its own two-stage cp.async ring of kRollChunk knots;
+// the serial loop only reads shared memory.  The mode comes from the context header:
+//   rmode 0  the LQR initial guess (iqr, :830-841): one candidate, controls clamped to their bounds
+//            instead of angle-wrapped
+//   rmode 1  speculative rollout of a group of four step sizes (:246-252); a lane that would need the
+//            general (fmod) branch of NormalizeAngle -- a blown-up rollout -- is DEFERRED instead of
+//            dragging the warp through that branch at every step
+//   rmode 2  faithful repeat of the deferred step sizes, requested by EVAL only if the search reaches one
+// A lane whose state stops being finite is RETIRED: every later state of that rollout would be non-finite
+// too, its cost NaN/inf, and the reference rejects such a step (the comparisons of :258 are false).
+constexpr int kRollGroups = 8;
+__device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, double* cta_ws, int my_id, int lane) {
+  const DevParams& P = a.P;
+  const int g = lane >> 2, ai = lane & 3;
+  const bool valid = my_id >= 0;
+  const int id0 = __shfl_sync(kFull, my_id, 0);  // group 0 is always valid: benign operands for empty groups
+  double* cx = cta_ws + (size_t)(valid ? my_id : id0) * a.cl.stride;
+  CtxHdr* h = reinterpret_cast<CtxHdr*>(cx + a.cl.hdr);
+  const int cur = h->cur, rmode = h->rmode;
+  const int gb = rmode == 0 ? 0 : h->gb;
+  unsigned want = 1u;
+  if (rmode == 1) want = (1u << (kNAlpha - gb < kSpec ? kNAlpha - gb : kSpec)) - 1u;
+  else if (rmode == 2) want = (h->deferred >> gb) & ((1u << kSpec) - 1u);
+  if (want == 0) want = 1u;  // (cannot happen; keeps the shadow index valid)
+  const bool iqr = rmode == 0, allow_general = rmode != 1;
+  const bool wanted = (want >> ai) & 1u;
+  const bool owner = valid && wanted;
+  const int ca = wanted ? ai : 31 - __clz(want);
+  const double alpha = kAlphaList[gb + ca];
+  const double* Xs = cx + a.cl.slots + cur * 8 * a.Kc;
+  const double* gains = cx + a.cl.gains;
+  double* out = cx + a.cl.slots + cand_slot(cur, ca) * 8 * a.Kc;
+  double* ring = sm + g * kRingDoubles;
+  constexpr int kStage = 8 * kRollChunk + kGainStride * kRollChunk;  // doubles per ring stage
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = h->g0[i];
+  if (owner) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i * a.Kc] = x[i];
+  }
+  // stage s of a group's ring: [8][kRollChunk] nominal x0..x5,u0,u1 then [kRollChunk][16] gain records;
+  // 16 + 32 sixteen-byte pieces per chunk, twelve per lane of the group
+  auto prefetch = [&](int k0, int s) {
+    double* st = ring + s * kStage;
+#pragma unroll
+    for (int p = ai; p < 4 * kRollChunk + kGainStride * kRollChunk / 2; p += 4) {
+      if (p < 4 * kRollChunk) {
+        const int comp = p / (kRollChunk / 2), part = p - comp * (kRollChunk / 2);
+        cp_async16(st + comp * kRollChunk + part * 2, Xs + comp * a.Kc + k0 + part * 2);
+      } else {
+        const int q = p - 4 * kRollChunk;
+        cp_async16(st + 8 * kRollChunk + q * 2, gains + (size_t)k0 * kGainStride + q * 2);
+      }
+    }
+    cp_async_commit();
+  };
+  bool dead = false, defer = false, slow = false;
+  prefetch(0, 0);
+  int stage = 0;
+  for (int k0 = 0; k0 < a.N; k0 += kRollChunk, stage ^= 1) {
+    if (k0 + kRollChunk < a.N) {
+      prefetch(k0 + kRollChunk, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncwarp();
-    if (c.lane == 0) {
-      h->cur = ns;
-      h->emode = 0;
+    const double* st = ring + stage * kStage;
+    const int kn = a.N - k0 < kRollChunk ? a.N - k0 : kRollChunk;
+    for (int kk = 0; kk < kn; ++kk) {
+      const int k = k0 + kk;
+      const double* Kk = st + 8 * kRollChunk + kk * kGainStride;
+      double dx[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dx[i] = x[i] - st[i * kRollChunk + kk];
+      double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
+#pragma unroll
+      for (int i = 1; i < 6; ++i) {
+        s0 = fma(Kk[i], dx[i], s0);
+        s1 = fma(Kk[6 + i], dx[i], s1);
+      }
+      double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
+      double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
+      if (iqr) {
+        u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
+        u1 = fmin(P.drmax, fmax(u1, P.drmin));
+      } else {
+        u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
+      }
+      rollout_step(P, x, u0, u1, allow_general, slow);
+      if (!iqr && !dead && !defer) {
+        const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
+        if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
+        else if (!(fabs(chk) <= 1.7976931348623157e308)) dead = true;  // NaN or inf somewhere in x
+      }
+      if (dead || defer) {
+        // park the lane on the nominal trajectory: benign operands for the remaining steps
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k + 1];
+        slow = false;
+      } else if (owner) {
+        out[6 * a.Kc + k] = u0;
+        out[7 * a.Kc + k] = u1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
+      }
     }
-    return PH_EVAL;
+    __syncwarp();
   }
-  if (rmode == 1) {
-    const int n = kNAlpha - gb < kSpec ? kNAlpha - gb : kSpec;
-    const unsigned fw = rollout(c, cur, (1u << n) - 1u, gb, false, false);
-    if (c.lane == 0) {
-      h->retired |= (fw & 0xffffu) << gb;
-      h->deferred |= (fw >> 16) << gb;
+  const unsigned db = __ballot_sync(kFull, dead), fb = __ballot_sync(kFull, defer);
+  const unsigned ret = (db >> (4 * g)) & want, def = (fb >> (4 * g)) & want;
+  __syncwarp();
+  if (valid && ai == 0) {
+    if (rmode == 0) {
+      h->cur = cand_slot(cur, 0);
+      h->emode = 0;
+    } else if (rmode == 1) {
+      h->retired |= ret << gb;
+      h->deferred |= def << gb;
       h->ai = gb;
       h->emode = 1;
+    } else {
+      h->retired |= ret << gb;
+      h->deferred &= ~(((1u << kSpec) - 1u) << gb);
     }
-    return PH_EVAL;
   }
-  // rmode == 2: the search reached a step size whose rollout needs the general NormalizeAngle branch:
-  // repeat all deferred ones of this group faithfully (lanes = deferred step sizes)
-  const unsigned def = (h->deferred >> gb) & ((1u << kSpec) - 1u);
-  const unsigned fw = rollout(c, cur, def, gb, true, false);
-  if (c.lane == 0) {
-    h->retired |= (fw & 0xffffu) << gb;
-    h->deferred &= ~(((1u << kSpec) - 1u) << gb);
+  if (a.init_states || a.init_controls) {
+    // iter_trajs[0] for the adapter (:170): copy the initial guesses out, one context at a time
+    __syncwarp();
+    for (int gg = 0; gg < kRollGroups; ++gg) {
+      const int id = __shfl_sync(kFull, my_id, gg * 4), rm = __shfl_sync(kFull, rmode, gg * 4);
+      if (id < 0 || rm != 0) continue;
+      double* cg = cta_ws + (size_t)id * a.cl.stride;
+      const CtxHdr* hg = reinterpret_cast<const CtxHdr*>(cg + a.cl.hdr);
+      const int curg = __shfl_sync(kFull, cur, gg * 4);
+      const double* src = cg + a.cl.slots + cand_slot(curg, 0) * 8 * a.Kc;
+      const size_t bb = hg->b;
+      for (int k = lane; k <= a.N; k += 32) {
+        if (a.init_states)
+          for (int i = 0; i < 6; ++i) a.init_states[(bb * (a.N + 1) + k) * 6 + i] = src[i * a.Kc + k];
+        if (a.init_controls && k < a.N) {
+          a.init_controls[(bb * a.N + k) * 2] = src[6 * a.Kc + k];
+          a.init_controls[(bb * a.N + k) * 2 + 1] = src[7 * a.Kc + k];
+        }
+      }
+    }
   }
-  return PH_EVAL;
 }
 
 // LIN: linearise + quadratise the iterate (:203-214) -> records in the context.
@@ -1786,7 +1793,46 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       }
     }
     key = __reduce_max_sync(kFull, key);
-    const int mine = ((key & 255) - rot) & (kMaxCtx - 1);
+    int mine = ((key & 255) - rot) & (kMaxCtx - 1);
+    if (type == PH_ROLL) {
+      // rollouts use four lanes per context: claim up to eight waiting contexts for this warp
+      int my_id = -1, got_n = 0;
+      for (int r = 0; r < kRollGroups && key >= 0; ++r) {
+        int ok = 0;
+        if (lane == 0) ok = atomicCAS(&s_state[mine], type, ST_BUSY) == type;
+        ok = __shfl_sync(kFull, ok, 0);
+        if (ok) {
+          if ((lane >> 2) == got_n) my_id = mine;
+          ++got_n;
+        }
+        // next candidate (this one is taken either way)
+        key = -1;
+#pragma unroll
+        for (int w = 0; w < kCtxWords; ++w) {
+          const int idx = lane + 32 * w;
+          if (idx == mine) sl[w] = ST_BUSY;
+          if (sl[w] == type) {
+            const int k1 = ((s_iter[idx] >> 2) << 8) | ((idx + rot) & (kMaxCtx - 1));
+            key = k1 > key ? k1 : key;
+          }
+        }
+        key = __reduce_max_sync(kFull, key);
+        mine = ((key & 255) - rot) & (kMaxCtx - 1);
+      }
+      if (got_n == 0) {
+        ++st_fail;
+        __nanosleep(100);
+        continue;
+      }
+      __threadfence();  // acquire
+      st_ph[PH_ROLL] += got_n;
+      roll_multi(a, smem, cta_ws, my_id, lane);
+      __threadfence();  // release
+      __syncwarp();
+      if ((lane & 3) == 0 && my_id >= 0) *(volatile int*)&s_state[my_id] = PH_EVAL;
+      __syncwarp();
+      continue;
+    }
     int got = 0;
     if (lane == 0) got = atomicCAS(&s_state[mine], type, ST_BUSY) == type;
     got = __shfl_sync(kFull, got, 0);
@@ -1799,12 +1845,12 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
     int next = type;
     do {
+      if (next == PH_ROLL) break;  // rollouts are batched eight contexts per warp: back to the scheduler
       if (next != PH_EVAL) c.seg_staged = false;  // the other phases reuse the segment region of the stage
       ++st_ph[next];
       if (next == PH_INIT) next = phase_init(c);
       else if (next == PH_BACK) next = phase_back(c);
       else if (next == PH_LIN) next = phase_lin(c);
-      else if (next == PH_ROLL) next = phase_roll(c);
       else next = phase_eval(c);
       __syncwarp();
     } while (next < PH_DONE && next == *(const volatile int*)&s_type);
