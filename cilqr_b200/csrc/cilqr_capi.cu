@@ -25,6 +25,7 @@ using cilqr::CtxLayout;
 namespace {
 
 constexpr int kSlots = 2;           // double buffering of the host path
+constexpr int kStatsWords = 8 + 2 + 256;  // scheduler counters, start time, completion histogram (2 ms buckets)
 constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granularity) on the host path
 
 struct Slot {
@@ -238,6 +239,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.cl = L.cl;
   a.Kc = L.Kc;
   a.ctx_per_cta = L.ctx;
+  a.hot_iter = 16;
+  if (const char* e = getenv("CILQR_B200_HOT")) a.hot_iter = atoi(e);  // development knob
   a.start = in->start;
   a.coarse = in->coarse;
   a.corridor = in->corridor;
@@ -259,7 +262,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.ticket = s->ticket;
   a.ready = ready;
   a.stats = s->stats;
-  CK(cudaMemsetAsync(s->stats, 0, 8 * sizeof(unsigned long long), stream));
+  CK(cudaMemsetAsync(s->stats, 0, kStatsWords * sizeof(unsigned long long), stream));
+  CK(cudaMemsetAsync(s->stats + 8, 0xff, sizeof(unsigned long long), stream));  // start time: atomicMin
   a.debug = 0;
   if (dbg) {
     a.debug = 1;
@@ -387,7 +391,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
     Slot* s = &h->slots[i];
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaMalloc(&s->ticket, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
-    if (cudaMalloc(&s->stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->stats, kStatsWords * sizeof(unsigned long long)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreateWithFlags(&s->ev_reset, cudaEventDisableTiming) != cudaSuccess) return bail(CILQR_E_CUDA);
@@ -602,6 +606,15 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   CK(d2h(out->hist_len, dout.hist_len, b_hl));
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(s->stream));
+  return CILQR_OK;
+}
+
+int cilqr_debug_completion_histogram(cilqr_handle* h, uint64_t out[256]) {
+  if (!h || !out || !h->timed) return CILQR_E_INVALID;
+  Slot* s = &h->slots[h->last_slot];
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(s->ev1));
+  CK(cudaMemcpy(out, s->stats + 10, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return CILQR_OK;
 }
 

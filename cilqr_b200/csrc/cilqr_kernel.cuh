@@ -154,6 +154,7 @@ struct KernelArgs {
   CtxLayout cl;
   int B, N, M_max, S_left, S_right, Kc;  // Kc: knot pitch of the plane / trajectory arrays
   int ctx_per_cta;
+  int hot_iter;  // a scenario that has run this many iterations keeps its warp through all phases until it exits
   const double* start;
   const double* coarse;
   const double* corridor;
@@ -174,7 +175,7 @@ struct KernelArgs {
   double* ws;            // [gridDim.x][ctx_per_cta][cl.stride]
   unsigned int* ticket;  // scenario counter
   const unsigned int* ready;  // host path: scenarios below *ready have arrived on the device (NULL: all)
-  unsigned long long* stats;  // optional [8]: scheduler passes, idle polls, failed claims, phases run by type (4), type switches
+  unsigned long long* stats;  // optional [8 + 2 + 256]: completion-time histogram (2 ms buckets) after the counters; [8]: scheduler passes, idle polls, failed claims, phases run by type (4), type switches
   DebugPtrs dbg;
   int debug;             // 1: stop after the first line-search evaluation and dump stages
 };
@@ -1127,6 +1128,13 @@ __device__ __noinline__ void finish_scenario(const Ctx& c) {
   const size_t b = h->b;
   const double* Xs = c.slot(h->cur);
   copy_traj(c, Xs, a.states + b * K * 6, a.controls + b * N * 2);
+  if (lane == 0 && a.stats) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const unsigned long long t0 = *(volatile unsigned long long*)(a.stats + 8);
+    unsigned long long bk = (now - t0) / 2000000ull;
+    atomicAdd(a.stats + 10 + (bk < 255 ? bk : 255), 1ull);
+  }
   if (lane == 0) {
     double* st = a.status + b * 8;
     st[0] = h->status;
@@ -1728,6 +1736,11 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     s_iter[i] = 0;
   }
   if (threadIdx.x == 0) s_type = PH_INIT;
+  if (threadIdx.x == 0 && a.stats) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMin(a.stats + 8, now);
+  }
   __syncthreads();
   // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
   // typical duration of the phases relative to one another: INIT 5, BACK 2, ROLL 5, EVAL 3, LIN 3
@@ -1762,6 +1775,58 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       continue;
     }
     naps = 0;
+    // ---- hot contexts first: a scenario far beyond the mean iteration count (the batch has a few with 10x)
+    // would otherwise advance one phase per epoch and finish long after everything else; it is taken
+    // whatever it waits for and keeps its warp, phase after phase, until it exits
+    {
+      int hk = -1;
+#pragma unroll
+      for (int w = 0; w < kCtxWords; ++w) {
+        const int idx = lane + 32 * w;
+        if (sl[w] < PH_DONE && s_iter[idx] >= a.hot_iter) {
+          const int k1 = (s_iter[idx] << 8) | idx;
+          hk = k1 > hk ? k1 : hk;
+        }
+      }
+      hk = __reduce_max_sync(kFull, hk);
+      if (hk >= 0) {
+        const int mine = hk & 255;
+        int want_state = 0;
+#pragma unroll
+        for (int w = 0; w < kCtxWords; ++w) {
+          const int v = __shfl_sync(kFull, sl[w], mine & 31);
+          if ((mine >> 5) == w) want_state = v;
+        }
+        int ok = 0;
+        if (lane == 0) ok = atomicCAS(&s_state[mine], want_state, ST_BUSY) == want_state;
+        ok = __shfl_sync(kFull, ok, 0);
+        if (ok) {
+          __threadfence();  // acquire
+          Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
+          int next = want_state;
+          do {
+            c.seg_staged = c.seg_staged && next == PH_EVAL;
+            ++st_ph[next];
+            if (next == PH_BACK) next = phase_back(c);
+            else if (next == PH_LIN) next = phase_lin(c);
+            else if (next == PH_ROLL) {
+              roll_multi(a, smem, cta_ws, lane < 4 ? mine : -1, lane);
+              __threadfence_block();
+              next = PH_EVAL;
+            } else next = phase_eval(c);
+            __syncwarp();
+          } while (next != PH_INIT && next < PH_DONE);
+          __threadfence();  // release
+          if (lane == 0) {
+            s_iter[mine] = 0;
+            *(volatile int*)&s_state[mine] = next;
+          }
+          __syncwarp();
+          naps = 0;
+          continue;
+        }
+      }
+    }
     int type = *(const volatile int*)&s_type;
     if (cnt[type] == 0) {
       int best = 0, best_score = -1;

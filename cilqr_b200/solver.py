@@ -62,7 +62,8 @@ class DebugOut(C.Structure):
 EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_destroy",
            "cilqr_plan_batch", "cilqr_plan_batch_device", "cilqr_synchronize",
            "cilqr_kernel_launches", "cilqr_last_kernel_ms", "cilqr_occupancy", "cilqr_strerror",
-           "cilqr_last_cuda_error", "cilqr_debug_first_iteration", "cilqr_debug_stats"]
+           "cilqr_last_cuda_error", "cilqr_debug_first_iteration", "cilqr_debug_stats",
+           "cilqr_debug_completion_histogram"]
 
 _lib = None
 
@@ -101,6 +102,7 @@ def load_library(build_if_missing: bool = True):
     L.cilqr_last_cuda_error.restype = C.c_char_p
     L.cilqr_debug_first_iteration.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(DebugOut)]
     L.cilqr_debug_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.cilqr_debug_completion_histogram.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -223,6 +225,12 @@ class Solver:
         self._check(self._L.cilqr_debug_stats(self._h, a))
         k = ["passes", "idle_polls", "failed_claims", "init", "back", "roll", "eval", "type_switches"]
         return dict(zip(k, [int(x) for x in a]))
+
+    def completion_histogram(self):
+        """Scenarios completed per 2 ms bucket since the start of the last launch."""
+        a = (C.c_uint64 * 256)()
+        self._check(self._L.cilqr_debug_completion_histogram(self._h, a))
+        return [int(x) for x in a]
 
     def occupancy(self, N: int, S_left: int, S_right: int):
         w, s = C.c_int(), C.c_int()

@@ -140,6 +140,8 @@ int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* 
 /* Scheduler counters of the last solve launch (development aid): scheduler passes, idle polls, failed
  * context claims, phases run {INIT, BACK, ROLL, EVAL}, phase-type switches -- summed over all warps. */
 int cilqr_debug_stats(cilqr_handle* h, uint64_t out[8]);
+/* Scenarios completed per 2 ms bucket since the start of the last solve launch (development aid). */
+int cilqr_debug_completion_histogram(cilqr_handle* h, uint64_t out[256]);
 const char* cilqr_strerror(int code);
 const char* cilqr_last_cuda_error(const cilqr_handle* h);
 int cilqr_abi_version(void);

@@ -43,6 +43,9 @@ def child(a):
     w, smem = solver.occupancy(N, batch.S, batch.S)
     try:
         print("stats", solver.debug_stats(), flush=True)
+        hh = solver.completion_histogram()
+        last = max(i for i, v in enumerate(hh) if v) + 1
+        print("stats completions per 2 ms:", hh[:last], flush=True)
     except Exception as e:  # older variant libraries
         print("stats unavailable", e, flush=True)
     conv = int((ss[:, 0] <= 2).sum().item())
