@@ -264,7 +264,7 @@ def main():
                "h2d_bytes_per_step": int(batch.input_bytes()) * world,
                "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) * world,
                "steps": n_e2e, "api": "cilqr_plan_batch (C ABI, host pointers): one solve launch fed by chunked H2D copies through a "
-                      "device watermark, then one D2H pass"}
+                      "device watermark; results written by the kernel straight into the pinned host buffers"}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

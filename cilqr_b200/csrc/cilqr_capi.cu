@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/cilqr_b200.h"
 
@@ -58,6 +59,7 @@ struct cilqr_handle {
   DevParams dev;
   int N_max = 0, M_max = 0, S_max = 0, B_max = 0;
   int chunk = kDefaultChunk;
+  bool no_zero_copy = false;  // CILQR_NO_ZERO_COPY=1: always stage outputs on the device (development knob)
   Slot slots[kSlots];
   int64_t launches = 0;
   int last_slot = 0;
@@ -374,6 +376,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
   h->B_max = B_max;
   const char* env_chunk = getenv("CILQR_CHUNK");
   if (env_chunk && atoi(env_chunk) > 0) h->chunk = atoi(env_chunk);
+  if (const char* e = getenv("CILQR_NO_ZERO_COPY")) h->no_zero_copy = atoi(e) != 0;
   auto bail = [&](int rc) {
     cilqr_destroy(h);
     return rc;
@@ -476,8 +479,17 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   if (in->B == 0) return CILQR_OK;
   CK(cudaSetDevice(h->device));
   const size_t K = in->N + 1, N = in->N, M = in->M_max, B = in->B;
-  const int chunk = std::max(1, std::min(h->chunk, in->B));
-  const int n_chunks = (in->B + chunk - 1) / chunk;
+  // chunk schedule: small first chunks (the kernel starts after the first one), doubling up to h->chunk
+  std::vector<size_t> chunk_end;
+  {
+    size_t done = 0, c = std::min<size_t>(512, (size_t)h->chunk);
+    while (done < (size_t)in->B) {
+      done = std::min<size_t>(done + c, (size_t)in->B);
+      chunk_end.push_back(done);
+      c = std::min<size_t>(c * 2, (size_t)h->chunk);
+    }
+  }
+  const int n_chunks = (int)chunk_end.size();
   const int H = out->hist_cap;
   // per-scenario byte counts
   const size_t b_start = 4 * 8, b_coarse = K * 6 * 8, b_corr = K * M * 3 * 8, b_cnt = K * 4;
@@ -538,9 +550,32 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   din.corridor_cnt = (const int32_t*)d_cnt;
   din.lane_left = (const double*)d_ll;
   din.lane_right = (const double*)d_lr;
+  // Outputs: a caller buffer in pinned (page-locked, device-mapped) host memory is written by the kernel
+  // directly as scenarios finish -- the results cross PCIe during the solve and need no D2H pass; any other
+  // buffer gets a device staging area and one copy after the kernel.
   char* q = s->out_buf;
-  auto carve = [&](bool want, size_t per) -> char* {
-    if (!want) return nullptr;
+  auto zero_copy = [&](void* host) -> void* {
+    if (!host || h->no_zero_copy) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+  };
+  bool staged[10];
+  int n_out = 0;
+  auto carve = [&](void* host, size_t per) -> char* {
+    staged[n_out] = false;
+    if (!host) {
+      ++n_out;
+      return nullptr;
+    }
+    if (void* d = zero_copy(host)) {
+      ++n_out;
+      return (char*)d;
+    }
+    staged[n_out++] = true;
     char* r = q;
     q += up(per * B);
     return r;
@@ -548,16 +583,16 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   CilqrBatchOut dout;
   memset(&dout, 0, sizeof(dout));
   dout.hist_cap = H;
-  dout.states = (double*)carve(true, b_st);
-  dout.controls = (double*)carve(true, b_ct);
-  dout.status = (double*)carve(true, b_status);
-  dout.trajectory = (double*)carve(out->trajectory != nullptr, b_traj);
-  dout.init_states = (double*)carve(out->init_states != nullptr, b_st);
-  dout.init_controls = (double*)carve(out->init_controls != nullptr, b_ct);
-  dout.cost_hist = (double*)carve(out->cost_hist != nullptr, b_ch);
-  dout.iter_states = (double*)carve(out->iter_states != nullptr, b_is);
-  dout.iter_controls = (double*)carve(out->iter_controls != nullptr, b_ic);
-  dout.hist_len = (int32_t*)carve(out->hist_len != nullptr, b_hl);
+  dout.states = (double*)carve(out->states, b_st);
+  dout.controls = (double*)carve(out->controls, b_ct);
+  dout.status = (double*)carve(out->status, b_status);
+  dout.trajectory = (double*)carve(out->trajectory, b_traj);
+  dout.init_states = (double*)carve(out->init_states, b_st);
+  dout.init_controls = (double*)carve(out->init_controls, b_ct);
+  dout.cost_hist = (double*)carve(out->cost_hist, b_ch);
+  dout.iter_states = (double*)carve(out->iter_states, b_is);
+  dout.iter_controls = (double*)carve(out->iter_controls, b_ic);
+  dout.hist_len = (int32_t*)carve(out->hist_len, b_hl);
   // watermark = 0, then the kernel (which waits for the watermark), then the copies that raise it
   CK(cudaMemsetAsync(s->ready, 0, sizeof(unsigned int), s->copy_stream));
   CK(cudaEventRecord(s->ev_reset, s->copy_stream));
@@ -567,7 +602,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   if (rc != CILQR_OK) return rc;
   cudaError_t ce = cudaSuccess;
   for (int ci = 0; ci < n_chunks && ce == cudaSuccess; ++ci) {
-    const size_t b0 = (size_t)ci * chunk, nb = std::min<size_t>(chunk, B - b0);
+    const size_t b0 = ci ? chunk_end[ci - 1] : 0, nb = chunk_end[ci] - b0;
     auto h2d = [&](char* dev, const void* src, size_t per) {
       if (ce == cudaSuccess)
         ce = cudaMemcpyAsync(dev + per * b0, (const char*)src + per * b0, per * nb, cudaMemcpyHostToDevice, s->copy_stream);
@@ -590,8 +625,10 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
     cudaStreamSynchronize(s->stream);
     return fail_cuda(h, ce, "host-to-device copy");
   }
+  int i_out = 0;
   auto d2h = [&](void* dst, const void* dev, size_t per) -> cudaError_t {
-    if (!dst) return cudaSuccess;
+    const bool need = staged[i_out++];
+    if (!dst || !need) return cudaSuccess;
     return cudaMemcpyAsync(dst, dev, per * B, cudaMemcpyDeviceToHost, s->stream);
   };
   CK(d2h(out->states, dout.states, b_st));

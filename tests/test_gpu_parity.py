@@ -169,6 +169,34 @@ def test_host_path_equals_device_path_and_is_deterministic(solver):
     np.testing.assert_allclose(tr[:, :, 0], np.broadcast_to(np.arange(batch.N + 1) * 0.1, tr[:, :, 0].shape), atol=1e-12)
 
 
+def test_host_path_pinned_outputs_are_written_in_place(solver):
+    """Outputs in pinned (device-mapped) host memory are written by the kernel directly (no D2H pass);
+    pageable outputs go through device staging.  Both must be bit-identical, with pinned inputs too, and
+    with a batch that spans several H2D chunks of the streaming host path."""
+    import torch
+    batch = scenarios.generate(9, 0, 700, N=30)
+    ref = solver.plan_batch(batch, trajectory=True, init_guess=True, hist_cap=3)
+    K, N, B = batch.N + 1, batch.N, batch.B
+    pin = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    out = dict(states=pin(B, K, 6), controls=pin(B, N, 2), status=pin(B, 8), trajectory=pin(B, K, 13),
+               init_states=pin(B, K, 6), init_controls=pin(B, N, 2), cost_hist=pin(B, 3, 5),
+               iter_states=pin(B, 3, K, 6), iter_controls=pin(B, 3, N, 2), hist_len=pin(B, 2, dt=torch.int32))
+    pb = scenarios.ScenarioBatch(batch.N, batch.M_max, batch.S, *[torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+                                 for a in (batch.start, batch.coarse, batch.corridor, batch.corridor_cnt,
+                                           batch.lane_left, batch.lane_right)])
+    import os
+    os.environ["CILQR_CHUNK"] = "128"  # read at handle creation: several chunks behind the watermark
+    try:
+        import cilqr_b200
+        s2 = cilqr_b200.Solver(device=0, N_max=N, M_max=batch.M_max, S_max=batch.S, B_max=B)
+    finally:
+        del os.environ["CILQR_CHUNK"]
+    got = s2.plan_batch(pb, trajectory=True, init_guess=True, hist_cap=3, out=out)
+    s2.close()
+    for k, v in ref.items():
+        assert np.array_equal(got[k], v), k
+
+
 def test_history_outputs(solver, oracle):
     """cost_ (ilqr_optimizer.cc:173,283,296) and iter_trajs (:170,294) histories, initial guess."""
     batch = scenarios.generate(9, 0, 16, N=40)
