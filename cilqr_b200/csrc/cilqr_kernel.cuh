@@ -51,7 +51,7 @@ constexpr int kRecStride = 40;    // doubles per knot of the linearisation recor
 constexpr int kBackChunk = 4;     // knots per cp.async stage of the Riccati ring
 constexpr int kRingDoubles = 2 * (8 * kRollChunk + kGainStride * kRollChunk);
 #ifndef CILQR_GROUP
-#define CILQR_GROUP 4
+#define CILQR_GROUP 8
 #endif
 constexpr int kGroup = CILQR_GROUP;  // lane segments per bounding-circle group of the pruned nearest search
 constexpr int kScratch = 192;     // doubles of per-warp Riccati scratch
@@ -510,6 +510,12 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   int Mw = __reduce_max_sync(kFull, M);
   chunk_stage(0, Mw, 0);
   int stage = 0;
+  // x, y of this lane's knot in the NEXT chunk travel from the context while the current chunk is processed
+  auto item_knot = [&](int j0) {
+    const int j = j0 + c.lane;
+    return (j < items ? j : items - 1) / kDisc;
+  };
+  double px_n = Xs[item_knot(0)], py_n = Xs[a.Kc + item_knot(0)];
 #pragma unroll 1
   for (int j0 = 0; j0 < items; j0 += 32, stage ^= 1) {
     int M_next = 0, Mw_next = 0;
@@ -530,8 +536,13 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     const int M_pre = (kTileBufs == 1 && j0 + 32 < items) ? chunk_M(j0 + 32) : 0;
     const unsigned short g2 = *reinterpret_cast<const unsigned short*>(guess + jj * 2);
     const double o = P.off[d];
-    const double xd = fma(o, trig[k * 2 + 1], Xs[k]);
-    const double yd = fma(o, trig[k * 2], Xs[a.Kc + k]);
+    const double xd = fma(o, trig[k * 2 + 1], px_n);
+    const double yd = fma(o, trig[k * 2], py_n);
+    if (j0 + 32 < items) {
+      const int kn = item_knot(j0 + 32);
+      px_n = Xs[kn];
+      py_n = Xs[a.Kc + kn];
+    }
     // corridor half-planes of this knot
     BarAcc bc = {1.0, 0.0}, bc2 = {1.0, 0.0};  // two running products: two independent multiply chains
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (k - j0 / kDisc);
