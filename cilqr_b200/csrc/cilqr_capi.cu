@@ -26,7 +26,7 @@ using cilqr::CtxLayout;
 namespace {
 
 constexpr int kSlots = 2;           // double buffering of the host path
-constexpr int kStatsWords = 8 + 2 + 256;  // scheduler counters, start time, completion histogram (2 ms buckets)
+constexpr int kStatsWords = 8 + 2 + 256 + 12;  // scheduler counters, start time, completion histogram (2 ms buckets)
 constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granularity) on the host path
 
 struct Slot {
@@ -652,6 +652,13 @@ int cilqr_debug_completion_histogram(cilqr_handle* h, uint64_t out[256]) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventSynchronize(s->ev1));
   CK(cudaMemcpy(out, s->stats + 10, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (getenv("CILQR_HOT_TIMING_DUMP")) {  // development: cycles / calls per phase type of hot contexts
+    uint64_t t[12];
+    CK(cudaMemcpy(t, s->stats + 266, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < 6; ++p)
+      fprintf(stderr, "hot phase %d: %llu calls, %.1f us each\n", p, (unsigned long long)t[6 + p],
+              t[6 + p] ? (double)t[p] / t[6 + p] / 1965.0 : 0.0);
+  }
   return CILQR_OK;
 }
 

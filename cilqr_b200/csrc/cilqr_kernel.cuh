@@ -1,20 +1,22 @@
 // cilqr_kernel.cuh -- device code of the batched CILQR solver (sm_100a).
 //
-// One warp solves one trajectory phase at a time.  A persistent grid of one CTA per SM (W warps)
-// owns C > W scenario CONTEXTS that live in a global workspace (L2 / HBM): shrunk corridor planes,
-// five trajectory slots (the iterate and four line-search candidates), feedback gains, lane
-// segments, nearest-segment indices and a small header with the solver scalars.  The solve of a
-// scenario is cut into PHASES -- INIT (load, shrink, LQR gains), BACK (linearise + Riccati), ROLL
-// (speculative rollout of four step sizes), EVAL (cost of one candidate + accept/reject logic) --
-// and in every round the CTA runs ONE phase type: the type with the most waiting contexts is chosen
-// and each warp takes one of them.  Reason (measured): a B200 SM feeds
-// unaligned instruction streams at full rate only while their combined hot code fits ~32 KB; the
-// whole solver is ~75 KB of fp64 code, so free-running warps at different phases are
-// instruction-fetch bound at 1 warp per scheduler (issue 20 %, identical from 4 to 12 warps/SM),
-// while warps that run the same phase together scale (2.7x at 12 warps/SM).  With contexts in global
-// memory the shared-memory stage per warp is only what the running phase needs (lane segments +
-// heading table for EVAL, a linearisation window + Riccati scratch for BACK, a cp.async ring of
-// gains / nominal trajectory for ROLL), so 12-16 warps fit at any horizon.
+// One warp runs one trajectory PHASE at a time.  A persistent grid of one CTA per SM (16 warps) owns
+// 128 scenario CONTEXTS that live in a global workspace (L2 / HBM): shrunk corridor planes, five
+// trajectory slots (the iterate and four line-search candidates), feedback gains, linearisation
+// records, lane segments, nearest-segment indices and a small header with the solver scalars.  The
+// solve of a scenario is cut into phases -- INIT (load, shrink, LQ records of the initial guess), LIN
+// (linearise + quadratise), BACK (Riccati sweep), ROLL (speculative rollout of four step sizes, eight
+// contexts per warp), EVAL (cost of one candidate + accept/reject logic) -- and at any moment the CTA
+// runs ONE phase type: warps claim waiting contexts of that type from a shared table and only move on
+// to the type with the most waiting work when none is left (no barriers; see cilqr_solve_kernel).
+// Reason (measured): a B200 SM feeds unaligned instruction streams at full rate
+// only while their combined hot code fits ~32 KB; the whole solver is ~75 KB of fp64 code, so
+// free-running warps at different phases are instruction-fetch bound at 1 warp per scheduler (issue
+// 20 %, identical from 4 to 12 warps/SM), while warps that run the same phase together scale (2.7x at
+// 12 warps/SM).  With contexts in global memory the shared-memory stage per warp is only what the
+// running phase needs (lane segments + heading table + a plane tile for EVAL, a record window + plane
+// tile for LIN, a record ring + Riccati scratch for BACK, cp.async rings of gains / nominal trajectory
+// for ROLL), so 16 warps fit at any horizon.
 //
 // All arithmetic is IEEE double like the reference (Eigen Matrix<double,...>); no tensor cores.
 //
@@ -764,21 +766,6 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
   }
 }
 
-// scratch map (doubles) used by backward / iqr
-constexpr int SV = 0;      // 36  Vxx (or P)
-constexpr int SVX = 36;    // 6   Vx
-constexpr int SW = 42;     // 36  V*A  (or A^T P)
-constexpr int SN = 78;     // 24  Nf
-constexpr int SBV = 102;   // 12  B^T V
-constexpr int SQXX = 114;  // 36  Qxx (upper triangle filled) / C in iqr
-constexpr int SQUX = 150;  // 12
-constexpr int SQX = 162;   // 6
-constexpr int SQU = 168;   // 2
-constexpr int SQUU = 170;  // 4
-constexpr int ST = 174;    // 12  T = Quu K + Qux
-constexpr int SK = 186;    // gains of this knot are read from Kg/kg directly
-static_assert(SK <= kScratch, "scratch overflow");
-
 // ---- Backward (ilqr_optimizer.cc:334-390) in augmented, lane-uniform form --------------------
 // With z = (x, 1) and F = [A | B] (6 x 8) one knot of the recursion is
 //   M   = [Vxx ; Vx^T]                       7 x 6   value function (row 6 = gradient)
@@ -819,7 +806,7 @@ constexpr int SG = 42;    // 56  G   [7][8]
 constexpr int SQH = 98;   // 64  Qh  [8][8]
 constexpr int SQL = 162;  // 8   ql
 constexpr int SKH = 170;  // 14  Kh  [2][7]
-static_assert(SKH + 14 <= SK, "scratch overflow");
+static_assert(SKH + 14 <= kScratch, "scratch overflow");
 
 // LIN phase body: linearise + quadratise every knot of the iterate in windows of kWin knots (shared
 // memory), and flush the records to the context, where the Riccati sweep of the BACK phase streams
@@ -1818,6 +1805,10 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
           do {
             c.seg_staged = c.seg_staged && next == PH_EVAL;
             ++st_ph[next];
+#ifdef CILQR_HOT_TIMING
+            const long long tq0 = clock64();
+            const int ph_now = next;
+#endif
             if (next == PH_BACK) next = phase_back(c);
             else if (next == PH_LIN) next = phase_lin(c);
             else if (next == PH_ROLL) {
@@ -1826,6 +1817,12 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
               next = PH_EVAL;
             } else next = phase_eval(c);
             __syncwarp();
+#ifdef CILQR_HOT_TIMING
+            if (lane == 0 && a.stats) {
+              atomicAdd(a.stats + 266 + ph_now, (unsigned long long)(clock64() - tq0));
+              atomicAdd(a.stats + 272 + ph_now, 1ull);
+            }
+#endif
           } while (next != PH_INIT && next < PH_DONE);
           __threadfence();  // release
           if (lane == 0) {
