@@ -1375,7 +1375,9 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, double*
   if (rmode == 1) want = (1u << (kNAlpha - gb < kSpec ? kNAlpha - gb : kSpec)) - 1u;
   else if (rmode == 2) want = (h->deferred >> gb) & ((1u << kSpec) - 1u);
   if (want == 0) want = 1u;  // (cannot happen; keeps the shadow index valid)
-  const bool iqr = rmode == 0, allow_general = rmode != 1;
+  // a scenario far beyond the mean iteration count usually blows up its largest step sizes: take the
+  // general wrap at once instead of deferring it to a second pass (it runs alone in this warp anyway)
+  const bool iqr = rmode == 0, allow_general = rmode != 1 || h->iter >= a.hot_iter;
   const bool wanted = (want >> ai) & 1u;
   const bool owner = valid && wanted;
   const int ca = wanted ? ai : 31 - __clz(want);

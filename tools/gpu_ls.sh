@@ -1,2 +1,3 @@
 #!/bin/bash
-CILQR_HOT_TIMING_DUMP=1 timeout 300 python tools/occ_sweep.py --child --lib cilqr_b200/lib/variants/libcilqr_b200_hott.so --horizon 100 --batch 65536 --reps 0 2>&1 | grep -E "hot phase|traj_per_s" | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/occ_sweep.py --horizon 100 --batch 65536 --pads 0 --reps 2 | tail -2 | cut -c1-900
