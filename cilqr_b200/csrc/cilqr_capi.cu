@@ -162,7 +162,7 @@ CtxLayout make_ctx_layout(int N, int M_max, int S_left, int S_right) {
   C.grp = C.seg + S * cilqr::kSegStride;
   C.nidx = even(C.grp + ng * 3);
   C.nidx_bytes = (K * 10 + 7) / 8 * 8;
-  C.hdr = C.nidx + 2 * C.nidx_bytes / 8;
+  C.hdr = C.nidx + cilqr::kTrajSlots * C.nidx_bytes / 8;
   C.stride = (C.hdr + cilqr::kHdrDoubles + 15) / 16 * 16;
   return C;
 }

@@ -126,7 +126,7 @@ struct CtxLayout {
   int lin;     // [Kpad][40]        linearisation records of the iterate (LIN -> BACK)
   int seg;     // [S_left+S_right][10]
   int grp;     // [groups][3]       bounding circles cx, cy, r
-  int nidx;    // 2 byte arrays [K][5][2] of nearest-segment indices
+  int nidx;    // one byte array [K][5][2] of nearest-segment indices per trajectory slot
   int hdr;     // CtxHdr
   int nidx_bytes;
   int stride;  // doubles per context
@@ -1510,7 +1510,7 @@ __device__ __noinline__ int phase_lin(Ctx& c) {
   const unsigned b = h->b;
   c.bind(b);
   const DebugPtrs* dbg = (a.debug && h->iter == 0) ? &a.dbg : nullptr;
-  linearize_all(c, c.slot(h->cur), c.nidx(h->nflip), dbg, (int)b);
+  linearize_all(c, c.slot(h->cur), c.nidx(h->cur), dbg, (int)b);
   return PH_BACK;
 }
 
@@ -1573,140 +1573,309 @@ __device__ __noinline__ int phase_back(Ctx& c) {
 }
 
 // EVAL: TotalCost of the initial guess (:172) or of ONE line-search candidate, followed by the
-// accept / reject / lambda / convergence logic of Optimize (:253-309).
-__device__ __noinline__ int phase_eval(Ctx& c) {
+// accept / reject / lambda / convergence logic of Optimize (:253-309).  The nearest-segment index table
+// of a trajectory lives with its slot: nidx(s) belongs to the trajectory in slot s.
+//
+// eval_initial   cost of the initial guess; iter_trajs[0], cost_[0]
+// eval_prepare   which candidate is next (skips retired ones); PH_ROLL when the next group of step sizes
+//                or a deferred repeat must be rolled out first; -2 when every step size was rejected
+// eval_decide    accept (the candidate becomes the iterate, exits) or reject (advance to the next one)
+__device__ __noinline__ int eval_initial(Ctx& c) {
   const KernelArgs& a = c.a;
-  const DevParams& P = a.P;
   const int N = a.N, K = N + 1, lane = c.lane;
   CtxHdr* h = c.h;
   const unsigned b = h->b;
-  c.bind(b);
   const DebugPtrs* dbg = a.debug ? &a.dbg : nullptr;
-  const double reg_ratio = 1.6, reg_min = 1e-8, reg_max = 1e11, beta_min = 1e-4, beta_max = 10.0;
   double cost5[5];
-  const int cur = h->cur, nflip = h->nflip;
-  if (h->emode == 0) {
-    // ---- cost of the initial guess; iter_trajs[0], cost_[0]
-    stage_segments(c);
-    const double* Xs = c.slot(cur);
-    eval_cost(c, Xs, c.nidx(nflip), c.nidx(nflip), cost5);
-    __syncwarp();
-    push_cost(c, cost5);
-    push_traj(c, Xs);
-    if (lane == 0) h->cost_old = cost5[0];
-    if (dbg) {
-      copy_traj(c, Xs, dbg->X0 ? dbg->X0 + (size_t)b * K * 6 : nullptr, dbg->U0 ? dbg->U0 + (size_t)b * N * 2 : nullptr);
-      if (dbg->cost0 && lane == 0) for (int i = 0; i < 5; ++i) dbg->cost0[(size_t)b * 5 + i] = cost5[i];
-      if (dbg->nearest) {
-        const unsigned char* nn = c.nidx(nflip);
+  const int cur = h->cur;
+  stage_segments(c);
+  const double* Xs = c.slot(cur);
+  eval_cost(c, Xs, c.nidx(0), c.nidx(cur), cost5);  // nidx(0) is all zero: no previous iterate
+  __syncwarp();
+  push_cost(c, cost5);
+  push_traj(c, Xs);
+  if (lane == 0) h->cost_old = cost5[0];
+  if (dbg) {
+    copy_traj(c, Xs, dbg->X0 ? dbg->X0 + (size_t)b * K * 6 : nullptr, dbg->U0 ? dbg->U0 + (size_t)b * N * 2 : nullptr);
+    if (dbg->cost0 && lane == 0) for (int i = 0; i < 5; ++i) dbg->cost0[(size_t)b * 5 + i] = cost5[i];
+    if (dbg->nearest) {
+      const unsigned char* nn = c.nidx(cur);
 #pragma unroll 1
-        for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nn[i];
-      }
+      for (int i = lane; i < K * 10; i += 32) dbg->nearest[(size_t)b * K * 10 + i] = nn[i];
     }
-    return PH_LIN;
   }
-  // ---- line search (:246-265): candidates in the reference's order until the first accept
+  return PH_LIN;
+}
+
+__device__ __forceinline__ int eval_prepare(Ctx& c, int& ai_out) {
+  CtxHdr* h = c.h;
   int ai = h->ai;
   const int gb = h->gb;
   const unsigned retired = h->retired, deferred = h->deferred;
   while (ai < kNAlpha && ai < gb + kSpec && ((retired >> ai) & 1u)) ++ai;  // non-finite rollout: rejected
-  bool all_rejected = ai >= kNAlpha;
-  if (!all_rejected) {
-    if (ai >= gb + kSpec) {  // next group of step sizes
-      if (lane == 0) {
-        h->gb = gb + kSpec;
-        h->rmode = 1;
-      }
-      return PH_ROLL;
-    }
-    if ((deferred >> ai) & 1u) {
-      if (lane == 0) {
-        h->ai = ai;
-        h->rmode = 2;
-      }
-      return PH_ROLL;
-    }
-    stage_segments(c);
-    const double* cd = c.slot(cand_slot(cur, ai));
-    eval_cost(c, cd, c.nidx(nflip), c.nidx(nflip ^ 1), cost5);
+  ai_out = ai;
+  if (ai >= kNAlpha) return -2;
+  if (ai >= gb + kSpec) {  // next group of step sizes
     __syncwarp();
-    if (dbg && h->iter == 0 && ai == 0) {
+    if (c.lane == 0) {
+      h->gb = gb + kSpec;
+      h->rmode = 1;
+    }
+    return PH_ROLL;
+  }
+  if ((deferred >> ai) & 1u) {
+    __syncwarp();
+    if (c.lane == 0) {
+      h->ai = ai;
+      h->rmode = 2;
+    }
+    return PH_ROLL;
+  }
+  return -1;
+}
+
+// every step size rejected (:297-308)
+__device__ __noinline__ int eval_all_rejected(Ctx& c) {
+  const DevParams& P = c.a.P;
+  CtxHdr* h = c.h;
+  const double reg_ratio = 1.6, reg_min = 1e-8, reg_max = 1e11;
+  const double dl = fmax(h->dlambda * reg_ratio, reg_ratio);
+  const double lam = fmax(h->lambda * dl, reg_min);
+  const int iter = h->iter;
+  const bool overflow = lam > reg_max;
+  const bool exhausted = iter + 1 >= P.max_iter;
+  __syncwarp();
+  if (c.lane == 0) {
+    h->ahash = fnv1a(h->ahash, (unsigned)kNAlpha);
+    h->dlambda = dl;
+    h->lambda = lam;
+    if (overflow) h->status = 3;
+    else h->iter = iter + 1;
+  }
+  __syncwarp();
+  if (overflow || exhausted) {
+    finish_scenario(c);
+    return PH_INIT;
+  }
+  return PH_LIN;
+}
+
+__device__ __noinline__ int eval_decide(Ctx& c, int ai, const double cost5[5]) {
+  const KernelArgs& a = c.a;
+  const DevParams& P = a.P;
+  const int lane = c.lane;
+  CtxHdr* h = c.h;
+  const double reg_ratio = 1.6, reg_min = 1e-8, beta_min = 1e-4, beta_max = 10.0;
+  const int cur = h->cur, gb = h->gb;
+  const unsigned retired = h->retired;
+  const double* cd = c.slot(cand_slot(cur, ai));
+  const double alpha = kAlphaList[ai];
+  const double cost_old = h->cost_old;
+  const double dcost = cost_old - cost5[0];
+  const double expected = -alpha * (h->dV0 + alpha * h->dV1);
+  const double z = dcost / expected;
+  if ((z > beta_min && z < beta_max) && dcost > 0.0) {
+    // ---- accepted (:266-296): the candidate becomes the iterate
+    const double dl = fmin(h->dlambda / reg_ratio, 1.0 / reg_ratio);
+    const double lam = h->lambda;
+    int status = -1;
+    if (dcost < P.abs_tol || dcost / cost_old < P.rel_tol) status = dcost < P.abs_tol ? 0 : 1;
+    const int iter = h->iter;
+    __syncwarp();
+    if (lane == 0) {
+      h->ahash = fnv1a(h->ahash, (unsigned)ai);
+      h->cur = cand_slot(cur, ai);
+      h->dlambda = dl;
+      h->lambda = lam * dl * (lam > reg_min ? 1.0 : 0.0);
+      h->cost_old = cost5[0];
+      if (status >= 0) h->status = status;
+    }
+    push_cost(c, cost5);
+    if (status >= 0) {
+      finish_scenario(c);
+      return PH_INIT;
+    }
+    push_traj(c, cd);
+    if (iter + 1 >= P.max_iter) {  // loop exhausted (:312-319)
+      if (lane == 0) h->iter = iter + 1;
+      __syncwarp();
+      finish_scenario(c);
+      return PH_INIT;
+    }
+    if (lane == 0) h->iter = iter + 1;
+    return PH_LIN;
+  }
+  // rejected: next step size
+  ++ai;
+  while (ai < kNAlpha && ai < gb + kSpec && ((retired >> ai) & 1u)) ++ai;
+  if (ai < kNAlpha) {
+    __syncwarp();
+    if (lane == 0) h->ai = ai;
+    return PH_EVAL;  // (a group change / deferred repeat is resolved by the next eval_prepare)
+  }
+  return eval_all_rejected(c);
+}
+
+// cost of line-search candidate ai of the context (any warp may do this: the result only depends on the
+// context), nearest-segment indices -> nidx of the candidate's slot
+__device__ __forceinline__ void eval_candidate(Ctx& c, int cur, int ai, double cost5[5]) {
+  const int s = cand_slot(cur, ai);
+  stage_segments(c);
+  eval_cost(c, c.slot(s), c.nidx(cur), c.nidx(s), cost5);
+  __syncwarp();
+}
+
+__device__ __noinline__ int phase_eval(Ctx& c) {
+  const KernelArgs& a = c.a;
+  const int N = a.N, K = N + 1, lane = c.lane;
+  CtxHdr* h = c.h;
+  const unsigned b = h->b;
+  c.bind(b);
+  if (h->emode == 0) return eval_initial(c);
+  // ---- line search (:246-265): candidates in the reference's order until the first accept
+  int ai;
+  const int r = eval_prepare(c, ai);
+  if (r == -2) return eval_all_rejected(c);
+  if (r >= 0) return r;
+  double cost5[5];
+  eval_candidate(c, h->cur, ai, cost5);
+  if (a.debug) {  // stage dump mode: one backward + one forward only; the initial guess is returned
+    const DebugPtrs* dbg = &a.dbg;
+    if (h->iter == 0 && ai == 0) {
+      const double* cd = c.slot(cand_slot(h->cur, ai));
       copy_traj(c, cd, dbg->Xn ? dbg->Xn + (size_t)b * K * 6 : nullptr, dbg->Un ? dbg->Un + (size_t)b * N * 2 : nullptr);
       if (dbg->costn && lane == 0) for (int i = 0; i < 5; ++i) dbg->costn[(size_t)b * 5 + i] = cost5[i];
     }
-    if (a.debug) {  // stage dump mode: one backward + one forward only; the initial guess is returned
-      __syncwarp();
-      finish_scenario(c);
-      return PH_INIT;
+    __syncwarp();
+    finish_scenario(c);
+    return PH_INIT;
+  }
+  return eval_decide(c, ai, cost5);
+}
+
+// ---- Help requests: a warp that runs a hot context alone (see the scheduler) lets idle warps of the CTA
+// evaluate the other candidates of the current line-search group at the same time.  One request per CTA.
+constexpr int kHelpClosed = 1 << 20;
+struct HelpBoard {
+  int owner;             // context index of the requester, -1: board free
+  int next;              // next list position to claim (atomic); >= kHelpClosed: closed
+  int n;                 // list length
+  int cur;               // the iterate's slot when the request was opened (an accept changes the header)
+  int list[kSpec];       // candidate (step-size) indices in search order; position 0 is the owner's
+  volatile int done[kSpec];
+  double cost[kSpec][5];
+};
+
+// Line search of a hot context with helpers.  Returns the next phase (never PH_EVAL).
+__device__ __noinline__ int gang_eval(Ctx& c, HelpBoard* hb, int mine) {
+  const int lane = c.lane;
+  CtxHdr* h = c.h;
+  c.bind(h->b);
+  for (;;) {
+    __syncwarp();
+    int ai;
+    const int r = eval_prepare(c, ai);
+    if (r == -2) return eval_all_rejected(c);
+    if (r >= 0) return r;
+    // candidates of this group that can be evaluated now, in search order
+    const int gb = h->gb;
+    const unsigned retired = h->retired, deferred = h->deferred;
+    int list[kSpec], n = 0;
+    for (int q = ai; q < kNAlpha && q < gb + kSpec; ++q) {
+      if ((retired >> q) & 1u) continue;
+      if ((deferred >> q) & 1u) break;
+      list[n++] = q;
     }
-    const double alpha = kAlphaList[ai];
-    const double cost_old = h->cost_old;
-    const double dcost = cost_old - cost5[0];
-    const double expected = -alpha * (h->dV0 + alpha * h->dV1);
-    const double z = dcost / expected;
-    if ((z > beta_min && z < beta_max) && dcost > 0.0) {
-      // ---- accepted (:266-296): the candidate becomes the iterate
-      const double dl = fmin(h->dlambda / reg_ratio, 1.0 / reg_ratio);
-      const double lam = h->lambda;
-      int status = -1;
-      if (dcost < P.abs_tol || dcost / cost_old < P.rel_tol) status = dcost < P.abs_tol ? 0 : 1;
-      const int iter = h->iter;
-      __syncwarp();
-      if (lane == 0) {
-        h->ahash = fnv1a(h->ahash, (unsigned)ai);
-        h->cur = cand_slot(cur, ai);
-        h->nflip = nflip ^ 1;
-        h->dlambda = dl;
-        h->lambda = lam * dl * (lam > reg_min ? 1.0 : 0.0);
-        h->cost_old = cost5[0];
-        if (status >= 0) h->status = status;
-      }
-      push_cost(c, cost5);
-      if (status >= 0) {
-        finish_scenario(c);
-        return PH_INIT;
-      }
-      push_traj(c, cd);
-      if (iter + 1 >= P.max_iter) {  // loop exhausted (:312-319)
-        if (lane == 0) h->iter = iter + 1;
+    // open the board (if it is free) for positions 1..n-1
+    int have_board = 0;
+    if (n > 1) {
+      if (lane == 0) have_board = atomicCAS(&hb->owner, -1, mine) == -1;
+      have_board = __shfl_sync(kFull, have_board, 0);
+      if (have_board) {
+        if (lane == 0) {
+          hb->n = n;
+          hb->cur = h->cur;
+          for (int i = 0; i < kSpec; ++i) {
+            hb->list[i] = i < n ? list[i] : 0;
+            hb->done[i] = 0;
+          }
+          __threadfence_block();
+          atomicExch(&hb->next, 1);
+        }
         __syncwarp();
-        finish_scenario(c);
-        return PH_INIT;
       }
-      if (lane == 0) h->iter = iter + 1;
-      return PH_LIN;
     }
-    // rejected: next step size
-    ++ai;
-    while (ai < kNAlpha && ai < gb + kSpec && ((retired >> ai) & 1u)) ++ai;
-    if (ai < kNAlpha) {
-      if (lane == 0) h->ai = ai;
-      return PH_EVAL;  // (a group change / deferred repeat is resolved at the top of the next EVAL)
+    double cost5[5];
+    const int cur0 = h->cur;
+    eval_candidate(c, cur0, list[0], cost5);
+    int next = PH_EVAL;
+    for (int i = 0;; ) {
+      next = eval_decide(c, list[i], cost5);
+      if (next != PH_EVAL) break;  // accepted, or exits
+      if (++i >= n) break;         // rejected all of the list: prepare again (next group / deferred / all rejected)
+      // cost of list[i]: from a helper if one took it, else computed here
+      int mine_too = 1;
+      if (have_board) {
+        int k = 0;
+        if (lane == 0) k = atomicCAS(&hb->next, i, i + 1);  // claim position i if nobody has
+        k = __shfl_sync(kFull, k, 0);
+        mine_too = k == i;
+      }
+      if (mine_too) {
+        if (have_board && lane == 0) hb->done[i] = 1;  // (the close below only has to wait for helpers)
+        eval_candidate(c, cur0, list[i], cost5);
+      } else {
+        unsigned spins = 0;
+        while (hb->done[i] == 0 && ++spins < (1u << 24)) __nanosleep(200);
+        __threadfence_block();
+#pragma unroll
+        for (int q = 0; q < 5; ++q) cost5[q] = hb->cost[i][q];
+      }
     }
-    all_rejected = true;
+    if (have_board) {
+      // close: nobody may claim any more; wait for the helpers that already did (they read the candidate
+      // slots and write the nidx tables the next rollout / evaluation will overwrite)
+      int claimed = 0;
+      if (lane == 0) claimed = atomicExch(&hb->next, kHelpClosed);
+      claimed = __shfl_sync(kFull, claimed, 0);
+      claimed = claimed < n ? claimed : n;
+      for (int i = 1; i < claimed; ++i) {
+        unsigned spins = 0;
+        while (hb->done[i] == 0 && ++spins < (1u << 24)) __nanosleep(200);
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) atomicExch(&hb->owner, -1);
+      __syncwarp();
+    }
+    if (next != PH_EVAL) return next;
   }
-  // ---- every step size rejected (:297-308)
-  {
-    const double dl = fmax(h->dlambda * reg_ratio, reg_ratio);
-    const double lam = fmax(h->lambda * dl, reg_min);
-    const int iter = h->iter;
-    const bool overflow = lam > reg_max;
-    const bool exhausted = iter + 1 >= P.max_iter;
-    __syncwarp();
-    if (lane == 0) {
-      h->ahash = fnv1a(h->ahash, (unsigned)kNAlpha);
-      h->dlambda = dl;
-      h->lambda = lam;
-      if (overflow) h->status = 3;
-      else h->iter = iter + 1;
-    }
-    __syncwarp();
-    if (overflow || exhausted) {
-      finish_scenario(c);
-      return PH_INIT;
-    }
-    return PH_LIN;
+}
+
+// An idle warp looks at the board; returns true if it evaluated a candidate for somebody.
+__device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, double* cta_ws, HelpBoard* hb, int lane) {
+  const int owner = *(volatile int*)&hb->owner;
+  const int nx = *(volatile int*)&hb->next;
+  if (owner < 0 || nx >= *(volatile int*)&hb->n || nx >= kHelpClosed) return false;
+  int k = 0;
+  if (lane == 0) k = atomicAdd(&hb->next, 1);
+  k = __shfl_sync(kFull, k, 0);
+  if (k >= kHelpClosed || k >= *(volatile int*)&hb->n) return false;
+  __threadfence_block();
+  // the request is stable from here on: its owner waits for done[k] before it changes anything
+  const int id = *(volatile int*)&hb->owner;
+  const int ai = hb->list[k], cur = hb->cur;
+  Ctx c(a, smem, cta_ws + (size_t)id * a.cl.stride, lane);
+  c.bind(c.h->b);
+  double cost5[5];
+  eval_candidate(c, cur, ai, cost5);
+  if (lane == 0) {
+    for (int q = 0; q < 5; ++q) hb->cost[k][q] = cost5[q];
+    __threadfence();
+    hb->done[k] = 1;
   }
+  __syncwarp();
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1725,6 +1894,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   extern __shared__ __align__(16) double smem_cta[];
   __shared__ int s_state[kMaxCtx];
   __shared__ int s_iter[kMaxCtx];  // iterations run so far by the scenario in each context (claim priority)
+  __shared__ HelpBoard s_help;
   __shared__ int s_type;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1735,7 +1905,12 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     s_state[i] = i < C ? PH_INIT : PH_DONE;
     s_iter[i] = 0;
   }
-  if (threadIdx.x == 0) s_type = PH_INIT;
+  if (threadIdx.x == 0) {
+    s_type = PH_INIT;
+    s_help.owner = -1;
+    s_help.next = kHelpClosed;
+    s_help.n = 0;
+  }
   if (threadIdx.x == 0 && a.stats) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1767,7 +1942,12 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
 #pragma unroll
       for (int w = 0; w < kCtxWords; ++w) b |= sl[w] == ST_BUSY;
       if (!__any_sync(kFull, b)) break;  // every context is DONE
-      // the remaining contexts are all being run by other warps: back off (up to ~4 us between polls)
+      // the remaining contexts are all being run by other warps: help one of them if it asks ...
+      if (help_once(a, smem, cta_ws, &s_help, lane)) {
+        naps = 0;
+        continue;
+      }
+      // ... else back off (up to ~4 us between polls)
       ++naps;
       ++st_poll;
       __nanosleep(naps < 16 ? 250 : 4000);
@@ -1817,7 +1997,11 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
               roll_multi(a, smem, cta_ws, lane < 4 ? mine : -1, lane);
               __threadfence_block();
               next = PH_EVAL;
-            } else next = phase_eval(c);
+            } else if (c.h->emode == 1 && !a.debug) {
+              next = gang_eval(c, &s_help, mine);
+            } else {
+              next = phase_eval(c);
+            }
             __syncwarp();
 #ifdef CILQR_HOT_TIMING
             if (lane == 0 && a.stats) {
