@@ -242,6 +242,8 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.Kc = L.Kc;
   a.ctx_per_cta = L.ctx;
   a.hot_iter = 16;
+  a.hot_live = L.warps;
+  if (const char* e = getenv("CILQR_B200_HOT_LIVE")) a.hot_live = atoi(e);  // development knob
   if (const char* e = getenv("CILQR_B200_HOT")) a.hot_iter = atoi(e);  // development knob
   a.start = in->start;
   a.coarse = in->coarse;

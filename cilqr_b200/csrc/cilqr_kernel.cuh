@@ -156,6 +156,7 @@ struct KernelArgs {
   CtxLayout cl;
   int B, N, M_max, S_left, S_right, Kc;  // Kc: knot pitch of the plane / trajectory arrays
   int ctx_per_cta;
+  int hot_live;  // when at most this many contexts of the CTA are alive, every context is treated as hot
   int hot_iter;  // a scenario that has run this many iterations keeps its warp through all phases until it exits
   const double* start;
   const double* coarse;
@@ -812,41 +813,44 @@ static_assert(SKH + 14 <= kScratch, "scratch overflow");
 // memory), and flush the records to the context, where the Riccati sweep of the BACK phase streams
 // them from.  (One phase for both was 57 KB of code -- more than the ~32 KB an SM's instruction cache
 // feeds to unaligned warps -- and spilled at 128 registers.)
-__device__ __noinline__ void linearize_all(const Ctx& c, const double* Xs, const unsigned char* nidx,
-                                           const DebugPtrs* dbg, int b) {
+__device__ __noinline__ void linearize_window(const Ctx& c, int k0, const double* Xs, const unsigned char* nidx,
+                                              const DebugPtrs* dbg, int b) {
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
   double* lin = c.sm + a.sm.lin;
   double* R = c.linrec();
-  for (int k0 = 0; k0 < K; k0 += kWin) {
-    const int k = k0 + lane;
-    const int nk = K - k0 < kWin ? K - k0 : kWin;
-    const bool lin_lane = lane < kWin && k < K;
-    __syncwarp();
-    if (lin_lane) linearize_knot(c, k, Xs, lin + lane * kLinStride);
-    __syncwarp();
-    linearize_discs(c, k0, nk, Xs, nidx, lin);
-    if (dbg) {
-      if (lin_lane) {
-        const double* rec = lin + lane * kLinStride;
-        if (k < N) {
-          if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
-          if (dbg->Ju) for (int i = 0; i < 2; ++i) dbg->Ju[((size_t)b * N + k) * 2 + i] = rec[LJU + i];
-          if (dbg->Hu) for (int i = 0; i < 2; ++i) dbg->Hu[((size_t)b * N + k) * 2 + i] = rec[LHU + i];
-        }
-        if (dbg->Jx) for (int i = 0; i < 6; ++i) dbg->Jx[((size_t)b * K + k) * 6 + i] = rec[LJX + i];
-        if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
+  const int k = k0 + lane;
+  const int nk = K - k0 < kWin ? K - k0 : kWin;
+  const bool lin_lane = lane < kWin && k < K;
+  __syncwarp();
+  if (lin_lane) linearize_knot(c, k, Xs, lin + lane * kLinStride);
+  __syncwarp();
+  linearize_discs(c, k0, nk, Xs, nidx, lin);
+  if (dbg) {
+    if (lin_lane) {
+      const double* rec = lin + lane * kLinStride;
+      if (k < N) {
+        if (dbg->A11) for (int i = 0; i < 12; ++i) dbg->A11[((size_t)b * N + k) * 12 + i] = rec[LA + i];
+        if (dbg->Ju) for (int i = 0; i < 2; ++i) dbg->Ju[((size_t)b * N + k) * 2 + i] = rec[LJU + i];
+        if (dbg->Hu) for (int i = 0; i < 2; ++i) dbg->Hu[((size_t)b * N + k) * 2 + i] = rec[LHU + i];
       }
-    }
-    // window -> context, coalesced (record stride 37 in shared memory, 40 in the context)
-#pragma unroll 1
-    for (int idx = lane; idx < nk * kRecStride; idx += 32) {
-      const int kk = idx / kRecStride, i = idx - kk * kRecStride;
-      R[(size_t)(k0 + kk) * kRecStride + i] = i < kLinStride ? lin[kk * kLinStride + i] : 0.0;
+      if (dbg->Jx) for (int i = 0; i < 6; ++i) dbg->Jx[((size_t)b * K + k) * 6 + i] = rec[LJX + i];
+      if (dbg->Hx) for (int i = 0; i < 9; ++i) dbg->Hx[((size_t)b * K + k) * 9 + i] = rec[LHX + i];
     }
   }
+  // window -> context, coalesced (record stride 37 in shared memory, 40 in the context)
+#pragma unroll 1
+  for (int idx = lane; idx < nk * kRecStride; idx += 32) {
+    const int kk = idx / kRecStride, i = idx - kk * kRecStride;
+    R[(size_t)(k0 + kk) * kRecStride + i] = i < kLinStride ? lin[kk * kLinStride + i] : 0.0;
+  }
   __syncwarp();
+}
+
+__device__ __forceinline__ void linearize_all(const Ctx& c, const double* Xs, const unsigned char* nidx,
+                                              const DebugPtrs* dbg, int b) {
+  for (int k0 = 0; k0 <= c.a.N; k0 += kWin) linearize_window(c, k0, Xs, nidx, dbg, b);
 }
 
 __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double dV[2]) {
@@ -1759,7 +1763,9 @@ constexpr int kHelpClosed = 1 << 20;
 struct HelpBoard {
   int owner;             // context index of the requester, -1: board free
   int next;              // next list position to claim (atomic); >= kHelpClosed: closed
-  int n;                 // list length
+  int n;                 // list length (kind 0) / number of linearisation windows (kind 1)
+  int kind;              // 0: line-search candidates, 1: windows of the linearisation
+  int done_cnt;          // kind 1: windows finished (atomic)
   int cur;               // the iterate's slot when the request was opened (an accept changes the header)
   int list[kSpec];       // candidate (step-size) indices in search order; position 0 is the owner's
   volatile int done[kSpec];
@@ -1794,6 +1800,7 @@ __device__ __noinline__ int gang_eval(Ctx& c, HelpBoard* hb, int mine) {
       if (have_board) {
         if (lane == 0) {
           hb->n = n;
+          hb->kind = 0;
           hb->cur = h->cur;
           for (int i = 0; i < kSpec; ++i) {
             hb->list[i] = i < n ? list[i] : 0;
@@ -1852,6 +1859,50 @@ __device__ __noinline__ int gang_eval(Ctx& c, HelpBoard* hb, int mine) {
   }
 }
 
+// Linearisation of a hot context with helpers: the windows of the horizon are independent.
+__device__ __noinline__ int gang_lin(Ctx& c, HelpBoard* hb, int mine) {
+  const KernelArgs& a = c.a;
+  const int lane = c.lane;
+  CtxHdr* h = c.h;
+  c.bind(h->b);
+  int have_board = 0;
+  if (lane == 0) have_board = atomicCAS(&hb->owner, -1, mine) == -1;
+  have_board = __shfl_sync(kFull, have_board, 0);
+  if (!have_board || a.debug) {
+    if (have_board && lane == 0) atomicExch(&hb->owner, -1);
+    return phase_lin(c);
+  }
+  const int cur = h->cur, n = (a.N + kWin) / kWin;
+  if (lane == 0) {
+    hb->n = n;
+    hb->kind = 1;
+    hb->cur = cur;
+    hb->done_cnt = 0;
+    __threadfence_block();
+    atomicExch(&hb->next, 0);
+  }
+  __syncwarp();
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(&hb->next, 1);
+    k = __shfl_sync(kFull, k, 0);
+    if (k >= n) break;
+    linearize_window(c, k * kWin, c.slot(cur), c.nidx(cur), nullptr, 0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&hb->done_cnt, 1);
+  }
+  // every window has been claimed; wait for the helpers' ones
+  if (lane == 0) atomicExch(&hb->next, kHelpClosed);
+  unsigned spins = 0;
+  while (*(volatile int*)&hb->done_cnt < n && ++spins < (1u << 24)) __nanosleep(200);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(&hb->owner, -1);
+  __syncwarp();
+  return PH_BACK;
+}
+
 // An idle warp looks at the board; returns true if it evaluated a candidate for somebody.
 __device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, double* cta_ws, HelpBoard* hb, int lane) {
   const int owner = *(volatile int*)&hb->owner;
@@ -1864,9 +1915,17 @@ __device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, double
   __threadfence_block();
   // the request is stable from here on: its owner waits for done[k] before it changes anything
   const int id = *(volatile int*)&hb->owner;
-  const int ai = hb->list[k], cur = hb->cur;
+  const int cur = hb->cur;
   Ctx c(a, smem, cta_ws + (size_t)id * a.cl.stride, lane);
   c.bind(c.h->b);
+  if (*(volatile int*)&hb->kind == 1) {
+    linearize_window(c, k * kWin, c.slot(cur), c.nidx(cur), nullptr, 0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&hb->done_cnt, 1);
+    return true;
+  }
+  const int ai = hb->list[k];
   double cost5[5];
   eval_candidate(c, cur, ai, cost5);
   if (lane == 0) {
@@ -1959,11 +2018,18 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     // would otherwise advance one phase per epoch and finish long after everything else; it is taken
     // whatever it waits for and keeps its warp, phase after phase, until it exits
     {
+      // (once no more contexts are alive than the CTA has warps -- the end of the batch -- every context is
+      // treated as hot: each gets its own warp for good, and the idle warps help)
+      int nbusy = 0;
+#pragma unroll
+      for (int w = 0; w < kCtxWords; ++w) nbusy += __popc(__ballot_sync(kFull, sl[w] == ST_BUSY));
+      const int live = nbusy + cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+      const int hot_thr = live <= a.hot_live ? 0 : a.hot_iter;
       int hk = -1;
 #pragma unroll
       for (int w = 0; w < kCtxWords; ++w) {
         const int idx = lane + 32 * w;
-        if (sl[w] < PH_DONE && s_iter[idx] >= a.hot_iter) {
+        if (sl[w] < PH_DONE && sl[w] != PH_INIT && s_iter[idx] >= hot_thr) {
           const int k1 = (s_iter[idx] << 8) | idx;
           hk = k1 > hk ? k1 : hk;
         }
@@ -1992,7 +2058,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
             const int ph_now = next;
 #endif
             if (next == PH_BACK) next = phase_back(c);
-            else if (next == PH_LIN) next = phase_lin(c);
+            else if (next == PH_LIN) next = gang_lin(c, &s_help, mine);
             else if (next == PH_ROLL) {
               roll_multi(a, smem, cta_ws, lane < 4 ? mine : -1, lane);
               __threadfence_block();
