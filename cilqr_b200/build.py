@@ -10,7 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200.so")
 SOURCES = ["cilqr_capi.cu"]
-DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", os.path.join("..", "..", "include", "cilqr_b200.h")]
+DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "corridor_kernel.cuh", os.path.join("..", "..", "include", "cilqr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
 

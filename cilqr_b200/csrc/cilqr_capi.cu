@@ -5,6 +5,7 @@
 // no CPU path in this library: without a CUDA device every entry point fails with
 // CILQR_E_NO_DEVICE / CILQR_E_CUDA.
 #include "cilqr_kernel.cuh"
+#include "corridor_kernel.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -65,6 +66,12 @@ struct cilqr_handle {
   int last_slot = 0;
   bool timed = false;
   std::string cuda_err;
+  // corridor builder: staging for the host path and launch timing
+  char* corr_buf = nullptr;
+  size_t corr_bytes = 0;
+  cudaEvent_t corr_ev0 = nullptr, corr_ev1 = nullptr;
+  bool corr_timed = false;
+  int64_t corr_launches = 0;
 };
 
 namespace {
@@ -428,6 +435,9 @@ void cilqr_destroy(cilqr_handle* h) {
     if (s->ready_host) cudaFreeHost(s->ready_host);
     if (s->stream) cudaStreamDestroy(s->stream);
   }
+  if (h->corr_buf) cudaFree(h->corr_buf);
+  if (h->corr_ev0) cudaEventDestroy(h->corr_ev0);
+  if (h->corr_ev1) cudaEventDestroy(h->corr_ev1);
   delete h;
 }
 
@@ -698,4 +708,194 @@ int cilqr_occupancy(const cilqr_handle* h, int N, int S_left, int S_right, int* 
   return CILQR_OK;
 }
 
+// ---- corridor builder -------------------------------------------------------------------------------
+void cilqr_corridor_default_config(CilqrCorridorConfig* c) {
+  if (!c) return;
+  c->max_diff_x = 25.0;  // planner_config.h:77-85
+  c->max_diff_y = 25.0;
+  c->radius = 150.0;
+  c->max_axis_x = 10.0;
+  c->max_axis_y = 10.0;
+  c->lane_segment_length = 5.0;
+  c->point_cap = 0;
+}
+
+static int corridor_launch(cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                           const CilqrCorridorOut* out, cudaStream_t st) {
+  corridor::Args a;
+  a.B = in->B;
+  a.K = in->K;
+  a.P_max = in->P_max;
+  a.M_max = in->M_max;
+  a.cap = (cfg->point_cap > 0 ? cfg->point_cap : 64) + 1;  // + the knot itself (flipData's zero slot)
+  a.max_diff_x = cfg->max_diff_x;
+  a.max_diff_y = cfg->max_diff_y;
+  a.radius = cfg->radius;
+  a.max_axis_x = cfg->max_axis_x;
+  a.max_axis_y = cfg->max_axis_y;
+  a.traj = in->traj;
+  a.obs_points = in->obs_points;
+  a.obs_cnt = in->obs_cnt;
+  a.corridor = out->corridor;
+  a.corridor_cnt = out->corridor_cnt;
+  a.polygon = out->polygon;
+  a.code = out->code;
+  // threads per CTA: as many warps as the per-thread shared-memory slice allows, 1 CTA per SM above
+  // 113 KB, 2 below
+  const size_t per_thread = corridor::smem_bytes_per_thread(a.cap);
+  int threads = (int)((size_t)(h->smem_optin - 1024) / per_thread) / 32 * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 32) return CILQR_E_SMEM;
+  const size_t smem = per_thread * threads;
+  static_assert(sizeof(float) == 4, "");
+  CK(cudaFuncSetAttribute(corridor::corridor_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)in->B * in->K;
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corridor::corridor_build_kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (items + threads - 1) / threads;
+  const long long resident = (long long)h->num_sms * per_sm;
+  if (blocks > resident) blocks = resident;  // persistent: grid-stride over the knots
+  if (blocks < 1) blocks = 1;
+  if (!h->corr_ev0) {
+    CK(cudaEventCreate(&h->corr_ev0));
+    CK(cudaEventCreate(&h->corr_ev1));
+  }
+  CK(cudaEventRecord(h->corr_ev0, st));
+  corridor::corridor_build_kernel<<<(unsigned)blocks, threads, smem, st>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->corr_ev1, st));
+  h->corr_timed = true;
+  h->corr_launches++;
+  return CILQR_OK;
+}
+
+static int corridor_validate(const cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                             const CilqrCorridorOut* out) {
+  if (!h || !cfg || !in || !out) return CILQR_E_INVALID;
+  if (in->B < 0 || in->K < 1 || in->P_max < 0 || in->M_max < 1) return CILQR_E_INVALID;
+  if (in->P_max + 8 > 250 || cfg->point_cap < 0 || cfg->point_cap > 250) return CILQR_E_CAPACITY;
+  if (in->B > 0 && (!in->traj || !in->obs_cnt || (in->P_max > 0 && !in->obs_points) || !out->corridor ||
+                    !out->corridor_cnt || !out->code))
+    return CILQR_E_INVALID;
+  return CILQR_OK;
+}
+
+int cilqr_corridor_batch_device(cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                                const CilqrCorridorOut* out, void* cuda_stream) {
+  int rc = corridor_validate(h, cfg, in, out);
+  if (rc != CILQR_OK) return rc;
+  if (in->B == 0) return CILQR_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slots[0].stream;
+  return corridor_launch(h, cfg, in, out, st);
+}
+
+static int corr_ensure(cilqr_handle* h, size_t bytes) {
+  if (h->corr_bytes >= bytes) return CILQR_OK;
+  if (h->corr_buf) cudaFree(h->corr_buf);
+  h->corr_buf = nullptr;
+  h->corr_bytes = 0;
+  CK(cudaMalloc(&h->corr_buf, bytes));
+  h->corr_bytes = bytes;
+  return CILQR_OK;
+}
+
+int cilqr_corridor_batch(cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                         const CilqrCorridorOut* out) {
+  int rc = corridor_validate(h, cfg, in, out);
+  if (rc != CILQR_OK) return rc;
+  if (in->B == 0) return CILQR_OK;
+  CK(cudaSetDevice(h->device));
+  const size_t items = (size_t)in->B * in->K;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_traj = up(items * 3 * 8), b_pts = up(items * in->P_max * 2 * 8), b_cnt = up(items * 4);
+  const size_t b_cor = up(items * in->M_max * 3 * 8), b_ccnt = up(items * 4);
+  const size_t b_poly = out->polygon ? up(items * in->M_max * 2 * 8) : 0, b_code = up(items * 4);
+  rc = corr_ensure(h, b_traj + b_pts + b_cnt + b_cor + b_ccnt + b_poly + b_code);
+  if (rc != CILQR_OK) return rc;
+  char* p = h->corr_buf;
+  CilqrCorridorIn din = *in;
+  CilqrCorridorOut dout;
+  din.traj = (const double*)p; p += b_traj;
+  din.obs_points = (const double*)p; p += b_pts;
+  din.obs_cnt = (const int32_t*)p; p += b_cnt;
+  dout.corridor = (double*)p; p += b_cor;
+  dout.corridor_cnt = (int32_t*)p; p += b_ccnt;
+  dout.polygon = out->polygon ? (double*)p : nullptr; p += b_poly;
+  dout.code = (int32_t*)p;
+  cudaStream_t st = h->slots[0].stream;
+  CK(cudaMemcpyAsync((void*)din.traj, in->traj, items * 3 * 8, cudaMemcpyHostToDevice, st));
+  if (in->P_max > 0)
+    CK(cudaMemcpyAsync((void*)din.obs_points, in->obs_points, items * in->P_max * 2 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((void*)din.obs_cnt, in->obs_cnt, items * 4, cudaMemcpyHostToDevice, st));
+  rc = corridor_launch(h, cfg, &din, &dout, st);
+  if (rc != CILQR_OK) return rc;
+  CK(cudaMemcpyAsync(out->corridor, dout.corridor, items * in->M_max * 3 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out->corridor_cnt, dout.corridor_cnt, items * 4, cudaMemcpyDeviceToHost, st));
+  if (out->polygon)
+    CK(cudaMemcpyAsync(out->polygon, dout.polygon, items * in->M_max * 2 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out->code, dout.code, items * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CILQR_OK;
+}
+
+int cilqr_lane_constraints_device(cilqr_handle* h, const CilqrCorridorConfig* cfg, int B, int n, int S_max,
+                                  int is_left, const double* boundary, double* out, int32_t* count,
+                                  void* cuda_stream) {
+  if (!h || !cfg || B < 0 || n < 1 || S_max < 1) return CILQR_E_INVALID;
+  if (B == 0) return CILQR_OK;
+  if (!boundary || !out || !count) return CILQR_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slots[0].stream;
+  corridor::LaneArgs a;
+  a.B = B;
+  a.n = n;
+  a.S_max = S_max;
+  a.is_left = is_left ? 1 : 0;
+  a.seg_len = cfg->lane_segment_length;
+  a.boundary = boundary;
+  a.out = out;
+  a.count = count;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)(((long long)B * 32 + threads - 1) / threads);
+  corridor::lane_constraints_kernel<<<blocks, threads, 0, st>>>(a);
+  CK(cudaGetLastError());
+  return CILQR_OK;
+}
+
+int cilqr_lane_constraints(cilqr_handle* h, const CilqrCorridorConfig* cfg, int B, int n, int S_max, int is_left,
+                           const double* boundary, double* out, int32_t* count) {
+  if (!h || !cfg || B < 0 || n < 1 || S_max < 1) return CILQR_E_INVALID;
+  if (B == 0) return CILQR_OK;
+  if (!boundary || !out || !count) return CILQR_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_in = up((size_t)B * n * 2 * 8), b_out = up((size_t)B * S_max * 7 * 8), b_cnt = up((size_t)B * 4);
+  int rc = corr_ensure(h, b_in + b_out + b_cnt);
+  if (rc != CILQR_OK) return rc;
+  char* p = h->corr_buf;
+  double* d_in = (double*)p;
+  double* d_out = (double*)(p + b_in);
+  int32_t* d_cnt = (int32_t*)(p + b_in + b_out);
+  cudaStream_t st = h->slots[0].stream;
+  CK(cudaMemcpyAsync(d_in, boundary, (size_t)B * n * 2 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_out, 0, (size_t)B * S_max * 7 * 8, st));
+  rc = cilqr_lane_constraints_device(h, cfg, B, n, S_max, is_left, d_in, d_out, d_cnt, st);
+  if (rc != CILQR_OK) return rc;
+  CK(cudaMemcpyAsync(out, d_out, (size_t)B * S_max * 7 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(count, d_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CILQR_OK;
+}
+
+int cilqr_corridor_last_kernel_ms(cilqr_handle* h, float* ms) {
+  if (!h || !ms || !h->corr_timed) return CILQR_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->corr_ev1));
+  CK(cudaEventElapsedTime(ms, h->corr_ev0, h->corr_ev1));
+  return CILQR_OK;
+}
+
 }  // extern "C"
+

@@ -229,7 +229,7 @@ def _path_profile(x, y, dt):
 
 
 def _gen_chunk(seed: int, chunk: int, n: int, N: int, n_obs: int, M_max: int, S: int, dt: float,
-               road_name: str = "gentle"):
+               road_name: str = "gentle", want_points: bool = False):
     rd = road(road_name)
     rng = np.random.Generator(np.random.Philox(key=[seed, chunk]))
     K = N + 1
@@ -322,9 +322,12 @@ def _gen_chunk(seed: int, chunk: int, n: int, N: int, n_obs: int, M_max: int, S:
     best_dy = np.zeros((n, n_obs, K))
     hx = half[None, :, 0, None]
     hy = half[None, :, 1, None]
+    corners = []
     for sx, sy in ((-1, -1), (-1, 1), (1, 1), (1, -1)):  # transform_footprint order
         kx = ocx + sx * hx * cos_o - sy * hy * sin_o - px[:, None, :]
         ky = ocy + sx * hx * sin_o + sy * hy * cos_o - py[:, None, :]
+        if want_points:
+            corners.append(np.stack([kx + px[:, None, :], ky + py[:, None, :]], axis=-1))  # [n,n_obs,K,2]
         d2 = kx * kx + ky * ky
         better = d2 < best_d2
         best_d2 = np.where(better, d2, best_d2)
@@ -380,6 +383,16 @@ def _gen_chunk(seed: int, chunk: int, n: int, N: int, n_obs: int, M_max: int, S:
         ln[..., 5] -= ox[:, None]
         ln[..., 4] -= oy[:, None]
         ln[..., 6] -= oy[:, None]
+    if want_points:
+        # obstacle points per knot as Environment::QueryStatic/DynamicObstaclesPoints hand them to
+        # Corridor::BuildCorridor (environment.cpp:163-194): static obstacles first, then the dynamic ones at
+        # the knot's time, four corners each -> [n, K, 4*n_obs, 2], ego-centred like everything else
+        pts = np.stack(corners, axis=2)  # [n, n_obs, 4, K, 2]
+        perm = list(range(n_ped + n_mov, n_obs)) + list(range(n_ped + n_mov))
+        pts = np.transpose(pts[:, perm], (0, 3, 1, 2, 4)).reshape(n, K, 4 * n_obs, 2).copy()
+        pts[..., 0] -= ox[:, None, None]
+        pts[..., 1] -= oy[:, None, None]
+        return start, coarse, corridor, corridor_cnt, lanes[0], lanes[1], pts
     return start, coarse, corridor, corridor_cnt, lanes[0], lanes[1]
 
 
@@ -407,6 +420,53 @@ def generate(seed: int, first_id: int, count: int, N: int = 100, n_obs: int = 20
     arrs = [np.concatenate([p[i] for p in parts], axis=0)[lo:lo + count] for i in range(6)]
     arrs = [np.ascontiguousarray(a) for a in arrs]
     return ScenarioBatch(N, M_max, S, *arrs)
+
+
+@dataclass
+class CorridorInputs:
+    """Inputs of Corridor::Plan for a batch (include/cilqr_b200.h, CilqrCorridorIn)."""
+
+    traj: np.ndarray        # [B,K,3] x, y, theta of the coarse trajectory
+    obs_points: np.ndarray  # [B,K,P_max,2]
+    obs_cnt: np.ndarray     # [B,K] int32
+
+    @property
+    def B(self) -> int:
+        return self.traj.shape[0]
+
+    @property
+    def K(self) -> int:
+        return self.traj.shape[1]
+
+    @property
+    def P_max(self) -> int:
+        return self.obs_points.shape[2]
+
+
+def generate_with_obstacles(seed: int, first_id: int, count: int, N: int = 100, n_obs: int = 20,
+                            M_max: int = 20, S: int = 40, dt: float = 0.1, road_name: str = "gentle",
+                            drop_far: bool = True):
+    """Like generate(), and additionally the obstacle point clouds of the same scenarios: returns
+    (ScenarioBatch, CorridorInputs).  With ``drop_far`` the points of obstacles that are further than
+    60 m from the knot are dropped and the rest compacted (ragged obs_cnt), as a caller with a spatial
+    index would do; BuildCorridor's own +-25 m filter makes the result independent of that."""
+    c0, c1 = first_id // CHUNK, (first_id + count - 1) // CHUNK
+    parts = [_gen_chunk(seed, c, CHUNK, N, n_obs, M_max, S, dt, road_name, want_points=True) for c in range(c0, c1 + 1)]
+    lo = first_id - c0 * CHUNK
+    arrs = [np.ascontiguousarray(np.concatenate([p[i] for p in parts], axis=0)[lo:lo + count]) for i in range(7)]
+    batch = ScenarioBatch(N, M_max, S, *arrs[:6])
+    pts = arrs[6]
+    B, K, P, _ = pts.shape
+    cnt = np.full((B, K), P, dtype=np.int32)
+    if drop_far:
+        d = pts - batch.coarse[:, :, None, :2]
+        keep = (np.abs(d[..., 0]) <= 60.0) & (np.abs(d[..., 1]) <= 60.0)
+        order = np.argsort(~keep, axis=2, kind="stable")  # kept points first, original order preserved
+        pts = np.take_along_axis(pts, order[..., None], axis=2)
+        cnt = keep.sum(axis=2).astype(np.int32)
+        pts[np.arange(P)[None, None, :] >= cnt[..., None]] = np.nan  # slots >= cnt must never be read
+    traj = np.ascontiguousarray(batch.coarse[:, :, :3])
+    return batch, CorridorInputs(traj, np.ascontiguousarray(pts), cnt)
 
 
 def config_batch(index: int, count: int | None = None, first_id: int = 0) -> ScenarioBatch:

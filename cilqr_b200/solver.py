@@ -59,11 +59,31 @@ class DebugOut(C.Structure):
         "Xn", "Un", "costn", "nearest")]
 
 
+class CorridorConfig(C.Structure):
+    """POD mirror of CilqrCorridorConfig (CorridorConfig, planner_config.h:75-86)."""
+    _fields_ = [(n, C.c_double) for n in ("max_diff_x", "max_diff_y", "radius", "max_axis_x", "max_axis_y",
+                                          "lane_segment_length")] + [("point_cap", C.c_int32)]
+
+
+class CorridorIn(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("P_max", C.c_int32), ("M_max", C.c_int32),
+                ("traj", C.c_void_p), ("obs_points", C.c_void_p), ("obs_cnt", C.c_void_p)]
+
+
+class CorridorOut(C.Structure):
+    _fields_ = [("corridor", C.c_void_p), ("corridor_cnt", C.c_void_p), ("polygon", C.c_void_p),
+                ("code", C.c_void_p)]
+
+
+CORRIDOR_CODE_NAMES = ["ok", "no_points", "few_points", "origin", "capacity", "point_capacity"]
+
 EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_destroy",
            "cilqr_plan_batch", "cilqr_plan_batch_device", "cilqr_synchronize",
            "cilqr_kernel_launches", "cilqr_last_kernel_ms", "cilqr_occupancy", "cilqr_strerror",
            "cilqr_last_cuda_error", "cilqr_debug_first_iteration", "cilqr_debug_stats",
-           "cilqr_debug_completion_histogram"]
+           "cilqr_debug_completion_histogram", "cilqr_corridor_default_config", "cilqr_corridor_batch",
+           "cilqr_corridor_batch_device", "cilqr_lane_constraints", "cilqr_lane_constraints_device",
+           "cilqr_corridor_last_kernel_ms"]
 
 _lib = None
 
@@ -103,6 +123,17 @@ def load_library(build_if_missing: bool = True):
     L.cilqr_debug_first_iteration.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(DebugOut)]
     L.cilqr_debug_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.cilqr_debug_completion_histogram.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.cilqr_corridor_default_config.argtypes = [C.POINTER(CorridorConfig)]
+    L.cilqr_corridor_default_config.restype = None
+    L.cilqr_corridor_batch.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.POINTER(CorridorIn),
+                                       C.POINTER(CorridorOut)]
+    L.cilqr_corridor_batch_device.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.POINTER(CorridorIn),
+                                              C.POINTER(CorridorOut), C.c_void_p]
+    L.cilqr_lane_constraints.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cilqr_lane_constraints_device.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cilqr_corridor_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -111,6 +142,13 @@ def default_params() -> Params:
     p = Params()
     load_library().cilqr_default_params(C.byref(p))
     return p
+
+
+def default_corridor_config(point_cap: int = 0) -> CorridorConfig:
+    c = CorridorConfig()
+    load_library().cilqr_corridor_default_config(C.byref(c))
+    c.point_cap = point_cap
+    return c
 
 
 def _ptr(x):
@@ -236,3 +274,51 @@ class Solver:
         w, s = C.c_int(), C.c_int()
         self._check(self._L.cilqr_occupancy(self._h, N, S_left, S_right, C.byref(w), C.byref(s)))
         return w.value, s.value
+
+    # ---- corridor builder (Corridor::Plan, algorithm/ilqr/corridor.cc:17-54) --------------------------
+    def corridor_batch(self, traj, obs_points, obs_cnt, M_max: int, polygon: bool = False,
+                       cfg: CorridorConfig | None = None) -> dict:
+        """Host path of BuildCorridorConstraints for a batch: numpy in, numpy out."""
+        cfg = cfg or default_corridor_config()
+        traj = np.ascontiguousarray(traj, np.float64)
+        pts = np.ascontiguousarray(obs_points, np.float64)
+        cnt = np.ascontiguousarray(obs_cnt, np.int32)
+        B, K, P = pts.shape[:3]
+        o = {"corridor": np.zeros((B, K, M_max, 3)), "corridor_cnt": np.zeros((B, K), np.int32),
+             "code": np.zeros((B, K), np.int32)}
+        if polygon:
+            o["polygon"] = np.zeros((B, K, M_max, 2))
+        ci = CorridorIn(B, K, P, M_max, _ptr(traj), _ptr(pts), _ptr(cnt))
+        co = CorridorOut(_ptr(o["corridor"]), _ptr(o["corridor_cnt"]), _ptr(o.get("polygon")), _ptr(o["code"]))
+        self._check(self._L.cilqr_corridor_batch(self._h, C.byref(cfg), C.byref(ci), C.byref(co)))
+        return o
+
+    def corridor_batch_device(self, B, K, P_max, M_max, traj, obs_points, obs_cnt, corridor, corridor_cnt, code,
+                              polygon=None, cfg: CorridorConfig | None = None, stream: int | None = None):
+        """Device path: pointers / CUDA tensors; enqueues the build kernel and returns."""
+        cfg = cfg or default_corridor_config()
+        ci = CorridorIn(B, K, P_max, M_max, _ptr(traj), _ptr(obs_points), _ptr(obs_cnt))
+        co = CorridorOut(_ptr(corridor), _ptr(corridor_cnt), _ptr(polygon), _ptr(code))
+        self._check(self._L.cilqr_corridor_batch_device(self._h, C.byref(cfg), C.byref(ci), C.byref(co), stream))
+
+    def lane_constraints(self, boundary, is_left: bool, S_max: int, cfg: CorridorConfig | None = None):
+        """CalLeft/RightLaneConstraints for B boundary polylines [B,n,2] -> ([B,S_max,7], count [B])."""
+        cfg = cfg or default_corridor_config()
+        bd = np.ascontiguousarray(boundary, np.float64)
+        B, n = bd.shape[:2]
+        out = np.zeros((B, S_max, 7))
+        cnt = np.zeros(B, np.int32)
+        self._check(self._L.cilqr_lane_constraints(self._h, C.byref(cfg), B, n, S_max, int(is_left), _ptr(bd),
+                                                   _ptr(out), _ptr(cnt)))
+        return out, cnt
+
+    def lane_constraints_device(self, B, n, S_max, is_left, boundary, out, count,
+                                cfg: CorridorConfig | None = None, stream: int | None = None):
+        cfg = cfg or default_corridor_config()
+        self._check(self._L.cilqr_lane_constraints_device(self._h, C.byref(cfg), B, n, S_max, int(is_left),
+                                                          _ptr(boundary), _ptr(out), _ptr(count), stream))
+
+    def corridor_last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.cilqr_corridor_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CILQR_ABI_VERSION 1
+#define CILQR_ABI_VERSION 2
 
 /* error codes */
 #define CILQR_OK 0
@@ -158,6 +158,75 @@ typedef struct CilqrDebugOut {
   int32_t* nearest; /* [B][K][5][2] nearest lane segment per disc/side at the initial guess */
 } CilqrDebugOut;
 int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in_dev, const CilqrDebugOut* out_dev);
+
+/* ------------------------------------------------------------------------------------------------
+ * Safe-corridor builder: the step immediately before the solve.
+ * Replaces Corridor::Plan (algorithm/ilqr/corridor.h:31-36, corridor.cc:17-54) for B trajectories of
+ * K knots at once: BuildCorridorConstraints (:56-87) = per knot AddCorridorPoints (:89-120) +
+ * BuildCorridor (:122-263, three cv::convexHull calls on CV_32F points), and
+ * CalLeft/RightLaneConstraints (:265-307) with LaneBoundarySample (:309-322) and HalfPlaneConstraint
+ * (:324-331).  The environment queries (Environment::QueryStatic/DynamicObstaclesPoints,
+ * utils/environment.cpp:163-194) stay with the caller: it passes, per knot, the obstacle points it
+ * would hand to BuildCorridor (static obstacle points first, then the dynamic ones at pt.time).
+ * The outputs have exactly the layout cilqr_plan_batch(_device) reads (corridor / corridor_cnt /
+ * lane_left / lane_right), so on the device path the two calls chain without touching the host.
+ *
+ *   traj        [B][K][3]            x, y, theta of the coarse trajectory (TrajectoryPoint fields the
+ *                                    corridor reads, corridor.cc:76-79,96-97)
+ *   obs_points  [B][K][P_max][2]     obstacle points at knot k; obs_cnt [B][K] int32 of them are valid
+ *   corridor    [B][K][M_max][3] out half-planes (a,b,c), a*x + b*y < c, un-normalised polygon edges
+ *   corridor_cnt[B][K] int32     out
+ *   polygon     [B][K][M_max][2] out (optional) ConvexPolygons vertices, corridor.cc:245-250
+ *   code        [B][K] int32     out CILQR_CORR_* per knot; Corridor::Plan returns false iff any is != 0
+ * A knot with a non-zero code has corridor_cnt = 0.
+ */
+#define CILQR_CORR_OK 0
+#define CILQR_CORR_NO_POINTS 1      /* corridor.cc:127-130 */
+#define CILQR_CORR_FEW_POINTS 2     /* fewer than 4 flipped points, corridor.cc:179-182 */
+#define CILQR_CORR_ORIGIN 3         /* knot on the flipped hull: undefined in the reference (:193-209) */
+#define CILQR_CORR_CAPACITY 4       /* more than M_max planes at a knot */
+#define CILQR_CORR_POINT_CAPACITY 5 /* more points inside the +-max_diff window than point_cap */
+
+/* CorridorConfig, algorithm/params/planner_config.h:75-86 (is_multiple_sample = false). */
+typedef struct CilqrCorridorConfig {
+  double max_diff_x, max_diff_y, radius, max_axis_x, max_axis_y, lane_segment_length;
+  int32_t point_cap; /* capacity for the points that pass the +-max_diff filter at one knot (<= 250);
+                        sets the shared memory per thread.  0 = default (64). */
+} CilqrCorridorConfig;
+void cilqr_corridor_default_config(CilqrCorridorConfig* c);
+
+typedef struct CilqrCorridorIn {
+  int32_t B, K, P_max, M_max;
+  const double* traj;
+  const double* obs_points;
+  const int32_t* obs_cnt;
+} CilqrCorridorIn;
+
+typedef struct CilqrCorridorOut {
+  double* corridor;      /* required */
+  int32_t* corridor_cnt; /* required */
+  double* polygon;       /* optional */
+  int32_t* code;         /* required */
+} CilqrCorridorOut;
+
+/* HOST pointers; blocks until the outputs are in host memory. */
+int cilqr_corridor_batch(cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                         const CilqrCorridorOut* out);
+/* DEVICE pointers; enqueues on `cuda_stream` (NULL = the handle's stream) and returns. */
+int cilqr_corridor_batch_device(cilqr_handle* h, const CilqrCorridorConfig* cfg, const CilqrCorridorIn* in,
+                                const CilqrCorridorOut* out, void* cuda_stream);
+
+/* Lane constraints of B boundary polylines of n points each (boundary [B][n][2]):
+ * out [B][S_max][7] = a,b,c,x0,y0,x1,y1 per segment, count [B] int32 = number of segments, or -1 when
+ * fewer than two points were sampled (the reference returns false, corridor.cc:275-277), -2 when more
+ * than S_max.  is_left selects CalLeftLaneConstraints' segment direction (corridor.cc:279 vs :300). */
+int cilqr_lane_constraints(cilqr_handle* h, const CilqrCorridorConfig* cfg, int B, int n, int S_max, int is_left,
+                           const double* boundary, double* out, int32_t* count);
+int cilqr_lane_constraints_device(cilqr_handle* h, const CilqrCorridorConfig* cfg, int B, int n, int S_max,
+                                  int is_left, const double* boundary, double* out, int32_t* count,
+                                  void* cuda_stream);
+/* CUDA-event time of the last corridor kernel enqueued through this handle. */
+int cilqr_corridor_last_kernel_ms(cilqr_handle* h, float* ms);
 
 #ifdef __cplusplus
 }

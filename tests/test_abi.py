@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", cilqr_b200.lib_path()], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", out), n
-    assert lib.cilqr_abi_version() == 1
+    assert lib.cilqr_abi_version() == 2
 
 
 def test_product_library_does_not_link_the_oracle():
@@ -47,6 +47,10 @@ def test_struct_layout_matches_header():
     assert C.sizeof(S.BatchIn) == 24 + 6 * 8
     assert C.sizeof(S.BatchOut) == 10 * 8 + 8
     assert C.sizeof(S.DebugOut) == 17 * 8
+    # CilqrCorridorConfig: 6 doubles + int32 (+pad); CilqrCorridorIn: 4 int32 + 3 pointers; CilqrCorridorOut: 4 pointers
+    assert C.sizeof(S.CorridorConfig) == 6 * 8 + 8
+    assert C.sizeof(S.CorridorIn) == 16 + 3 * 8
+    assert C.sizeof(S.CorridorOut) == 4 * 8
 
 
 def test_default_params_equal_the_oracles(oracle):
