@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--ref-sample", type=int, default=2048, help="scenarios per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-corridor", action="store_true", help="skip the corridor-builder side measurement")
+    ap.add_argument("--corridor-base", type=int, default=2048,
+                    help="scenarios generated on the host for the corridor measurement (tiled on the device)")
     return ap.parse_args()
 
 
@@ -107,6 +110,49 @@ def cpu_baseline(a, kind_note=""):
     return {"value": conv / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {n} scenarios of the bench workload, C restatement of the reference solver "
                       f"(gcc -O2, double), {cores} pthreads, {dt:.2f} s wall; mean iterations {st[:, 1].mean():.2f}"}
+
+
+def corridor_measurement(solver, a, dev, stream, peak):
+    """Side measurement (rank 0): the batched Corridor::Plan kernel (SURVEY 8(f) rank 1, the step before the
+    solve) at the bench shape, next to its CPU restatement on one host core.  Not part of `value`."""
+    import torch
+    from cilqr_b200 import scenarios
+    from cilqr_b200.solver import default_corridor_config
+    from oracle import corridor_binding as cb
+    base, N, M = min(a.corridor_base, a.batch_per_gpu), a.horizon, 20
+    _, ci = scenarios.generate_with_obstacles(SEED, 0, base, N=N, n_obs=a.obstacles)
+    rep = max(1, a.batch_per_gpu // base)
+    B, K, P = base * rep, ci.K, ci.P_max
+    tile = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev).repeat(rep, *([1] * (x.ndim - 1)))  # noqa: E731
+    traj, pts, cnt = tile(ci.traj), tile(ci.obs_points), tile(ci.obs_cnt)
+    cor = torch.zeros(B, K, M, 3, dtype=torch.float64, device=dev)
+    ccnt = torch.zeros(B, K, dtype=torch.int32, device=dev)
+    code = torch.zeros(B, K, dtype=torch.int32, device=dev)
+    cfg = default_corridor_config(point_cap=4 * a.obstacles + 16)
+    ms = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        solver.corridor_batch_device(B, K, P, M, traj, pts, cnt, cor, ccnt, code, cfg=cfg, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        ms.append(solver.corridor_last_kernel_ms())
+    kms = float(np.mean(ms[1:]))
+    # algorithmic bytes: trajectory + valid obstacle points + counts in, planes + counts + codes out
+    alg = traj.numel() * 8 + int(cnt.sum().item()) * 16 + cnt.numel() * 4 + int(ccnt.sum().item()) * 24 + ccnt.numel() * 8
+    fails = int((code != 0).sum().item())
+    n_cpu = min(base, 512)
+    t0 = time.perf_counter()
+    ocor, ocnt, _, ocode = cb.plan_batch(ci.traj[:n_cpu], ci.obs_points[:n_cpu], ci.obs_cnt[:n_cpu], M)
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(ccnt[:n_cpu].cpu().numpy(), ocnt))
+    return {"kernel": "corridor_build_kernel", "knots_per_launch": B * K, "kernel_ms": kms,
+            "traj_per_s": B / kms * 1e3, "knots_per_s": B * K / kms * 1e3, "failed_knots": fails,
+            "planes_per_knot": float(ccnt.double().mean().item()),
+            "roofline": {"bound": "hbm", "achieved": alg / kms / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": alg / kms / 1e6 / peak, "algorithmic_bytes_per_launch": alg},
+            "cpu_baseline": {"value": n_cpu / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"first {n_cpu} scenarios x {K} knots, oracle/corridor_oracle.c, 1 thread, "
+                                       f"{cpu_s:.2f} s; plane counts equal to the GPU's: {same}"},
+            "note": f"{base} generated scenarios tiled x{rep} on the device; one thread per knot, point_cap {cfg.point_cap}"}
 
 
 def run_reference(a):
@@ -272,6 +318,9 @@ def main():
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        corridor = None
+        if not a.no_corridor:
+            corridor = corridor_measurement(solver, a, dev, stream, peak)
         alg_bytes = scenarios.algorithmic_bytes(N, batch.M_max, batch.S) * B
         achieved = alg_bytes / (kmean_ms * 1e-3) / 1e9
         traffic = None
@@ -299,6 +348,8 @@ def main():
         }
         if e2e:
             res["e2e"] = e2e
+        if corridor:
+            res["corridor"] = corridor
         if not a.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(res), flush=True)

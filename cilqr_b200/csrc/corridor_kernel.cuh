@@ -104,9 +104,19 @@ __device__ int sklansky(const Slice& s, const float* X, const float* Y, int star
   SETSTK(2, pnext);
   end += incr;
   float prevx = PX(pprev), prevy = PY(pprev), curx = PX(pcur), cury = PY(pcur);
+  // the point after pnext is fetched one step ahead: every branch but the pop advances pnext by incr, so
+  // the two dependent shared-memory loads (order byte, then coordinates) overlap the arithmetic of this step
+  float nextx = 0.0f, nexty = 0.0f, aheadx = 0.0f, aheady = 0.0f;
+  if (pnext != end) { nextx = PX(pnext); nexty = PY(pnext); }
+  bool have_ahead = false;
   while (pnext != end) {
-    const float nextx = PX(pnext), nexty = PY(pnext);
+    if (!have_ahead) {
+      const int pa = pnext + incr;
+      if (pa != end) { aheadx = PX(pa); aheady = PY(pa); }
+      have_ahead = true;
+    }
     const float by = fsub(nexty, cury);
+    bool advance = true;
     if (sgnf(by) != nsign) {
       const float ax = fsub(curx, prevx);
       const float bx = fsub(nextx, curx);
@@ -130,11 +140,16 @@ __device__ int sklansky(const Slice& s, const float* X, const float* Y, int star
           pprev = STK(stacksize - 4);
           prevx = PX(pprev); prevy = PY(pprev);
           stacksize--;
+          advance = false;  // pnext stays: the point fetched ahead stays ahead
         }
       }
     } else {
       pnext += incr;
       SETSTK(stacksize - 1, pnext);
+    }
+    if (advance) {
+      nextx = aheadx; nexty = aheady;
+      have_ahead = false;
     }
   }
   return --stacksize;
@@ -149,17 +164,31 @@ __device__ int sklansky(const Slice& s, const float* X, const float* Y, int star
 __device__ int convex_hull(const Slice& s, const float* X, const float* Y, int total, bool clockwise) {
   const int T = s.T;
   if (total <= 0) return 0;
-  // insertion sort of the index permutation (the comparator is a strict total order)
-  for (int i = 0; i < total; ++i) {
-    const float xi = X[i * T], yi = Y[i * T];
-    int j = i;
-    while (j > 0) {
-      const int o = s.get(F_ORD, j - 1);
-      if (!pt_less(xi, yi, i, X[o * T], Y[o * T], o)) break;
-      s.set(F_ORD, j, o);
-      --j;
+  // sort of the index permutation by rank counting: the comparator is a strict total order, so the rank
+  // of a point is its sorted position.  O(n^2) comparisons, but every one of them is independent (the
+  // insertion sort this replaces was a chain of dependent shared-memory read-modify-writes, and with only a
+  // few warps per SM -- the per-thread slice is ~1 KB -- latency, not issue rate, is what costs).  Four
+  // points are ranked per sweep so that each loaded (x, y) is used four times.
+  for (int i = 0; i < total; i += 4) {
+    float xi[4], yi[4];
+    int r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ii = i + q < total ? i + q : total - 1;
+      xi[q] = X[ii * T];
+      yi[q] = Y[ii * T];
+      r[q] = 0;
     }
-    s.set(F_ORD, j, i);
+#pragma unroll 4
+    for (int j = 0; j < total; ++j) {
+      const float xj = X[j * T], yj = Y[j * T];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        r[q] += (xj < xi[q]) | ((xj == xi[q]) & ((yj < yi[q]) | ((yj == yi[q]) & (j < i + q))));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i + q < total) s.set(F_ORD, r[q], i + q);
   }
   int miny_ind = 0, maxy_ind = 0;
   {

@@ -58,7 +58,7 @@ def test_corridor_parity_with_oracle(solver, corr_oracle, N, B, seed, n_obs):
     M = 24
     cor, cnt, poly, code = corr_oracle.plan_batch(ci.traj, ci.obs_points, ci.obs_cnt, M)
     got = solver.corridor_batch(ci.traj, ci.obs_points, ci.obs_cnt, M, polygon=True,
-                                cfg=default_corridor_config(point_cap=4 * n_obs + 8))
+                                cfg=default_corridor_config(point_cap=4 * n_obs + 16))
     _check(got, cor, cnt, code)
     assert solver.corridor_last_kernel_ms() > 0
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarises an ncu report of the solve kernel: headline metrics + per-function instruction / stall-sample shares.
-usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep [out.md]"""
+usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep [out.md] [source file for the function ranges]"""
 import csv, io, re, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -29,8 +29,7 @@ for r in rows:
 ci, si = h2.index("Instructions Executed"), h2.index("# Samples")
 tot = sum(int(r[ci]) for r in lines if r[ci].isdigit()); tots = sum(int(r[si]) for r in lines if r[si].isdigit())
 # function ranges from the source file itself
-srcfile = [r[1] for r in lines]
-text = open("cilqr_b200/csrc/cilqr_kernel.cuh").read().split("\n")
+text = open(sys.argv[3] if len(sys.argv) > 3 else "cilqr_b200/csrc/cilqr_kernel.cuh").read().split("\n")
 funcs = []
 for i, l in enumerate(text, 1):
     m = re.match(r"^(?:template <[^>]*>\s*)?__(?:device|global)__.*?\b(\w+)\(", l)
