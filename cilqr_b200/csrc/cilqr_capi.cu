@@ -829,6 +829,8 @@ int cilqr_corridor_batch(cilqr_handle* h, const CilqrCorridorConfig* cfg, const 
   if (in->P_max > 0)
     CK(cudaMemcpyAsync((void*)din.obs_points, in->obs_points, items * in->P_max * 2 * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync((void*)din.obs_cnt, in->obs_cnt, items * 4, cudaMemcpyHostToDevice, st));
+  // slots beyond corridor_cnt are not written by the kernel: return them as zeros, not as stale staging data
+  CK(cudaMemsetAsync(dout.corridor, 0, b_cor + b_ccnt + b_poly + b_code, st));
   rc = corridor_launch(h, cfg, &din, &dout, st);
   if (rc != CILQR_OK) return rc;
   CK(cudaMemcpyAsync(out->corridor, dout.corridor, items * in->M_max * 3 * 8, cudaMemcpyDeviceToHost, st));

@@ -169,26 +169,38 @@ __device__ int convex_hull(const Slice& s, const float* X, const float* Y, int t
   // insertion sort this replaces was a chain of dependent shared-memory read-modify-writes, and with only a
   // few warps per SM -- the per-thread slice is ~1 KB -- latency, not issue rate, is what costs).  Four
   // points are ranked per sweep so that each loaded (x, y) is used four times.
+  // Coincident x are rare (the duplicated box corners), so the sweep compares x only and counts the ties;
+  // a point with ties is then ranked among them by (y, index) in a second, short sweep.
   for (int i = 0; i < total; i += 4) {
-    float xi[4], yi[4];
-    int r[4];
+    float xi[4];
+    int r[4], e[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int ii = i + q < total ? i + q : total - 1;
-      xi[q] = X[ii * T];
-      yi[q] = Y[ii * T];
+      xi[q] = X[(i + q < total ? i + q : total - 1) * T];
       r[q] = 0;
+      e[q] = 0;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < total; ++j) {
-      const float xj = X[j * T], yj = Y[j * T];
+      const float xj = X[j * T];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        r[q] += (xj < xi[q]) | ((xj == xi[q]) & ((yj < yi[q]) | ((yj == yi[q]) & (j < i + q))));
+      for (int q = 0; q < 4; ++q) {
+        r[q] += xj < xi[q];
+        e[q] += xj == xi[q];
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (i + q < total) s.set(F_ORD, r[q], i + q);
+    for (int q = 0; q < 4; ++q) {
+      if (i + q >= total) continue;
+      if (e[q] > 1) {  // e counts the point itself
+        const float yi = Y[(i + q) * T];
+        for (int j = 0; j < total; ++j) {
+          const float yj = Y[j * T];
+          r[q] += (X[j * T] == xi[q]) & ((yj < yi) | ((yj == yi) & (j < i + q)));
+        }
+      }
+      s.set(F_ORD, r[q], i + q);
+    }
   }
   int miny_ind = 0, maxy_ind = 0;
   {
@@ -328,9 +340,11 @@ __global__ void __launch_bounds__(256) corridor_build_kernel(const Args a) {
     // :135-177 filter + sphere flip about the knot.  flipData's unused slots are (0,0) = the knot
     // itself; they are interior to the hull of the flipped box points, so one of them is kept.
     int nf = 0;
+    double qx, qy;  // the next point is loaded one step ahead of the double-precision work on this one
+    point(0, &qx, &qy);
     for (int i = 0; i < n; ++i) {
-      double px, py;
-      point(i, &px, &py);
+      const double px = qx, py = qy;
+      if (i + 1 < n) point(i + 1, &qx, &qy);
       const double dx = dsub(px, ox), dy = dsub(py, oy);
       if (fabs(dx) > a.max_diff_x || fabs(dy) > a.max_diff_y) continue;
       const double norm2 = __dsqrt_rn(dadd(dmul(dx, dx), dmul(dy, dy)));

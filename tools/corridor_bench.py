@@ -33,13 +33,13 @@ if __name__ == "__main__":
     ccnt = torch.zeros(B, K, dtype=torch.int32, device=dev)
     code = torch.zeros(B, K, dtype=torch.int32, device=dev)
     s = cilqr_b200.Solver(device=0)
-    cfg = default_corridor_config(point_cap=a.cap or 4 * a.obstacles + 8)
+    cfg = default_corridor_config(point_cap=a.cap or 4 * a.obstacles + 16)
     ms = []
     for _ in range(a.reps + 1):
         s.corridor_batch_device(B, K, P, a.mmax, traj, pts, cnt, cor, ccnt, code, cfg=cfg)
         s.synchronize()
         ms.append(s.corridor_last_kernel_ms())
-    ms = ms[1:]
+    ms = ms[1:] or ms
     codes = np.bincount(code.cpu().numpy().ravel(), minlength=6).tolist()
     in_bytes = traj.numel() * 8 + int(cnt.sum().item()) * 16 + cnt.numel() * 4
     out_bytes = int(ccnt.sum().item()) * 24 + ccnt.numel() * 8
