@@ -60,5 +60,25 @@ def build_adapter_demo(force: bool = False) -> str:
     return ADAPTER_DEMO
 
 
+CORRIDOR_DEMO = os.path.join(LIB_DIR, "corridor_demo")
+
+
+def build_corridor_demo(force: bool = False) -> str:
+    """Compiles tests/adapter/corridor_demo.cc -- the reference's Corridor call site driven through the
+    header-compatible planning::Corridor (include/cilqr/corridor_b200.h) -- against the stand-ins."""
+    root = os.path.dirname(_HERE)
+    src = os.path.join(root, "tests", "adapter", "corridor_demo.cc")
+    hdr = os.path.join(root, "include", "cilqr", "corridor_b200.h")
+    if (not force and os.path.exists(CORRIDOR_DEMO)
+            and os.path.getmtime(CORRIDOR_DEMO) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB_PATH))):
+        return CORRIDOR_DEMO
+    build_library()
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(root, "tests", "adapter", "stubs"), src, "-o", CORRIDOR_DEMO,
+           "-L", LIB_DIR, "-lcilqr_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return CORRIDOR_DEMO
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

@@ -169,38 +169,41 @@ __device__ int convex_hull(const Slice& s, const float* X, const float* Y, int t
   // insertion sort this replaces was a chain of dependent shared-memory read-modify-writes, and with only a
   // few warps per SM -- the per-thread slice is ~1 KB -- latency, not issue rate, is what costs).  Four
   // points are ranked per sweep so that each loaded (x, y) is used four times.
-  // Coincident x are rare (the duplicated box corners), so the sweep compares x only and counts the ties;
-  // a point with ties is then ranked among them by (y, index) in a second, short sweep.
+  // The index tie-break of the comparator is folded into the sweep: against the points before the block a
+  // coincident point ranks first ("<="), against the points after it last ("<"), so both sweeps are three
+  // predicate-combining float compares per pair; only the block's own 4 x 4 pairs use the general rule.
   for (int i = 0; i < total; i += 4) {
-    float xi[4];
-    int r[4], e[4];
+    float xi[4], yi[4];
+    int r[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      xi[q] = X[(i + q < total ? i + q : total - 1) * T];
+      const int ii = i + q < total ? i + q : total - 1;
+      xi[q] = X[ii * T];
+      yi[q] = Y[ii * T];
       r[q] = 0;
-      e[q] = 0;
     }
-#pragma unroll 8
-    for (int j = 0; j < total; ++j) {
-      const float xj = X[j * T];
+#pragma unroll 4
+    for (int j = 0; j < i; ++j) {
+      const float xj = X[j * T], yj = Y[j * T];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        r[q] += xj < xi[q];
-        e[q] += xj == xi[q];
-      }
+      for (int q = 0; q < 4; ++q) r[q] += (xj < xi[q]) | ((xj == xi[q]) & (yj <= yi[q]));
+    }
+    const int jend = i + 4 < total ? i + 4 : total;
+    for (int j = i; j < jend; ++j) {
+      const float xj = X[j * T], yj = Y[j * T];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        r[q] += (xj < xi[q]) | ((xj == xi[q]) & ((yj < yi[q]) | ((yj == yi[q]) & (j < i + q))));
+    }
+#pragma unroll 4
+    for (int j = i + 4; j < total; ++j) {
+      const float xj = X[j * T], yj = Y[j * T];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] += (xj < xi[q]) | ((xj == xi[q]) & (yj < yi[q]));
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (i + q >= total) continue;
-      if (e[q] > 1) {  // e counts the point itself
-        const float yi = Y[(i + q) * T];
-        for (int j = 0; j < total; ++j) {
-          const float yj = Y[j * T];
-          r[q] += (X[j * T] == xi[q]) & ((yj < yi) | ((yj == yi) & (j < i + q)));
-        }
-      }
-      s.set(F_ORD, r[q], i + q);
-    }
+    for (int q = 0; q < 4; ++q)
+      if (i + q < total) s.set(F_ORD, r[q], i + q);
   }
   int miny_ind = 0, maxy_ind = 0;
   {

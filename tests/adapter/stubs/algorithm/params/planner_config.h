@@ -26,3 +26,15 @@ struct IlqrConfig {
   double rho = 1e-9;
 };
 }  // namespace planning
+namespace planning {
+// Stand-in for algorithm/params/planner_config.h:75-86.
+struct CorridorConfig {
+  bool is_multiple_sample = false;
+  double max_diff_x = 25.0;
+  double max_diff_y = 25.0;
+  double radius = 150.0;
+  double max_axis_x = 10.0;
+  double max_axis_y = 10.0;
+  double lane_segment_length = 5.0;
+};
+}  // namespace planning
