@@ -5,7 +5,8 @@
 // Drop-in use inside the reference tree: include this header instead of
 // "algorithm/ilqr/corridor.h" in algorithm/planner/trajectory_planner.h, drop algorithm/ilqr/corridor.cc
 // (and with it the OpenCV dependency of the planner library) from CMakeLists.txt.  The call sites
-// trajectory_planner.cpp:25 (construction), :49-57 (Plan) and :99-101 (points_for_corridors) compile
+// trajectory_planner.cpp:25 (member initialiser), :49-57 (Plan) and planning_node.cc:87-103
+// (convex polygons / points_for_corridors for plotting) compile
 // unchanged.
 //
 // The environment queries stay on the host exactly as in the reference (BuildCorridorConstraints,
@@ -161,7 +162,7 @@ class Corridor {
       return false;
     }
     for (int k = 0; k < K; ++k) {
-      // points_for_corridors_ (visualisation, trajectory_planner.cpp:99-101): the knot's obstacle points
+      // points_for_corridors_ (visualisation, planning_node.cc:88,103): the knot's obstacle points
       // followed by the eight box points of AddCorridorPoints (corridor.cc:89-120)
       AppendBoxPoints(trajectory.trajectory()[k], &per_knot[k]);
       points_for_corridors_.push_back(per_knot[k]);

@@ -1,5 +1,5 @@
 // corridor_demo.cc -- drives planning::Corridor (include/cilqr/corridor_b200.h) the way the reference's
-// TrajectoryPlanner does (algorithm/planner/trajectory_planner.cpp:25,49-57,99-101): construct with
+// TrajectoryPlanner does (algorithm/planner/trajectory_planner.cpp:25,49-57, planning_node.cc:87-103): construct with
 // (CorridorConfig, Env), call Plan once, read the constraints, polygons, lanes and points_for_corridors().
 //
 //   corridor_demo <scene.bin> <result.bin>
@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
 
   CorridorConfig config;
   Corridor corridor;
-  corridor = Corridor(config, env);  // trajectory_planner.cpp:25
+  corridor = Corridor(config, env);  // trajectory_planner.cpp:25 (there: member initialiser)
   CorridorConstraints cc;
   ConvexPolygons polys;
   LaneConstraints left, right;

@@ -1,5 +1,5 @@
 """The reference's C++ call site of the corridor (TrajectoryPlanner -> Corridor::Plan,
-trajectory_planner.cpp:25,49-57,99-101) driven through the header-compatible planning::Corridor of
+trajectory_planner.cpp:25,49-57, planning_node.cc:87-103) driven through the header-compatible planning::Corridor of
 include/cilqr/corridor_b200.h, compiled against the stand-ins in tests/adapter/stubs."""
 import subprocess
 
