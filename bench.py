@@ -139,6 +139,10 @@ def corridor_measurement(solver, a, dev, stream, peak):
     # algorithmic bytes: trajectory + valid obstacle points + counts in, planes + counts + codes out
     alg = traj.numel() * 8 + int(cnt.sum().item()) * 16 + cnt.numel() * 4 + int(ccnt.sum().item()) * 24 + ccnt.numel() * 8
     fails = int((code != 0).sum().item())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("corridor", {}).get("dram_bytes_per_launch")
     n_cpu = min(base, 512)
     t0 = time.perf_counter()
     ocor, ocnt, _, ocode = cb.plan_batch(ci.traj[:n_cpu], ci.obs_points[:n_cpu], ci.obs_cnt[:n_cpu], M)
@@ -148,7 +152,7 @@ def corridor_measurement(solver, a, dev, stream, peak):
             "traj_per_s": B / kms * 1e3, "knots_per_s": B * K / kms * 1e3, "failed_knots": fails,
             "planes_per_knot": float(ccnt.double().mean().item()),
             "roofline": {"bound": "hbm", "achieved": alg / kms / 1e6, "peak": peak, "unit": "GB/s",
-                         "frac": alg / kms / 1e6 / peak, "algorithmic_bytes_per_launch": alg},
+                         "frac": alg / kms / 1e6 / peak, "algorithmic_bytes_per_launch": alg, "traffic": traffic},
             "cpu_baseline": {"value": n_cpu / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"first {n_cpu} scenarios x {K} knots, oracle/corridor_oracle.c, 1 thread, "
                                        f"{cpu_s:.2f} s; plane counts equal to the GPU's: {same}"},
