@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--obstacles", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=4096, help="scenarios in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=2048, help="scenarios per step of --impl reference")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="batches in flight in the timed region (one solver handle + stream each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-corridor", action="store_true", help="skip the corridor-builder side measurement")
@@ -225,86 +227,138 @@ def main():
     host_in = [batch.start, batch.coarse, batch.corridor, batch.corridor_cnt, batch.lane_left, batch.lane_right]
     pinned = [torch.from_numpy(x).pin_memory() for x in host_in]
     dev_in = [t.to(dev, non_blocking=True) for t in pinned]
-    block = torch.empty(sharding.block_doubles(B, N), dtype=torch.float64, device=dev)
-    states, controls, status = sharding.carve_block(block, B, N)
-    gathered = torch.empty((world, block.numel()), dtype=torch.float64, device=dev) if world > 1 else None
+    F = max(1, a.in_flight)
+    blocks = [torch.empty(sharding.block_doubles(B, N), dtype=torch.float64, device=dev) for _ in range(F)]
+    views = [sharding.carve_block(blk, B, N) for blk in blocks]
+    gathered = [torch.empty((world, blocks[0].numel()), dtype=torch.float64, device=dev) if world > 1 else None
+                for _ in range(F)]
     torch.cuda.synchronize()
 
-    solver = cilqr_b200.Solver(device=local, N_max=max(N, 100), M_max=batch.M_max, S_max=batch.S, B_max=B)
-    # a dedicated (non-default) torch stream: the solve kernel, the events that time it and the NCCL
-    # all-gather are all enqueued on it (a NULL stream would make the library use its own stream)
-    stream = torch.cuda.Stream(device=dev)
+    # One handle = one solve stream + one context workspace.  F handles keep F batches in flight: the
+    # persistent solve kernel releases an SM as soon as that SM's scenarios are done, so the next batch's
+    # kernel (another stream) fills the SMs that the drain and the straggler tail of this one leave idle.
+    solvers = [cilqr_b200.Solver(device=local, N_max=max(N, 100), M_max=batch.M_max, S_max=batch.S, B_max=B)
+               for _ in range(F)]
+    solver = solvers[0]
+    # dedicated (non-default) torch streams: solve kernels, the events that time them and the NCCL
+    # all-gathers are enqueued on them (a NULL stream would make the library use its own stream)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(F)]
+    comm_stream = torch.cuda.Stream(device=dev)
+    stream = streams[0]
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    kernel_ms = []
+    assert all(st.cuda_stream != 0 for st in streams)
+    states, controls, status = views[0]
 
-    def step():
-        solver.plan_batch_device(B, N, batch.M_max, batch.S, batch.S, *dev_in, states, controls, status,
-                                 stream=stream.cuda_stream)
+    def launch(f):
+        """one step on slot f: solve on that slot's stream, then (N > 1) the all-gather of its result block,
+        ordered after the solve by an event, on the communication stream (collectives stay in issue order)"""
+        st = streams[f]
+        solvers[f].plan_batch_device(B, N, batch.M_max, batch.S, batch.S, *dev_in, *views[f], stream=st.cuda_stream)
         if world > 1:
-            sharding.gather_blocks(block, total, N, out=gathered)
+            done = torch.cuda.Event()
+            done.record(st)
+            comm_stream.wait_event(done)
+            with torch.cuda.stream(comm_stream):
+                sharding.gather_blocks(blocks[f], total, N, out=gathered[f])
 
-    for _ in range(a.warmup):
-        step()
+    def join():
+        """stream 0 waits for everything enqueued on the other streams"""
+        for st in streams[1:] + [comm_stream]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            streams[0].wait_event(ev)
+
+    for i in range(a.warmup):
+        launch(i % F)
+    join()
     torch.cuda.synchronize()
+
+    def timed(n_flight):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(streams[0])
+        for st in streams[1:] + [comm_stream]:
+            st.wait_event(t0)
+        for i in range(a.steps):
+            launch(i % n_flight)
+        join()
+        t1.record(streams[0])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    # ---- (1) one batch in flight: per-launch kernel time (the roofline's denominator) and the serial rate
+    launches0 = sum(sv.kernel_launches() for sv in solvers)
+    k_ms = []
+    serial_ms = 0.0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = solver.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    conv_steps = []
-    e0.record()
     for _ in range(a.steps):
         ek0, ek1, eg = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        ek0.record()
-        solver.plan_batch_device(B, N, batch.M_max, batch.S, batch.S, *dev_in, states, controls, status,
-                                 stream=stream.cuda_stream)
-        ek1.record()
-        if world > 1:
-            sharding.gather_blocks(block, total, N, out=gathered)
-        eg.record()
-        kernel_ms.append((ek0, ek1, eg))
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clk = clocks.stop()
-    launches = solver.kernel_launches() - launches0
+        ek0.record(streams[0])
+        launch(0)
+        ek1.record(streams[0])
+        join()
+        eg.record(streams[0])
+        torch.cuda.synchronize()
+        k_ms.append(ek0.elapsed_time(ek1))
+        serial_ms += ek0.elapsed_time(eg)
     lib_kernel_ms = solver.last_kernel_ms()  # the library's own event pair around its last solve launch
-    elapsed_ms = e0.elapsed_time(e1)
-    k_ms = [x.elapsed_time(y) for x, y, _ in kernel_ms]
-    g_ms = [y.elapsed_time(z) for _, y, z in kernel_ms]
+    # ---- (2) the timed region: K steps, up to F batches in flight
+    clocks = ClockSampler(local)
+    clocks.start()
+    elapsed_ms = timed(F)
+    clk = clocks.stop()
+    launches = sum(sv.kernel_launches() for sv in solvers) - launches0 - a.steps
     conv_local = int((status[:, 0] <= 2).sum().item())  # every step solves the same scenarios
+    for v in views[1:]:
+        assert int((v[2][:, 0] <= 2).sum().item()) == conv_local, "slots disagree on the same scenarios"
     iters_mean = float(status[:, 1].mean().item())
-    t = torch.tensor([elapsed_ms, float(np.mean(k_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, float(np.mean(k_ms)), serial_ms], dtype=torch.float64, device=dev)
     c = torch.tensor([conv_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    elapsed_ms, kmean_ms = float(t[0]), float(t[1])
+    elapsed_ms, kmean_ms, serial_ms = float(t[0]), float(t[1]), float(t[2])
     conv_total = int(c[0])
     value = conv_total * a.steps / (elapsed_ms * 1e-3)
+    value_serial = conv_total * a.steps / (serial_ms * 1e-3)
 
     # ---- e2e through the host C ABI: pinned host inputs -> H2D -> solve -> D2H
     e2e = None
     if not a.no_e2e:
         hb = scenarios.ScenarioBatch(batch.N, batch.M_max, batch.S, *[p.numpy() for p in pinned])
-        out = {"states": torch.empty((B, K, 6), dtype=torch.float64).pin_memory().numpy(),
-               "controls": torch.empty((B, N, 2), dtype=torch.float64).pin_memory().numpy(),
-               "status": torch.empty((B, 8), dtype=torch.float64).pin_memory().numpy()}
-        solver.plan_batch(hb, out=out)  # warm-up (allocates the staging buffers)
+        outs = [{"states": torch.empty((B, K, 6), dtype=torch.float64).pin_memory().numpy(),
+                 "controls": torch.empty((B, N, 2), dtype=torch.float64).pin_memory().numpy(),
+                 "status": torch.empty((B, 8), dtype=torch.float64).pin_memory().numpy()} for _ in range(F)]
+        for f in range(F):
+            solvers[f].plan_batch(hb, out=outs[f])  # warm-up (allocates the staging buffers)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        n_e2e = max(1, min(a.steps, 3))
+        # F host threads, one handle each, every call blocking (ctypes releases the GIL): the H2D stream of one
+        # batch and the drain of another overlap, exactly as two planner threads sharing a GPU would
+        per_thread = 2
+        n_e2e = per_thread * F
+
+        def worker(f):
+            for _ in range(per_thread):
+                solvers[f].plan_batch(hb, out=outs[f])
+
+        threads = [threading.Thread(target=worker, args=(f,)) for f in range(F)]
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            solver.plan_batch(hb, out=out)
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
         dt = time.perf_counter() - t0
-        conv_e = float((out["status"][:, 0] <= 2).sum())
+        conv_e = float((outs[0]["status"][:, 0] <= 2).sum())
+        assert all(float((o["status"][:, 0] <= 2).sum()) == conv_e for o in outs)
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
         ce = torch.tensor([conv_e], dtype=torch.float64, device=dev)
         if world > 1:
@@ -312,8 +366,10 @@ def main():
             dist.all_reduce(ce, op=dist.ReduceOp.SUM)
         e2e = {"value": float(ce[0]) * n_e2e / float(te[0]), "unit": UNIT,
                "h2d_bytes_per_step": int(batch.input_bytes()) * world,
-               "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) * world,
-               "steps": n_e2e, "api": "cilqr_plan_batch (C ABI, host pointers): one solve launch fed by chunked H2D copies through a "
+               "d2h_bytes_per_step": int(sum(v.nbytes for v in outs[0].values())) * world,
+               "steps": n_e2e, "in_flight": F,
+               "api": "cilqr_plan_batch (C ABI, host pointers), one blocking call per step from each of "
+                      f"{F} host threads (one handle each): one solve launch fed by chunked H2D copies through a "
                       "device watermark; results written by the kernel straight into the pinned host buffers"}
 
     if rank == 0:
@@ -336,19 +392,26 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "total_scenarios_per_step": total,
+            "value_one_in_flight": value_serial,
+            "config": {"workload": workload_name(a), "total_scenarios_per_step": total, "in_flight": F,
+                       "pipelining": f"{F} batches in flight in the timed region (one handle + stream each; a step is "
+                                     "still one solve launch over one batch); value_one_in_flight = same K steps, "
+                                     "each waited for before the next is enqueued",
                        "l2_policy": f"inputs ({batch.input_bytes() / 1e9:.2f} GB per GPU) exceed the 126 MB L2; no flush",
                        "converged_fraction": conv_total / total, "mean_iterations": iters_mean,
                        "warps_per_sm": warps, "smem_bytes_per_warp": smem, "scenario_gen_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "cilqr_solve_kernel",
                          "kernel_ms": kmean_ms, "kernel_ms_library_events": lib_kernel_ms,
+                         "kernel_ms_note": "launch duration with one batch in flight (CUDA events on the launching "
+                                           "stream); with F in flight launches overlap and share the SMs",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "fp64 issue/latency bound, not HBM bound: compulsory traffic is inputs once + "
                                  "outputs once; `traffic` (ncu dram bytes per launch) is larger because the "
                                  "scenario contexts live in L2/HBM between solver phases (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches),
-            "kernel_ms_per_step": k_ms, "allgather_ms_per_step": g_ms if world > 1 else None,
+            "kernel_ms_per_step_one_in_flight": k_ms,
+            "allgather_ms_per_step": (serial_ms - sum(k_ms)) / a.steps if world > 1 else None,
         }
         if e2e:
             res["e2e"] = e2e
@@ -360,7 +423,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    solver.close()
+    for sv in solvers:
+        sv.close()
 
 
 if __name__ == "__main__":

@@ -1,5 +1,4 @@
 #!/bin/bash
-# Quick GPU session: parity tests, then the bench line.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-corridor > gpurun_out/bench_pipe.json 2> gpurun_out/bench_pipe.err; tail -5 gpurun_out/bench_pipe.err; cat gpurun_out/bench_pipe.json | cut -c1-1500
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-corridor --no-e2e --in-flight 3 2>&1 | tail -1 | cut -c1-400
