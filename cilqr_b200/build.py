@@ -9,10 +9,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200.so")
-SOURCES = ["cilqr_capi.cu"]
-DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "corridor_kernel.cuh", os.path.join("..", "..", "include", "cilqr_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
+# translation units: (source, extra flags).  dp_capi.cu restates double-precision decision logic of the
+# reference and is compiled without FMA contraction (-fmad=false); the solver TU keeps nvcc's default.
+UNITS = [("cilqr_capi.cu", []), ("dp_capi.cu", ["-fmad=false"])]
+DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "corridor_kernel.cuh", "dp_capi.cu", "dp_kernel.cuh", "cilqr_internal.h",
+        os.path.join("..", "..", "include", "cilqr_b200.h")]
+NVCC_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                "-Xcompiler", "-fPIC"]
+NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "static"]
 
 
 def _nvcc() -> str:
@@ -33,8 +37,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    objs = []
+    for src, extra in UNITS:
+        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_COMPILE + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        subprocess.check_call(cmd, cwd=CSRC)
+        objs.append(obj)
+    subprocess.check_call([_nvcc()] + NVCC_LINK + ["-o", LIB_PATH] + objs, cwd=CSRC)
     return LIB_PATH
 
 

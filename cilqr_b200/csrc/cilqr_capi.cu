@@ -6,6 +6,7 @@
 // CILQR_E_NO_DEVICE / CILQR_E_CUDA.
 #include "cilqr_kernel.cuh"
 #include "corridor_kernel.cuh"
+#include "cilqr_internal.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -72,6 +73,10 @@ struct cilqr_handle {
   cudaEvent_t corr_ev0 = nullptr, corr_ev1 = nullptr;
   bool corr_timed = false;
   int64_t corr_launches = 0;
+  // scratch / events of the other translation units (cilqr_internal.h)
+  char* aux_buf[2] = {nullptr, nullptr};
+  size_t aux_bytes[2] = {0, 0};
+  cudaEvent_t aux_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 namespace {
@@ -435,6 +440,11 @@ void cilqr_destroy(cilqr_handle* h) {
     if (s->ready_host) cudaFreeHost(s->ready_host);
     if (s->stream) cudaStreamDestroy(s->stream);
   }
+  for (int i = 0; i < 2; ++i) {
+    if (h->aux_buf[i]) cudaFree(h->aux_buf[i]);
+    for (int j = 0; j < 2; ++j)
+      if (h->aux_ev[i][j]) cudaEventDestroy(h->aux_ev[i][j]);
+  }
   if (h->corr_buf) cudaFree(h->corr_buf);
   if (h->corr_ev0) cudaEventDestroy(h->corr_ev0);
   if (h->corr_ev1) cudaEventDestroy(h->corr_ev1);
@@ -793,6 +803,11 @@ int cilqr_corridor_batch_device(cilqr_handle* h, const CilqrCorridorConfig* cfg,
 
 static int corr_ensure(cilqr_handle* h, size_t bytes) {
   if (h->corr_bytes >= bytes) return CILQR_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->aux_buf[i]) cudaFree(h->aux_buf[i]);
+    for (int j = 0; j < 2; ++j)
+      if (h->aux_ev[i][j]) cudaEventDestroy(h->aux_ev[i][j]);
+  }
   if (h->corr_buf) cudaFree(h->corr_buf);
   h->corr_buf = nullptr;
   h->corr_bytes = 0;
@@ -899,5 +914,30 @@ int cilqr_corridor_last_kernel_ms(cilqr_handle* h, float* ms) {
   return CILQR_OK;
 }
 
+// ---- cilqr_internal.h -------------------------------------------------------------------------------
+int cilqr_internal_device(const cilqr_handle* h) { return h->device; }
+cudaStream_t cilqr_internal_stream(cilqr_handle* h) { return h->slots[0].stream; }
+int cilqr_internal_num_sms(const cilqr_handle* h) { return h->num_sms; }
+int cilqr_internal_fail(cilqr_handle* h, cudaError_t e, const char* where) { return fail_cuda(h, e, where); }
+int cilqr_internal_scratch(cilqr_handle* h, int slot, size_t bytes, char** out) {
+  if (h->aux_bytes[slot] < bytes) {
+    if (h->aux_buf[slot]) cudaFree(h->aux_buf[slot]);
+    h->aux_buf[slot] = nullptr;
+    h->aux_bytes[slot] = 0;
+    CK(cudaMalloc(&h->aux_buf[slot], bytes));
+    h->aux_bytes[slot] = bytes;
+  }
+  *out = h->aux_buf[slot];
+  return CILQR_OK;
+}
+int cilqr_internal_events(cilqr_handle* h, int slot, cudaEvent_t* e0, cudaEvent_t* e1) {
+  for (int j = 0; j < 2; ++j)
+    if (!h->aux_ev[slot][j]) CK(cudaEventCreate(&h->aux_ev[slot][j]));
+  *e0 = h->aux_ev[slot][0];
+  *e1 = h->aux_ev[slot][1];
+  return CILQR_OK;
+}
+
 }  // extern "C"
+
 

@@ -1,0 +1,634 @@
+// dp_kernel.cuh -- batched coarse DP planner for sm_100a.
+//
+// Replaces DpPlanner::Plan of mpt0816/Cilqr (algorithm/planner/dp_planner.cpp:135-281) for B scenarios:
+// the 5 x 7 x 10 lattice search with GetCost (:87-133), GetCollisionCost (:40-85), InterpolateLinearly
+// (:283-320), GetLateralOffset (dp_planner.h:83-92), the reference-line queries of DiscretizedTrajectory
+// (utils/discretized_trajectory.cpp: EvaluateStation :110-121, GetCartesian :192-196, GetProjection :156-190,
+// slerp math_utils.h:208-225), the collision checks of Environment (utils/environment.cpp:51-141 with
+// Polygon2d::HasOverlap(Box2d) / IsPointIn, math/polygon2d.cpp:120-165) and ComputePathProfile
+// (utils/discrete_points_math.cc:27-176).
+//
+// Mapping: ONE CTA = ONE SCENARIO.  A layer of the lattice is 70 x 70 independent (parent, child)
+// transitions, each a walk of 16-17 path points with an early exit at the first collision; the threads of the
+// CTA take transitions round-robin and write their cost into a shared 70 x 70 table, then 70 threads pick
+// every child's best parent in the reference's (s, l) parent order with its strict '<' (first minimum wins).
+// The lattice (350 cells) and the table live in shared memory; the environment (centre line, road barrier:
+// shared by the batch, L2 resident; the scenario's obstacle polygons) is read from global memory.
+//
+// This translation unit is compiled with -fmad=false: every double expression is evaluated with the
+// reference's operation order and roundings.  cos/sin/atan/fmod/hypot are CUDA's (last-ulp differences from
+// glibc on rare arguments).
+#pragma once
+
+#ifndef DP_HOST_EMUL  // tools/dp_host_emul.cc runs this code on the CPU (development aid)
+#include <cuda_runtime.h>
+#endif
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace dp {
+
+constexpr int NT = 5, NS = 7, NL = 10, NP = NS * NL;  // dp_planner.h:27-29
+constexpr double kMathEps = 1e-10;                    // math::kMathEpsilon
+constexpr double kDpEps = 1e-3;                       // the file-local kMathEpsilon of dp_planner.cpp:29
+constexpr double kPi = 3.14159265358979323846;
+
+struct Lattice {  // DpPlanner::DpPlanner, dp_planner.cpp:31-38, computed on the host with the same expressions
+  double unit_time, time_[NT], station_[NS], lateral_[NL - 1], safe_margin;
+  double radius, f2x, r2x;  // VehicleParam(), vehicle_param.h:80-85
+  int nseg[NT];             // InterpolateLinearly's segment count per layer, :287-298
+  int K;
+};
+
+// DpPlanner::DpPlanner (dp_planner.cpp:31-38), math::LinSpaced (math_utils.h:244-254), VehicleParam()
+// (vehicle_param.h:80-85) and the segment counts of InterpolateLinearly (dp_planner.cpp:287-298); host side
+inline void make_lattice(double tf, double delta_t, double max_velocity, double width, double wheel_base,
+                         double front_hang_length, double rear_hang_length, Lattice* L) {
+  L->unit_time = tf / NT;
+  {
+    const double step = (tf - L->unit_time) / (NT - 1);
+    for (int i = 0; i < NT; ++i) L->time_[i] = L->unit_time + step * i;
+  }
+  {
+    const double step = (L->unit_time * max_velocity - 0) / (NS - 1);
+    for (int i = 0; i < NS; ++i) L->station_[i] = 0 + step * i;
+  }
+  {
+    const double step = (1.0 - 0) / (NL - 1 - 1);
+    for (int i = 0; i < NL - 1; ++i) L->lateral_[i] = 0 + step * i;
+  }
+  L->safe_margin = width / 2 * 1.5;
+  const double length = wheel_base + rear_hang_length + front_hang_length;
+  L->radius = hypot(0.25 * length, 0.5 * width);
+  L->r2x = 0.25 * length - rear_hang_length;
+  L->f2x = 0.75 * length - rear_hang_length;
+  L->K = 0;
+  for (int k = 0; k < NT; ++k) {
+    int nseg = 0;
+    for (double t = 0.0; t < tf + delta_t - kMathEps; t += delta_t) {
+      if (k == 0) {
+        if (t > 0.0 - kDpEps && t < L->unit_time + kDpEps) ++nseg;
+      } else {
+        if (t > L->time_[k] - L->unit_time + kMathEps && t < L->time_[k] + kMathEps) ++nseg;
+      }
+    }
+    L->nseg[k] = nseg;
+    L->K += nseg;
+  }
+}
+
+struct Args {
+  int B, R, NB, V, n_static, n_dyn, T;
+  double tf, delta_t, nominal_velocity, w_obstacle, w_lateral, w_lateral_change, w_lateral_velocity_change,
+      w_longitudinal_velocity_bias, w_longitudinal_velocity_change, wheel_base;
+  double ref_s0, ref_inv_ds;  // first station and 1 / mean spacing: a guess for the station search
+  Lattice lat;
+  const double* ref;      // [R][7]
+  const double* barrier;  // [NB][2]
+  const double* start;    // [B][3]
+  const double* static_poly;
+  const int* static_nv;
+  const double* dyn_time;
+  const int* dyn_samples;
+  const double* dyn_poly;
+  const int* dyn_nv;
+  double* trajectory;  // [B][K][13] or nullptr
+  double* coarse;      // [B][K][6] or nullptr
+  double* xytheta;     // [B][K][3] or nullptr
+  int* ok;
+  double* cost;
+  double* waypoints;
+};
+
+struct Cell {
+  double cost, current_s;
+  int ps, pl;
+};
+
+struct RefPoint {
+  double s, x, y, theta, kappa, lb, rb;
+};
+
+// math_utils.cpp:53-59
+__device__ __forceinline__ double normalize_angle(double angle) {
+  double a = fmod(angle + kPi, 2.0 * kPi);
+  if (a < 0.0) a += 2.0 * kPi;
+  return a - kPi;
+}
+
+// math_utils.h:208-225
+__device__ __forceinline__ double slerp(double a0, double t0, double a1, double t1, double t) {
+  if (fabs(t1 - t0) <= kMathEps) return normalize_angle(a0);
+  const double a0_n = normalize_angle(a0);
+  const double a1_n = normalize_angle(a1);
+  double d = a1_n - a0_n;
+  if (d > kPi) {
+    d = d - 2 * kPi;
+  } else if (d < -kPi) {
+    d = d + 2 * kPi;
+  }
+  const double r = (t - t0) / (t1 - t0);
+  const double a = a0_n + d * r;
+  return normalize_angle(a);
+}
+
+// LinearInterpolateTrajectory, discretized_trajectory.cpp:62-84
+__device__ __forceinline__ RefPoint interpolate(const double* p0, const double* p1, double s) {
+  RefPoint o;
+  const double s0 = p0[0], s1 = p1[0];
+  if (fabs(s1 - s0) < kMathEps) {
+    o.s = p0[0]; o.x = p0[1]; o.y = p0[2]; o.theta = p0[3]; o.kappa = p0[4]; o.lb = p0[5]; o.rb = p0[6];
+    return o;
+  }
+  const double weight = (s - s0) / (s1 - s0);
+  o.s = s;
+  o.x = (1 - weight) * p0[1] + weight * p1[1];
+  o.y = (1 - weight) * p0[2] + weight * p1[2];
+  o.theta = slerp(p0[3], p0[0], p1[3], p1[0], s);
+  o.kappa = (1 - weight) * p0[4] + weight * p1[4];
+  o.lb = (1 - weight) * p0[5] + weight * p1[5];
+  o.rb = (1 - weight) * p0[6] + weight * p1[6];
+  return o;
+}
+
+// EvaluateStation, :110-121 with QueryLowerBoundStationPoint :34-46.  std::lower_bound's answer (the first
+// index whose s is not less than the station) is unique for the sorted line, so it is found from a guess
+// (uniform spacing) corrected by stepping -- the same index in 2-3 loads instead of 12.
+__device__ __forceinline__ RefPoint evaluate_station(const Args& a, double station) {
+  const double* ref = a.ref;
+  const int R = a.R;
+  int it;
+  if (station >= ref[(size_t)(R - 1) * 7]) {
+    it = R - 1;
+  } else if (station < ref[0]) {
+    it = 0;
+  } else {
+    double g = (station - a.ref_s0) * a.ref_inv_ds;
+    it = g < 0.0 ? 0 : (g > (double)(R - 1) ? R - 1 : (int)g);
+    while (it > 0 && !(ref[(size_t)(it - 1) * 7] < station)) --it;
+    while (it < R && ref[(size_t)it * 7] < station) ++it;
+  }
+  if (it == 0) it = 1;
+  return interpolate(ref + (size_t)(it - 1) * 7, ref + (size_t)it * 7, station);
+}
+
+// Polygon2d::IsPointIn, polygon2d.cpp:120-140
+__device__ __forceinline__ bool polygon_is_point_in(const double* p, int nv, double minx, double maxx, double miny,
+                                                    double maxy, double x, double y) {
+  if (x < minx || x > maxx || y < miny || y > maxy) return false;
+  int j = nv - 1, c = 0;
+  for (int i = 0; i < nv; ++i) {
+    const double xi = p[2 * i], yi = p[2 * i + 1], xj = p[2 * j], yj = p[2 * j + 1];
+    if ((yi > y) != (yj > y)) {
+      const double side = (xi - x) * (yj - y) - (yi - y) * (xj - x);
+      if (yi < yj ? side > 0.0 : side < 0.0) ++c;
+    }
+    j = i;
+  }
+  return c & 1;
+}
+
+// Box2d::IsPointIn for Box2d(AABox2d): cos = 1, sin = 0 (box2d.cpp:93-105,123-129)
+__device__ __forceinline__ bool box_is_point_in(double px, double py, double cx, double cy, double half) {
+  const double x0 = px - cx, y0 = py - cy;
+  const double dx = fabs(x0 * 1.0 + y0 * 0.0), dy = fabs(-x0 * 0.0 + y0 * 1.0);
+  return dx <= half + kMathEps && dy <= half + kMathEps;
+}
+
+// Polygon2d::HasOverlap(const Box2d&), polygon2d.cpp:150-165
+__device__ bool polygon_overlaps_box(const double* p, int nv, double cx, double cy, double half) {
+  double minx = p[0], maxx = p[0], miny = p[1], maxy = p[1];
+  for (int i = 1; i < nv; ++i) {
+    minx = fmin(minx, p[2 * i]);
+    maxx = fmax(maxx, p[2 * i]);
+    miny = fmin(miny, p[2 * i + 1]);
+    maxy = fmax(maxy, p[2 * i + 1]);
+  }
+  const double bminx = cx - half, bmaxx = cx + half, bminy = cy - half, bmaxy = cy + half;
+  if (bmaxx < minx || bminx > maxx || bmaxy < miny || bminy > maxy) return false;
+  for (int i = 0; i < nv; ++i)
+    if (box_is_point_in(p[2 * i], p[2 * i + 1], cx, cy, half)) return true;
+  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx + half, cy - half)) return true;  // aabox2d.cpp:63-71
+  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx + half, cy + half)) return true;
+  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx - half, cy + half)) return true;
+  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx - half, cy - half)) return true;
+  return false;
+}
+
+// std::upper_bound over the barrier's x: first index with x > val
+__device__ __forceinline__ int barrier_upper_bound(const double* bar, int NB, double val) {
+  int lo = 0, hi = NB;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    if (val < bar[(size_t)mid * 2]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Environment::CheckStaticCollision, environment.cpp:51-87
+__device__ bool check_static(const Args& a, int b, double cx, double cy, double half) {
+  const double* polys = a.static_poly + (size_t)b * a.n_static * a.V * 2;
+  const int* nv = a.static_nv + (size_t)b * a.n_static;
+  for (int o = 0; o < a.n_static; ++o)
+    if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], cx, cy, half)) return true;
+  if (a.NB == 0) return false;
+  const double minx = cx - half, maxx = cx + half;
+  if (maxx < a.barrier[0] || minx > a.barrier[(size_t)(a.NB - 1) * 2]) return false;
+  int check_start = barrier_upper_bound(a.barrier, a.NB, minx);
+  const int check_end = barrier_upper_bound(a.barrier, a.NB, maxx);
+  if (check_start > 0) --check_start;
+  for (int i = check_start; i < check_end; ++i)
+    if (box_is_point_in(a.barrier[(size_t)i * 2], a.barrier[(size_t)i * 2 + 1], cx, cy, half)) return true;
+  return false;
+}
+
+// Environment::CheckDynamicCollision, environment.cpp:124-141 (query time == last sample time: the reference
+// dereferences end(); the last sample is used)
+__device__ bool check_dynamic(const Args& a, int b, double time, double cx, double cy, double half) {
+  for (int o = 0; o < a.n_dyn; ++o) {
+    const size_t ob = (size_t)b * a.n_dyn + o;
+    const int ns = a.dyn_samples[ob];
+    if (ns <= 0) continue;
+    const double* tt = a.dyn_time + ob * a.T;
+    if (tt[0] > time || tt[ns - 1] < time) continue;
+    int lo = 0, hi = ns;
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (time < tt[mid]) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= ns) lo = ns - 1;
+    if (polygon_overlaps_box(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], cx, cy, half)) return true;
+  }
+  return false;
+}
+
+// Environment::CheckOptimizationCollision, environment.cpp:99-122; GetDiscPositions, vehicle_param.h:88-95
+__device__ bool check_optimization_collision(const Args& a, int b, double time, double x, double y, double theta) {
+  const double radius = a.lat.radius;
+  const double half = (radius + 0.0 - (-radius - 0.0)) / 2.0;
+  const double ct = cos(theta), st = sin(theta);
+  const double xf = x + a.lat.f2x * ct, xr = x + a.lat.r2x * ct;
+  const double yf = y + a.lat.f2x * st, yr = y + a.lat.r2x * st;
+  const double c0 = (-radius - 0.0 + (radius + 0.0)) / 2.0;
+  const double fx = c0 + xf, fy = c0 + yf, rx = c0 + xr, ry = c0 + yr;
+  return check_static(a, b, fx, fy, half) || check_static(a, b, rx, ry, half) ||
+         check_dynamic(a, b, time, fx, fy, half) || check_dynamic(a, b, time, rx, ry, half);
+}
+
+struct Start {
+  double s, l;
+};
+
+// GetLateralOffset, dp_planner.h:83-92
+__device__ __forceinline__ double lateral_offset(const Args& a, double s, int l_ind) {
+  if (l_ind == NL - 1) return 0.0;
+  const RefPoint r = evaluate_station(a, s);
+  const double lb = -r.rb + a.lat.safe_margin;
+  const double ub = r.lb - a.lat.safe_margin;
+  return lb + (ub - lb) * a.lat.lateral_[l_ind];
+}
+
+// InterpolateLinearly, dp_planner.cpp:283-320, as the segment's generator: point i = (s0 + i ds, l0 + i dl)
+struct Segment {
+  double p_s, p_l, s_step, l_step;
+  int nseg;
+};
+__device__ __forceinline__ Segment make_segment(const Args& a, const Start& st, double parent_s, int parent_l_ind,
+                                                int cur_t_ind, int cur_s_ind, int cur_l_ind) {
+  Segment g;
+  g.nseg = a.lat.nseg[cur_t_ind];
+  g.p_l = st.l;
+  g.p_s = st.s;
+  if (parent_l_ind >= 0) {
+    g.p_s = parent_s;
+    g.p_l = lateral_offset(a, g.p_s, parent_l_ind);
+  }
+  const double cur_s = g.p_s + a.lat.station_[cur_s_ind];
+  const double cur_l = lateral_offset(a, cur_s, cur_l_ind);
+  g.s_step = a.lat.station_[cur_s_ind] / g.nseg;
+  g.l_step = (cur_l - g.p_l) / g.nseg;
+  return g;
+}
+
+// GetCollisionCost, dp_planner.cpp:40-85; pt < 0: the parent is the start state
+__device__ double collision_cost(const Args& a, int b, const Start& st, const Cell* cells, int pt, int psi, int pli,
+                                 int ct, int csi, int cli) {
+  double parent_s = st.s, grandparent_s = st.s;
+  double last_l = st.l, last_s = st.s;
+  if (pt >= 0) {
+    const Cell cell = cells[pt * NP + psi * NL + pli];
+    parent_s = cell.current_s;
+    if (pt > 0) grandparent_s = cells[(pt - 1) * NP + cell.ps * NL + cell.pl].current_s;
+    const Segment prev = make_segment(a, st, grandparent_s, cell.pl, pt, psi, pli);
+    last_l = prev.p_l + (prev.nseg - 1) * prev.l_step;
+    last_s = prev.p_s + (prev.nseg - 1) * prev.s_step;
+  }
+  const Segment g = make_segment(a, st, parent_s, pli, ct, csi, cli);
+  const double parent_time = pt < 0 ? 0.0 : a.lat.time_[pt];
+  for (int i = 0; i < g.nseg; ++i) {
+    const double ps = g.p_s + i * g.s_step, pl = g.p_l + i * g.l_step;
+    const double dl = pl - last_l;
+    const double ds = fmax(ps - last_s, kDpEps);
+    last_l = pl;
+    last_s = ps;
+    const RefPoint r = evaluate_station(a, ps);  // GetCartesian (:192-196) evaluates the same station
+    const double cx = r.x - pl * sin(r.theta);
+    const double cy = r.y + pl * cos(r.theta);
+    const double lb = fmin(0.0, -r.rb + a.lat.safe_margin);
+    const double ub = fmax(0.0, r.lb - a.lat.safe_margin);
+    if (pl < lb - kDpEps || pl > ub + kDpEps) return a.w_obstacle;
+    const double heading = r.theta + atan((dl / ds) / (1 - r.kappa * pl));
+    const double time = parent_time + i * (a.lat.unit_time / g.nseg);
+    if (check_optimization_collision(a, b, time, cx, cy, heading)) return a.w_obstacle;
+  }
+  return 0.0;
+}
+
+// GetCost, dp_planner.cpp:87-133
+__device__ double get_cost(const Args& a, int b, const Start& st, const Cell* cells, int pt, int psi, int pli, int ct,
+                           int csi, int cli, double* cur_s_out) {
+  double parent_s = st.s, grandparent_s = st.s;
+  double parent_l = st.l, grandparent_l = st.l;
+  if (pt >= 0) {
+    const Cell cell = cells[pt * NP + psi * NL + pli];
+    parent_s = cell.current_s;
+    parent_l = lateral_offset(a, parent_s, pli);
+    if (pt >= 1) {
+      grandparent_s = cells[(pt - 1) * NP + cell.ps * NL + cell.pl].current_s;
+      grandparent_l = lateral_offset(a, grandparent_s, cell.pl);
+    }
+  }
+  const double cur_s = parent_s + a.lat.station_[csi];
+  const double cur_l = lateral_offset(a, cur_s, cli);
+  const double ds1 = cur_s - parent_s;
+  const double dl1 = cur_l - parent_l;
+  const double ds0 = parent_s - grandparent_s;
+  const double dl0 = parent_l - grandparent_l;
+  *cur_s_out = cur_s;
+  const double cost_obstacle = collision_cost(a, b, st, cells, pt, psi, pli, ct, csi, cli);
+  if (cost_obstacle >= a.w_obstacle) return a.w_obstacle;
+  const double cost_lateral = fabs(cur_l);
+  const double cost_lateral_change = fabs(parent_l - cur_l) / (a.lat.station_[csi] + kDpEps);
+  const double cost_lateral_change_t = fabs(dl1 - dl0) / a.lat.unit_time;
+  const double cost_longitudinal_velocity = fabs(ds1 / a.lat.unit_time - a.nominal_velocity);
+  const double cost_longitudinal_velocity_change = fabs((ds1 - ds0) / a.lat.unit_time);
+  return a.w_lateral * cost_lateral + a.w_lateral_change * cost_lateral_change +
+         a.w_lateral_velocity_change * cost_lateral_change_t +
+         a.w_longitudinal_velocity_bias * cost_longitudinal_velocity +
+         a.w_longitudinal_velocity_change * cost_longitudinal_velocity_change;
+}
+
+constexpr int kMaxThreads = 256;
+constexpr int kMaxKnots = 512;
+
+// shared-memory layout (bytes); K <= kMaxKnots
+__host__ __device__ inline size_t smem_bytes(int K) {
+  return sizeof(Cell) * NT * NP + sizeof(double) * NP * NP + sizeof(double) * kMaxThreads + sizeof(int) * kMaxThreads +
+         sizeof(double) * 8 + sizeof(int) * 3 * NT + sizeof(double) * 10 * (size_t)K + 64;
+}
+
+__global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
+  extern __shared__ __align__(16) unsigned char dp_smem[];
+  Cell* cells = reinterpret_cast<Cell*>(dp_smem);                        // [NT][NP]
+  double* delta = reinterpret_cast<double*>(cells + NT * NP);             // [NP parents][NP children]
+  double* red_d = delta + NP * NP;                                        // [threads]
+  double* misc = red_d + kMaxThreads;                                     // start_s, start_l, min_cost
+  int* red_i = reinterpret_cast<int*>(misc + 8);                          // [threads]
+  int* wp = red_i + kMaxThreads;                                          // [NT][3]: s index, l index, parent l index
+  double* kn = reinterpret_cast<double*>(wp + 3 * NT + 1);                // 10 arrays of K doubles
+  kn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(kn) + 15) & ~(uintptr_t)15);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int K = a.lat.K;
+  double *xs = kn, *ys = kn + K, *acc_s = kn + 2 * K, *speeds = kn + 3 * K, *accel = kn + 4 * K, *xds = kn + 5 * K,
+         *yds = kn + 6 * K, *xdds = kn + 7 * K, *ydds = kn + 8 * K, *th = kn + 9 * K;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __syncthreads();
+    const double sx = a.start[(size_t)b * 3], sy = a.start[(size_t)b * 3 + 1];
+    // ---- GetProjection, discretized_trajectory.cpp:156-190; QueryNearestPoint (:136-154): first minimum
+    {
+      double best = DBL_MAX;
+      int bi = 0x7fffffff;
+      for (int i = tid; i < a.R; i += nt) {
+        const double dx = a.ref[(size_t)i * 7 + 1] - sx, dy = a.ref[(size_t)i * 7 + 2] - sy;
+        const double d = dx * dx + dy * dy;
+        if (d < best) {
+          best = d;
+          bi = i;
+        }
+      }
+      red_d[tid] = best;
+      red_i[tid] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double best = DBL_MAX;
+      int idx = 0;
+      bool any = false;
+      for (int t = 0; t < nt; ++t) {
+        if (red_i[t] == 0x7fffffff) continue;
+        if (!any || red_d[t] < best || (red_d[t] == best && red_i[t] < idx)) {
+          best = red_d[t];
+          idx = red_i[t];
+          any = true;
+        }
+      }
+      const double* pr = a.ref + (size_t)idx * 7;
+      RefPoint pp;
+      pp.s = pr[0]; pp.x = pr[1]; pp.y = pr[2]; pp.theta = pr[3]; pp.kappa = pr[4]; pp.lb = pr[5]; pp.rb = pr[6];
+      const int index_start = idx - 1 > 0 ? idx - 1 : 0;
+      const int index_end = idx + 1 < a.R - 1 ? idx + 1 : a.R - 1;
+      if (index_start < index_end) {
+        const double* p0 = a.ref + (size_t)index_start * 7;
+        const double* p1 = a.ref + (size_t)index_end * 7;
+        const double v0x = sx - p0[1], v0y = sy - p0[2];
+        const double v1x = p1[1] - p0[1], v1y = p1[2] - p0[2];
+        const double v1_norm = sqrt(v1x * v1x + v1y * v1y);
+        const double dot = v0x * v1x + v0y * v1y;
+        const double delta_s = dot / v1_norm;
+        pp = interpolate(p0, p1, p0[0] + delta_s);
+      }
+      const double nr_x = sx - pp.x, nr_y = sy - pp.y;
+      misc[0] = pp.s;
+      misc[1] = copysign(hypot(nr_x, nr_y), nr_y * cos(pp.theta) - nr_x * sin(pp.theta));
+    }
+    __syncthreads();
+    Start st;
+    st.s = misc[0];
+    st.l = misc[1];
+
+    // ---- first layer, dp_planner.cpp:151-158
+    for (int p = tid; p < NP; p += nt) {
+      double cur_s;
+      const double c = get_cost(a, b, st, cells, -1, -1, -1, 0, p / NL, p % NL, &cur_s);
+      Cell cell;
+      cell.cost = c;
+      cell.current_s = cur_s;
+      cell.ps = -1;
+      cell.pl = -1;
+      cells[p] = cell;
+    }
+    __syncthreads();
+    // ---- dynamic programming, :160-181
+    for (int i = 0; i < NT - 1; ++i) {
+      for (int q = tid; q < NP * NP; q += nt) {
+        const int parent = q / NP, child = q - parent * NP;
+        double cur_s;
+        delta[q] = get_cost(a, b, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);
+      }
+      __syncthreads();
+      for (int child = tid; child < NP; child += nt) {
+        Cell best;
+        best.cost = DBL_MAX;
+        best.current_s = DBL_MIN;
+        best.ps = -1;
+        best.pl = -1;
+        for (int parent = 0; parent < NP; ++parent) {  // (j, k) order; strict '<': the first minimum wins
+          const double cur_cost = cells[i * NP + parent].cost + delta[parent * NP + child];
+          if (cur_cost < best.cost) {
+            best.cost = cur_cost;
+            best.current_s = cells[i * NP + parent].current_s + a.lat.station_[child / NL];
+            best.ps = parent / NL;
+            best.pl = parent % NL;
+          }
+        }
+        cells[(i + 1) * NP + child] = best;
+      }
+      __syncthreads();
+    }
+    // ---- least cost in the final layer (:183-194) and trace back (:196-204)
+    if (tid == 0) {
+      double min_cost = DBL_MAX;
+      int ms = 0, ml = 0;
+      for (int p = 0; p < NP; ++p) {
+        const double c = cells[(NT - 1) * NP + p].cost;
+        if (c < min_cost) {
+          ms = p / NL;
+          ml = p % NL;
+          min_cost = c;
+        }
+      }
+      misc[2] = min_cost;
+      for (int i = NT - 1; i >= 0; --i) {
+        const Cell c = cells[i * NP + ms * NL + ml];
+        wp[3 * i] = ms;
+        wp[3 * i + 1] = ml;
+        wp[3 * i + 2] = c.pl;
+        ms = c.ps;
+        ml = c.pl;
+      }
+      a.ok[b] = min_cost < a.w_obstacle ? 1 : 0;
+      if (a.cost) a.cost[b] = min_cost;
+      if (a.waypoints)
+        for (int i = 0; i < NT; ++i) {
+          a.waypoints[((size_t)b * NT + i) * 3] = wp[3 * i];
+          a.waypoints[((size_t)b * NT + i) * 3 + 1] = wp[3 * i + 1];
+          a.waypoints[((size_t)b * NT + i) * 3 + 2] = cells[i * NP + wp[3 * i] * NL + wp[3 * i + 1]].current_s;
+        }
+    }
+    __syncthreads();
+    // ---- interpolation of the optimum, :212-243: knot n = point j of layer i; (dl, ds) against the previous point
+    for (int n = tid; n < K; n += nt) {
+      int i = 0, j = n;
+      while (j >= a.lat.nseg[i]) {
+        j -= a.lat.nseg[i];
+        ++i;
+      }
+      const double parent_s = i > 0 ? cells[(i - 1) * NP + wp[3 * (i - 1)] * NL + wp[3 * (i - 1) + 1]].current_s : st.s;
+      const Segment g = make_segment(a, st, parent_s, wp[3 * i + 2], i, wp[3 * i], wp[3 * i + 1]);
+      const double ps = g.p_s + j * g.s_step, pl = g.p_l + j * g.l_step;
+      double last_s, last_l;
+      if (j > 0) {
+        last_s = g.p_s + (j - 1) * g.s_step;
+        last_l = g.p_l + (j - 1) * g.l_step;
+      } else if (i > 0) {
+        const double gp_s =
+            i > 1 ? cells[(i - 2) * NP + wp[3 * (i - 2)] * NL + wp[3 * (i - 2) + 1]].current_s : st.s;
+        const Segment pg = make_segment(a, st, gp_s, wp[3 * (i - 1) + 2], i - 1, wp[3 * (i - 1)], wp[3 * (i - 1) + 1]);
+        last_s = pg.p_s + (pg.nseg - 1) * pg.s_step;
+        last_l = pg.p_l + (pg.nseg - 1) * pg.l_step;
+      } else {
+        last_s = st.s;
+        last_l = st.l;
+      }
+      const double dl = pl - last_l;
+      const double ds = fmax(ps - last_s, kDpEps);
+      const RefPoint r = evaluate_station(a, ps);
+      xs[n] = r.x - pl * sin(r.theta);
+      ys[n] = r.y + pl * cos(r.theta);
+      th[n] = r.theta + atan((dl / ds) / (1 - r.kappa * pl));
+      if (a.trajectory) a.trajectory[((size_t)b * K + n) * 13 + 1] = ps;
+    }
+    __syncthreads();
+    // ---- ComputePathProfile, discrete_points_math.cc:27-176 (the running sum is serial in the reference)
+    if (tid == 0) {
+      double distance = 0.0, fx = xs[0], fy = ys[0];
+      acc_s[0] = distance;
+      for (int i = 1; i < K; ++i) {
+        const double nx = xs[i], ny = ys[i];
+        const double end_segment_s = sqrt((fx - nx) * (fx - nx) + (fy - ny) * (fy - ny));
+        acc_s[i] = end_segment_s + distance;
+        distance += end_segment_s;
+        fx = nx;
+        fy = ny;
+      }
+    }
+    __syncthreads();
+    for (int i = tid + 1; i < K; i += nt) speeds[i - 1] = (acc_s[i] - acc_s[i - 1]) / a.delta_t;
+    __syncthreads();
+    if (tid == 0) speeds[K - 1] = speeds[K - 2];
+    __syncthreads();
+    for (int i = tid + 1; i < K; i += nt) accel[i - 1] = (speeds[i] - speeds[i - 1]) / a.delta_t;
+    for (int i = tid; i < K; i += nt) {
+      const int lo = i == 0 ? 0 : i - 1, hi = i == K - 1 ? K - 1 : i + 1;
+      xds[i] = (xs[hi] - xs[lo]) / (acc_s[hi] - acc_s[lo]);
+      yds[i] = (ys[hi] - ys[lo]) / (acc_s[hi] - acc_s[lo]);
+    }
+    __syncthreads();
+    if (tid == 0) accel[K - 1] = accel[K - 2];
+    for (int i = tid; i < K; i += nt) {
+      const int lo = i == 0 ? 0 : i - 1, hi = i == K - 1 ? K - 1 : i + 1;
+      xdds[i] = (xds[hi] - xds[lo]) / (acc_s[hi] - acc_s[lo]);
+      ydds[i] = (yds[hi] - yds[lo]) / (acc_s[hi] - acc_s[lo]);
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += nt) {
+      const double kappa = (xds[i] * ydds[i] - yds[i] * xdds[i]) /
+                           (sqrt(xds[i] * xds[i] + yds[i] * yds[i]) * (xds[i] * xds[i] + yds[i] * yds[i]) + 1e-6);
+      const double delta_w = atan(kappa * a.wheel_base);  // :270
+      if (a.trajectory) {
+        double* d = a.trajectory + ((size_t)b * K + i) * 13;
+        d[0] = a.delta_t * i;
+        d[2] = xs[i];
+        d[3] = ys[i];
+        d[4] = th[i];
+        d[5] = kappa;
+        d[6] = speeds[i];
+        d[7] = accel[i];
+        d[8] = 0.0;
+        d[9] = delta_w;
+        d[10] = 0.0;
+        d[11] = 0.0;
+        d[12] = 0.0;
+      }
+      if (a.coarse) {
+        double* d = a.coarse + ((size_t)b * K + i) * 6;
+        d[0] = xs[i];
+        d[1] = ys[i];
+        d[2] = th[i];
+        d[3] = speeds[i];
+        d[4] = accel[i];
+        d[5] = delta_w;
+      }
+      if (a.xytheta) {
+        double* d = a.xytheta + ((size_t)b * K + i) * 3;
+        d[0] = xs[i];
+        d[1] = ys[i];
+        d[2] = th[i];
+      }
+    }
+  }
+}
+
+}  // namespace dp

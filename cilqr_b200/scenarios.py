@@ -469,6 +469,83 @@ def generate_with_obstacles(seed: int, first_id: int, count: int, N: int = 100, 
     return batch, CorridorInputs(traj, np.ascontiguousarray(pts), cnt)
 
 
+@dataclass
+class DpBatch:
+    """Inputs of DpPlanner::Plan for a batch (include/cilqr_b200.h, CilqrDpIn).  The centre line and the road
+    barrier are shared by the batch (one road), obstacles and the start state are per scenario."""
+
+    ref: np.ndarray          # [R,7] s, x, y, theta, kappa, left_bound, right_bound
+    start: np.ndarray        # [B,3] x, y, theta
+    static_poly: np.ndarray  # [B,n_static,4,2]
+    static_nv: np.ndarray    # [B,n_static] int32
+    dyn_time: np.ndarray     # [B,n_dyn,T]
+    dyn_samples: np.ndarray  # [B,n_dyn] int32
+    dyn_poly: np.ndarray     # [B,n_dyn,T,4,2]
+    dyn_nv: np.ndarray       # [B,n_dyn] int32
+
+    @property
+    def B(self) -> int:
+        return self.start.shape[0]
+
+
+def reference_line(road_name: str = "gentle", step: float = 0.1) -> np.ndarray:
+    """The centre line as the reference publishes it (script/reference_publisher.py:200-226: station, pose,
+    curvature and the two bounds every 0.1 m) -> [R,7]."""
+    rd = road(road_name)
+    s = np.arange(0.0, rd.s_max + 1e-9, step)
+    x, y, th, kap = rd.eval(s)
+    return np.ascontiguousarray(np.stack([s, x, y, th, kap, np.full_like(s, _LEFT_BOUND), np.full_like(s, _RIGHT_BOUND)],
+                                         axis=1))
+
+
+def generate_dp(seed: int, count: int, n_obs: int = 11, tf: float = 8.0, dt: float = 0.1,
+                road_name: str = "gentle") -> DpBatch:
+    """random_pedestrian-style scenes for the DP planner: the obstacle mix, sizes and speeds of
+    script/reference_publisher.py:116-194 (pedestrians crossing, moving and static vehicles), each dynamic obstacle
+    as a polygon trajectory sampled every dt (DynamicObstacles.msg), the ego start near the centre line."""
+    rd = road(road_name)
+    rng = np.random.Generator(np.random.Philox(key=[seed, 977]))
+    n = count
+    T = int(round(tf / dt)) + 1
+    t = np.arange(T) * dt
+    n_ped = int(round(n_obs * 6 / 11.0))
+    n_mov = int(round(n_obs * 3 / 11.0))
+    n_sta = n_obs - n_ped - n_mov
+    s0 = rng.uniform(5.0, rd.s_max - 130.0, size=n)
+    l0 = rng.uniform(-1.0, 0.5, size=n)
+    cx, cy, cth, _ = rd.eval(s0)
+    start = np.stack([cx - l0 * np.sin(cth), cy + l0 * np.cos(cth), cth + rng.normal(0.0, 0.02, size=n)], axis=-1)
+
+    def corners(s, l, th_fixed, hx, hy):
+        ox, oy, oth, _ = rd.eval(s)
+        px, py = ox - l * np.sin(oth), oy + l * np.cos(oth)
+        th = oth if th_fixed is None else np.full_like(oth, th_fixed)
+        c, sn = np.cos(th), np.sin(th)
+        out = []
+        for sx, sy in ((-1, -1), (-1, 1), (1, 1), (1, -1)):
+            out.append(np.stack([px + sx * hx * c - sy * hy * sn, py + sx * hx * sn + sy * hy * c], axis=-1))
+        return np.stack(out, axis=-2)
+
+    ped_s = s0[:, None] + rng.uniform(8.0, 90.0, size=(n, n_ped))
+    ped_v = 0.4 + rng.random(size=(n, n_ped))
+    ped_dir = np.where(rng.random(size=(n, n_ped)) > 0.5, 1.0, -1.0)
+    ub, lb = _LEFT_BOUND + 1.0, -_RIGHT_BOUND - 1.0
+    prog = np.clip((t[None, None, :] - ((ped_s - s0[:, None]) / 20.0)[..., None]) * ped_v[..., None], 0.0, ub - lb)
+    ped_l = np.where(ped_dir[..., None] > 0, ub - prog, lb + prog)
+    ped = corners(np.broadcast_to(ped_s[..., None], ped_l.shape), ped_l, 0.0, 0.5, 0.5)
+    mov_s = s0[:, None, None] + rng.uniform(-10.0, 80.0, size=(n, n_mov, 1)) + (4.0 + 2.0 * rng.random(size=(n, n_mov, 1))) * t
+    mov_l = np.broadcast_to(np.where(rng.random(size=(n, n_mov, 1)) > 0.5, 0.0, -4.0), mov_s.shape)
+    mov = corners(np.minimum(mov_s, rd.s_max - 1.0), mov_l, None, 2.0, 1.0)
+    sta_s = s0[:, None] + rng.uniform(15.0, 95.0, size=(n, n_sta))
+    sta_l = np.array([1.0, 0.0, -4.0])[rng.integers(0, 3, size=(n, n_sta))]
+    sta = corners(sta_s, sta_l, None, 2.0, 1.0)
+    dyn_poly = np.ascontiguousarray(np.concatenate([ped, mov], axis=1))
+    nd = n_ped + n_mov
+    return DpBatch(reference_line(road_name), np.ascontiguousarray(start), np.ascontiguousarray(sta),
+                   np.full((n, n_sta), 4, np.int32), np.ascontiguousarray(np.broadcast_to(t, (n, nd, T))),
+                   np.full((n, nd), T, np.int32), dyn_poly, np.full((n, nd), 4, np.int32))
+
+
 def config_batch(index: int, count: int | None = None, first_id: int = 0) -> ScenarioBatch:
     """BASELINE.json configs; seed = 20260101 + index."""
     table = {

@@ -75,6 +75,24 @@ class CorridorOut(C.Structure):
                 ("code", C.c_void_p)]
 
 
+class DpConfig(C.Structure):
+    """POD mirror of CilqrDpConfig (PlannerConfig planner_config.h:88-141 + VehicleParam fields)."""
+    _fields_ = [(n, C.c_double) for n in (
+        "tf", "delta_t", "dp_nominal_velocity", "dp_w_obstacle", "dp_w_lateral", "dp_w_lateral_change",
+        "dp_w_lateral_velocity_change", "dp_w_longitudinal_velocity_bias", "dp_w_longitudinal_velocity_change",
+        "max_velocity", "width", "wheel_base", "front_hang_length", "rear_hang_length")]
+
+
+class DpIn(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "R", "NB", "V", "n_static", "n_dyn", "T")] + [
+        (n, C.c_void_p) for n in ("ref", "barrier", "start", "static_poly", "static_nv", "dyn_time", "dyn_samples",
+                                  "dyn_poly", "dyn_nv")]
+
+
+class DpOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("trajectory", "coarse", "xytheta", "ok", "cost", "waypoints")]
+
+
 CORRIDOR_CODE_NAMES = ["ok", "no_points", "few_points", "origin", "capacity", "point_capacity"]
 
 EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_destroy",
@@ -83,7 +101,8 @@ EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_d
            "cilqr_last_cuda_error", "cilqr_debug_first_iteration", "cilqr_debug_stats",
            "cilqr_debug_completion_histogram", "cilqr_corridor_default_config", "cilqr_corridor_batch",
            "cilqr_corridor_batch_device", "cilqr_lane_constraints", "cilqr_lane_constraints_device",
-           "cilqr_corridor_last_kernel_ms"]
+           "cilqr_corridor_last_kernel_ms", "cilqr_dp_default_config", "cilqr_dp_num_knots",
+           "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms"]
 
 _lib = None
 
@@ -134,6 +153,13 @@ def load_library(build_if_missing: bool = True):
     L.cilqr_lane_constraints_device.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.c_int, C.c_int, C.c_int,
                                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cilqr_corridor_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cilqr_dp_default_config.argtypes = [C.POINTER(DpConfig)]
+    L.cilqr_dp_default_config.restype = None
+    L.cilqr_dp_num_knots.argtypes = [C.POINTER(DpConfig)]
+    L.cilqr_dp_plan_batch.argtypes = [C.c_void_p, C.POINTER(DpConfig), C.POINTER(DpIn), C.POINTER(DpOut)]
+    L.cilqr_dp_plan_batch_device.argtypes = [C.c_void_p, C.POINTER(DpConfig), C.POINTER(DpIn), C.POINTER(DpOut),
+                                             C.c_void_p]
+    L.cilqr_dp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -149,6 +175,17 @@ def default_corridor_config(point_cap: int = 0) -> CorridorConfig:
     load_library().cilqr_corridor_default_config(C.byref(c))
     c.point_cap = point_cap
     return c
+
+
+def default_dp_config() -> DpConfig:
+    c = DpConfig()
+    load_library().cilqr_dp_default_config(C.byref(c))
+    return c
+
+
+def dp_num_knots(cfg: DpConfig | None = None) -> int:
+    cfg = cfg or default_dp_config()
+    return load_library().cilqr_dp_num_knots(C.byref(cfg))
 
 
 def _ptr(x):
@@ -321,4 +358,40 @@ class Solver:
     def corridor_last_kernel_ms(self) -> float:
         ms = C.c_float()
         self._check(self._L.cilqr_corridor_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- coarse DP planner (DpPlanner::Plan, algorithm/planner/dp_planner.cpp:135-281) -----------------
+    def dp_plan_batch(self, dpb, barrier, cfg: DpConfig | None = None, waypoints: bool = False) -> dict:
+        """Host path: ``dpb`` is a scenarios.DpBatch-like object, ``barrier`` the road barrier [NB,2] sorted by x."""
+        cfg = cfg or default_dp_config()
+        K = dp_num_knots(cfg)
+        B = dpb.start.shape[0]
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)  # noqa: E731
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)  # noqa: E731
+        arrs = [f64(dpb.ref), f64(barrier), f64(dpb.start), f64(dpb.static_poly), i32(dpb.static_nv), f64(dpb.dyn_time),
+                i32(dpb.dyn_samples), f64(dpb.dyn_poly), i32(dpb.dyn_nv)]
+        V = arrs[3].shape[2] if arrs[3].ndim == 4 and arrs[3].shape[1] > 0 else (arrs[7].shape[3] if arrs[7].ndim == 5 else 4)
+        di = DpIn(B, arrs[0].shape[0], arrs[1].shape[0], V, arrs[3].shape[1], arrs[7].shape[1],
+                  arrs[7].shape[2] if arrs[7].ndim == 5 else 0, *[_ptr(a) for a in arrs])
+        o = {"trajectory": np.zeros((B, K, 13)), "coarse": np.zeros((B, K, 6)), "xytheta": np.zeros((B, K, 3)),
+             "ok": np.zeros(B, np.int32), "cost": np.zeros(B)}
+        if waypoints:
+            o["waypoints"] = np.zeros((B, 5, 3))
+        do = DpOut(*[_ptr(o.get(n)) for n in ("trajectory", "coarse", "xytheta", "ok", "cost", "waypoints")])
+        self._check(self._L.cilqr_dp_plan_batch(self._h, C.byref(cfg), C.byref(di), C.byref(do)))
+        return o
+
+    def dp_plan_batch_device(self, B, R, NB, V, n_static, n_dyn, T, ref, barrier, start, static_poly, static_nv,
+                             dyn_time, dyn_samples, dyn_poly, dyn_nv, ok, trajectory=None, coarse=None, xytheta=None,
+                             cost=None, waypoints=None, cfg: DpConfig | None = None, stream: int | None = None):
+        """Device path: pointers / CUDA tensors; enqueues the planner kernel and returns."""
+        cfg = cfg or default_dp_config()
+        di = DpIn(B, R, NB, V, n_static, n_dyn, T, *[_ptr(a) for a in (ref, barrier, start, static_poly, static_nv,
+                                                                        dyn_time, dyn_samples, dyn_poly, dyn_nv)])
+        do = DpOut(_ptr(trajectory), _ptr(coarse), _ptr(xytheta), _ptr(ok), _ptr(cost), _ptr(waypoints))
+        self._check(self._L.cilqr_dp_plan_batch_device(self._h, C.byref(cfg), C.byref(di), C.byref(do), stream))
+
+    def dp_last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.cilqr_dp_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CILQR_ABI_VERSION 2
+#define CILQR_ABI_VERSION 3
 
 /* error codes */
 #define CILQR_OK 0
@@ -227,6 +227,64 @@ int cilqr_lane_constraints_device(cilqr_handle* h, const CilqrCorridorConfig* cf
                                   void* cuda_stream);
 /* CUDA-event time of the last corridor kernel enqueued through this handle. */
 int cilqr_corridor_last_kernel_ms(cilqr_handle* h, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse DP planner: the step before the corridor.
+ * Replaces DpPlanner::Plan (algorithm/planner/dp_planner.h:31-37, dp_planner.cpp:135-281) for B scenarios at
+ * once: the 5 x 7 x 10 lattice search (GetCost :87-133, GetCollisionCost :40-85, InterpolateLinearly :283-320)
+ * with the collision checks of Environment (utils/environment.cpp:51-141) and the trajectory profile
+ * (ComputePathProfile, utils/discrete_points_math.cc:27-176).  The Environment is passed as flat arrays:
+ *
+ *   ref        [R][7]                 s, x, y, theta, kappa, left_bound, right_bound: the centre line
+ *                                     (CenterLinePoint.msg -> Environment::set_reference); shared by the batch
+ *   barrier    [NB][2]                Environment::road_barrier_ (environment.cpp:24-49), sorted by x; shared
+ *   start      [B][3]                 x, y, theta of the planning start (dp_planner.cpp:135-141)
+ *   static_poly[B][n_static][V][2]    static obstacle polygons, static_nv [B][n_static] vertices used
+ *   dyn_time   [B][n_dyn][T]          sample times of every dynamic obstacle (ascending), dyn_samples [B][n_dyn]
+ *   dyn_poly   [B][n_dyn][T][V][2]    its polygon at every sample, dyn_nv [B][n_dyn]
+ *   trajectory [B][K][13]  out (opt.) TrajectoryPoint records (time, s, x, y, theta, kappa, velocity, a, jerk,
+ *                                     delta, delta_rate, left_bound, right_bound), K = cilqr_dp_num_knots()
+ *   coarse     [B][K][6]   out (opt.) x, y, theta, velocity, a, delta  = CilqrBatchIn::coarse
+ *   xytheta    [B][K][3]   out (opt.) x, y, theta                      = CilqrCorridorIn::traj
+ *   ok         [B] int32   out        DpPlanner::Plan's return value (min_cost < dp_w_obstacle)
+ *   cost       [B]         out (opt.) min_cost;  waypoints [B][5][3] out (opt.) s index, l index, current_s
+ */
+typedef struct CilqrDpConfig { /* PlannerConfig, planner_config.h:88-141 + VehicleParam fields the planner reads */
+  double tf, delta_t, dp_nominal_velocity, dp_w_obstacle, dp_w_lateral, dp_w_lateral_change,
+      dp_w_lateral_velocity_change, dp_w_longitudinal_velocity_bias, dp_w_longitudinal_velocity_change;
+  double max_velocity, width, wheel_base, front_hang_length, rear_hang_length;
+} CilqrDpConfig;
+void cilqr_dp_default_config(CilqrDpConfig* c);
+int cilqr_dp_num_knots(const CilqrDpConfig* c);
+
+typedef struct CilqrDpIn {
+  int32_t B, R, NB, V, n_static, n_dyn, T;
+  const double* ref;
+  const double* barrier;
+  const double* start;
+  const double* static_poly;
+  const int32_t* static_nv;
+  const double* dyn_time;
+  const int32_t* dyn_samples;
+  const double* dyn_poly;
+  const int32_t* dyn_nv;
+} CilqrDpIn;
+
+typedef struct CilqrDpOut {
+  double* trajectory;
+  double* coarse;
+  double* xytheta;
+  int32_t* ok; /* required */
+  double* cost;
+  double* waypoints;
+} CilqrDpOut;
+
+/* DEVICE pointers; enqueues on `cuda_stream` (NULL = the handle's stream) and returns. */
+int cilqr_dp_plan_batch_device(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const CilqrDpOut* out,
+                               void* cuda_stream);
+/* HOST pointers; blocks until the outputs are in host memory. */
+int cilqr_dp_plan_batch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const CilqrDpOut* out);
+int cilqr_dp_last_kernel_ms(cilqr_handle* h, float* ms);
 
 #ifdef __cplusplus
 }

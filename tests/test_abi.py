@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", cilqr_b200.lib_path()], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", out), n
-    assert lib.cilqr_abi_version() == 2
+    assert lib.cilqr_abi_version() == 3
 
 
 def test_product_library_does_not_link_the_oracle():
@@ -51,6 +51,10 @@ def test_struct_layout_matches_header():
     assert C.sizeof(S.CorridorConfig) == 6 * 8 + 8
     assert C.sizeof(S.CorridorIn) == 16 + 3 * 8
     assert C.sizeof(S.CorridorOut) == 4 * 8
+    # CilqrDpConfig: 14 doubles; CilqrDpIn: 7 int32 (+pad) + 9 pointers; CilqrDpOut: 6 pointers
+    assert C.sizeof(S.DpConfig) == 14 * 8
+    assert C.sizeof(S.DpIn) == 32 + 9 * 8
+    assert C.sizeof(S.DpOut) == 6 * 8
 
 
 def test_default_params_equal_the_oracles(oracle):
