@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "cilqr_internal.h"
 
@@ -27,8 +28,10 @@ int validate(const cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* i
   return CILQR_OK;
 }
 
+// host_barrier: the barrier points in host memory (the host path has them; the device path copies them back once
+// per call -- 16 bytes per point)
 int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const CilqrDpOut* out, double ref_s0,
-           double ref_s1, cudaStream_t st) {
+           double ref_s1, const double* host_barrier, cudaStream_t st) {
   dp::Args a;
   memset(&a, 0, sizeof(a));
   dp::make_lattice(cfg->tf, cfg->delta_t, cfg->max_velocity, cfg->width, cfg->wheel_base, cfg->front_hang_length,
@@ -50,7 +53,21 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
   a.dyn_nv = in->dyn_nv;
   a.trajectory = out->trajectory; a.coarse = out->coarse; a.xytheta = out->xytheta; a.ok = out->ok; a.cost = out->cost;
   a.waypoints = out->waypoints;
-  const size_t smem = dp::smem_bytes(a.lat.K);
+  // the barrier grid: built on the host, uploaded to the handle's scratch (slot 0)
+  std::vector<int> gs, gi;
+  dp::build_grid(host_barrier, in->NB, a.lat.radius, &a, &gs, &gi);
+  {
+    char* g = nullptr;
+    const size_t b0 = (gs.size() * sizeof(int) + 255) & ~(size_t)255, b1 = gi.size() * sizeof(int);
+    int rcg = cilqr_internal_scratch(h, 0, b0 + b1, &g);
+    if (rcg != CILQR_OK) return rcg;
+    CKH(cudaMemcpyAsync(g, gs.data(), gs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKH(cudaMemcpyAsync(g + b0, gi.data(), b1, cudaMemcpyHostToDevice, st));
+    CKH(cudaStreamSynchronize(st));  // gs / gi are locals
+    a.grid_start = (const int*)g;
+    a.grid_idx = (const int*)(g + b0);
+  }
+  const size_t smem = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn);
   CKH(cudaFuncSetAttribute(dp::dp_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp::dp_plan_kernel, dp::kMaxThreads, smem));
@@ -103,12 +120,14 @@ int cilqr_dp_plan_batch_device(cilqr_handle* h, const CilqrDpConfig* cfg, const 
   if (rc != CILQR_OK || in->B == 0) return rc;
   CKH(cudaSetDevice(cilqr_internal_device(h)));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cilqr_internal_stream(h);
-  // first / last station of the centre line (for the station-search guess)
+  // first / last station of the centre line (for the station-search guess) and the barrier (for its grid)
   double ends[2];
+  std::vector<double> hb((size_t)(in->NB > 0 ? in->NB : 1) * 2);
   CKH(cudaMemcpyAsync(&ends[0], in->ref, sizeof(double), cudaMemcpyDeviceToHost, st));
   CKH(cudaMemcpyAsync(&ends[1], in->ref + (size_t)(in->R - 1) * 7, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (in->NB > 0) CKH(cudaMemcpyAsync(hb.data(), in->barrier, (size_t)in->NB * 16, cudaMemcpyDeviceToHost, st));
   CKH(cudaStreamSynchronize(st));
-  return launch(h, cfg, in, out, ends[0], ends[1], st);
+  return launch(h, cfg, in, out, ends[0], ends[1], hb.data(), st);
 }
 
 int cilqr_dp_plan_batch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const CilqrDpOut* out) {
@@ -157,7 +176,7 @@ int cilqr_dp_plan_batch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDp
   dout.ok = (int32_t*)p[12];
   dout.cost = out->cost ? (double*)p[13] : nullptr;
   dout.waypoints = out->waypoints ? (double*)p[14] : nullptr;
-  rc = launch(h, cfg, &din, &dout, in->ref[0], in->ref[(size_t)(in->R - 1) * 7], st);
+  rc = launch(h, cfg, &din, &dout, in->ref[0], in->ref[(size_t)(in->R - 1) * 7], in->barrier, st);
   if (rc != CILQR_OK) return rc;
   if (out->trajectory) CKH(cudaMemcpyAsync(out->trajectory, dout.trajectory, B * K * 13 * 8, cudaMemcpyDeviceToHost, st));
   if (out->coarse) CKH(cudaMemcpyAsync(out->coarse, dout.coarse, B * K * 6 * 8, cudaMemcpyDeviceToHost, st));

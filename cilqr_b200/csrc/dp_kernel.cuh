@@ -27,6 +27,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace dp {
 
 constexpr int NT = 5, NS = 7, NL = 10, NP = NS * NL;  // dp_planner.h:27-29
@@ -86,6 +88,12 @@ struct Args {
   Lattice lat;
   const double* ref;      // [R][7]
   const double* barrier;  // [NB][2]
+  // uniform grid over the barrier points (built by the library from `barrier`): cell (ix, iy) holds the sorted-
+  // barrier indices grid_idx[grid_start[iy * gnx + ix] .. grid_start[iy * gnx + ix + 1])
+  double gx0, gy0, ginv;
+  int gnx, gny;
+  const int* grid_start;
+  const int* grid_idx;
   const double* start;    // [B][3]
   const double* static_poly;
   const int* static_nv;
@@ -100,6 +108,39 @@ struct Args {
   double* cost;
   double* waypoints;
 };
+
+// Host side: buckets the barrier points into square cells a little wider than the collision box, so that a box
+// reaches at most 2 x 2 cells.  cell(p) = floor((p - origin) * ginv) is monotone in p, and the kernel computes the
+// cells of a query with the same expression, so every point the box test can accept lies in a scanned cell.
+inline void build_grid(const double* barrier, int NB, double half, Args* a, std::vector<int>* start,
+                       std::vector<int>* idx) {
+  const double cs = 2.0 * half + 1e-6;
+  double minx = 0, maxx = 0, miny = 0, maxy = 0;
+  for (int i = 0; i < NB; ++i) {
+    const double x = barrier[2 * i], y = barrier[2 * i + 1];
+    if (i == 0 || x < minx) minx = x;
+    if (i == 0 || x > maxx) maxx = x;
+    if (i == 0 || y < miny) miny = y;
+    if (i == 0 || y > maxy) maxy = y;
+  }
+  a->gx0 = minx - cs;
+  a->gy0 = miny - cs;
+  a->ginv = 1.0 / cs;
+  a->gnx = NB ? (int)floor((maxx - a->gx0) * a->ginv) + 2 : 1;
+  a->gny = NB ? (int)floor((maxy - a->gy0) * a->ginv) + 2 : 1;
+  const size_t cells = (size_t)a->gnx * a->gny;
+  start->assign(cells + 1, 0);
+  idx->assign(NB > 0 ? NB : 1, 0);
+  std::vector<int> cell(NB > 0 ? NB : 1);
+  for (int i = 0; i < NB; ++i) {
+    const int ix = (int)floor((barrier[2 * i] - a->gx0) * a->ginv), iy = (int)floor((barrier[2 * i + 1] - a->gy0) * a->ginv);
+    cell[i] = iy * a->gnx + ix;
+    ++(*start)[cell[i] + 1];
+  }
+  for (size_t c = 0; c < cells; ++c) (*start)[c + 1] += (*start)[c];
+  std::vector<int> fill(start->begin(), start->end() - 1);
+  for (int i = 0; i < NB; ++i) (*idx)[fill[cell[i]]++] = i;
+}
 
 struct Cell {
   double cost, current_s;
@@ -196,8 +237,8 @@ __device__ __forceinline__ bool box_is_point_in(double px, double py, double cx,
   return dx <= half + kMathEps && dy <= half + kMathEps;
 }
 
-// Polygon2d::HasOverlap(const Box2d&), polygon2d.cpp:150-165
-__device__ bool polygon_overlaps_box(const double* p, int nv, double cx, double cy, double half) {
+// a polygon's axis-aligned bounds as Polygon2d::BuildFromPoints computes them (polygon2d.cpp:246-256)
+__device__ __forceinline__ void polygon_aabb(const double* p, int nv, double* o) {
   double minx = p[0], maxx = p[0], miny = p[1], maxy = p[1];
   for (int i = 1; i < nv; ++i) {
     minx = fmin(minx, p[2 * i]);
@@ -205,14 +246,23 @@ __device__ bool polygon_overlaps_box(const double* p, int nv, double cx, double 
     miny = fmin(miny, p[2 * i + 1]);
     maxy = fmax(maxy, p[2 * i + 1]);
   }
+  o[0] = minx; o[1] = maxx; o[2] = miny; o[3] = maxy;
+}
+
+__device__ __forceinline__ bool aabb_disjoint(const double* o, double cx, double cy, double half) {
   const double bminx = cx - half, bmaxx = cx + half, bminy = cy - half, bmaxy = cy + half;
-  if (bmaxx < minx || bminx > maxx || bmaxy < miny || bminy > maxy) return false;
+  return bmaxx < o[0] || bminx > o[1] || bmaxy < o[2] || bminy > o[3];
+}
+
+// Polygon2d::HasOverlap(const Box2d&), polygon2d.cpp:150-165, after its bounding-box rejection
+__device__ bool polygon_overlaps_box(const double* p, int nv, const double* bb, double cx, double cy, double half) {
+  if (aabb_disjoint(bb, cx, cy, half)) return false;
   for (int i = 0; i < nv; ++i)
     if (box_is_point_in(p[2 * i], p[2 * i + 1], cx, cy, half)) return true;
-  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx + half, cy - half)) return true;  // aabox2d.cpp:63-71
-  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx + half, cy + half)) return true;
-  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx - half, cy + half)) return true;
-  if (polygon_is_point_in(p, nv, minx, maxx, miny, maxy, cx - half, cy - half)) return true;
+  if (polygon_is_point_in(p, nv, bb[0], bb[1], bb[2], bb[3], cx + half, cy - half)) return true;  // aabox2d.cpp:63-71
+  if (polygon_is_point_in(p, nv, bb[0], bb[1], bb[2], bb[3], cx + half, cy + half)) return true;
+  if (polygon_is_point_in(p, nv, bb[0], bb[1], bb[2], bb[3], cx - half, cy + half)) return true;
+  if (polygon_is_point_in(p, nv, bb[0], bb[1], bb[2], bb[3], cx - half, cy - half)) return true;
   return false;
 }
 
@@ -227,26 +277,51 @@ __device__ __forceinline__ int barrier_upper_bound(const double* bar, int NB, do
 }
 
 // Environment::CheckStaticCollision, environment.cpp:51-87
-__device__ bool check_static(const Args& a, int b, double cx, double cy, double half) {
+// obb: per scenario, in shared memory: the bounds of every static polygon, then for every dynamic obstacle the
+// bounds of ALL its samples (a box that misses those misses every sample's own bounding box, which is the
+// reference's first test)
+__device__ bool check_static(const Args& a, int b, const double* obb, double cx, double cy, double half) {
   const double* polys = a.static_poly + (size_t)b * a.n_static * a.V * 2;
   const int* nv = a.static_nv + (size_t)b * a.n_static;
-  for (int o = 0; o < a.n_static; ++o)
-    if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], cx, cy, half)) return true;
+  for (int o = 0; o < a.n_static; ++o) {
+    if (aabb_disjoint(obb + 4 * o, cx, cy, half)) continue;
+    if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], obb + 4 * o, cx, cy, half)) return true;
+  }
   if (a.NB == 0) return false;
   const double minx = cx - half, maxx = cx + half;
   if (maxx < a.barrier[0] || minx > a.barrier[(size_t)(a.NB - 1) * 2]) return false;
-  int check_start = barrier_upper_bound(a.barrier, a.NB, minx);
-  const int check_end = barrier_upper_bound(a.barrier, a.NB, maxx);
-  if (check_start > 0) --check_start;
-  for (int i = check_start; i < check_end; ++i)
-    if (box_is_point_in(a.barrier[(size_t)i * 2], a.barrier[(size_t)i * 2 + 1], cx, cy, half)) return true;
+  // The reference tests the sorted points with index in [upper_bound(minx) - 1, upper_bound(maxx)), i.e. those with
+  // minx < x <= maxx plus the last one with x <= minx.  The same points are found through the grid: only the (at
+  // most 2 x 2) cells the box can reach are scanned, a hit counts if x <= maxx and (x > minx or it is that one
+  // extra point -- the binary search is only run when such a candidate shows up).
+  const double m = half + 1e-9;  // the box test accepts |d| <= half + 1e-10
+  int ix0 = (int)floor((cx - m - a.gx0) * a.ginv), ix1 = (int)floor((cx + m - a.gx0) * a.ginv);
+  int iy0 = (int)floor((cy - m - a.gy0) * a.ginv), iy1 = (int)floor((cy + m - a.gy0) * a.ginv);
+  if (ix1 < 0 || iy1 < 0 || ix0 >= a.gnx || iy0 >= a.gny) return false;
+  ix0 = ix0 < 0 ? 0 : ix0;
+  iy0 = iy0 < 0 ? 0 : iy0;
+  ix1 = ix1 >= a.gnx ? a.gnx - 1 : ix1;
+  iy1 = iy1 >= a.gny ? a.gny - 1 : iy1;
+  for (int iy = iy0; iy <= iy1; ++iy)
+    for (int ix = ix0; ix <= ix1; ++ix) {
+      const int c = iy * a.gnx + ix;
+      for (int k = a.grid_start[c]; k < a.grid_start[c + 1]; ++k) {
+        const int i = a.grid_idx[k];
+        const double px = a.barrier[(size_t)i * 2], py = a.barrier[(size_t)i * 2 + 1];
+        if (!box_is_point_in(px, py, cx, cy, half)) continue;
+        if (!(px <= maxx)) continue;  // index >= upper_bound(maxx)
+        if (px > minx) return true;
+        if (i == barrier_upper_bound(a.barrier, a.NB, minx) - 1) return true;
+      }
+    }
   return false;
 }
 
 // Environment::CheckDynamicCollision, environment.cpp:124-141 (query time == last sample time: the reference
 // dereferences end(); the last sample is used)
-__device__ bool check_dynamic(const Args& a, int b, double time, double cx, double cy, double half) {
+__device__ bool check_dynamic(const Args& a, int b, const double* obb, double time, double cx, double cy, double half) {
   for (int o = 0; o < a.n_dyn; ++o) {
+    if (aabb_disjoint(obb + 4 * (a.n_static + o), cx, cy, half)) continue;
     const size_t ob = (size_t)b * a.n_dyn + o;
     const int ns = a.dyn_samples[ob];
     if (ns <= 0) continue;
@@ -258,13 +333,16 @@ __device__ bool check_dynamic(const Args& a, int b, double time, double cx, doub
       if (time < tt[mid]) hi = mid; else lo = mid + 1;
     }
     if (lo >= ns) lo = ns - 1;
-    if (polygon_overlaps_box(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], cx, cy, half)) return true;
+    double bb[4];
+    polygon_aabb(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], bb);
+    if (polygon_overlaps_box(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], bb, cx, cy, half)) return true;
   }
   return false;
 }
 
 // Environment::CheckOptimizationCollision, environment.cpp:99-122; GetDiscPositions, vehicle_param.h:88-95
-__device__ bool check_optimization_collision(const Args& a, int b, double time, double x, double y, double theta) {
+__device__ bool check_optimization_collision(const Args& a, int b, const double* obb, double time, double x, double y,
+                                             double theta) {
   const double radius = a.lat.radius;
   const double half = (radius + 0.0 - (-radius - 0.0)) / 2.0;
   const double ct = cos(theta), st = sin(theta);
@@ -272,8 +350,8 @@ __device__ bool check_optimization_collision(const Args& a, int b, double time, 
   const double yf = y + a.lat.f2x * st, yr = y + a.lat.r2x * st;
   const double c0 = (-radius - 0.0 + (radius + 0.0)) / 2.0;
   const double fx = c0 + xf, fy = c0 + yf, rx = c0 + xr, ry = c0 + yr;
-  return check_static(a, b, fx, fy, half) || check_static(a, b, rx, ry, half) ||
-         check_dynamic(a, b, time, fx, fy, half) || check_dynamic(a, b, time, rx, ry, half);
+  return check_static(a, b, obb, fx, fy, half) || check_static(a, b, obb, rx, ry, half) ||
+         check_dynamic(a, b, obb, time, fx, fy, half) || check_dynamic(a, b, obb, time, rx, ry, half);
 }
 
 struct Start {
@@ -312,8 +390,8 @@ __device__ __forceinline__ Segment make_segment(const Args& a, const Start& st, 
 }
 
 // GetCollisionCost, dp_planner.cpp:40-85; pt < 0: the parent is the start state
-__device__ double collision_cost(const Args& a, int b, const Start& st, const Cell* cells, int pt, int psi, int pli,
-                                 int ct, int csi, int cli) {
+__device__ double collision_cost(const Args& a, int b, const double* obb, const Start& st, const Cell* cells, int pt,
+                                 int psi, int pli, int ct, int csi, int cli) {
   double parent_s = st.s, grandparent_s = st.s;
   double last_l = st.l, last_s = st.s;
   if (pt >= 0) {
@@ -340,14 +418,14 @@ __device__ double collision_cost(const Args& a, int b, const Start& st, const Ce
     if (pl < lb - kDpEps || pl > ub + kDpEps) return a.w_obstacle;
     const double heading = r.theta + atan((dl / ds) / (1 - r.kappa * pl));
     const double time = parent_time + i * (a.lat.unit_time / g.nseg);
-    if (check_optimization_collision(a, b, time, cx, cy, heading)) return a.w_obstacle;
+    if (check_optimization_collision(a, b, obb, time, cx, cy, heading)) return a.w_obstacle;
   }
   return 0.0;
 }
 
 // GetCost, dp_planner.cpp:87-133
-__device__ double get_cost(const Args& a, int b, const Start& st, const Cell* cells, int pt, int psi, int pli, int ct,
-                           int csi, int cli, double* cur_s_out) {
+__device__ double get_cost(const Args& a, int b, const double* obb, const Start& st, const Cell* cells, int pt, int psi,
+                           int pli, int ct, int csi, int cli, double* cur_s_out) {
   double parent_s = st.s, grandparent_s = st.s;
   double parent_l = st.l, grandparent_l = st.l;
   if (pt >= 0) {
@@ -366,7 +444,7 @@ __device__ double get_cost(const Args& a, int b, const Start& st, const Cell* ce
   const double ds0 = parent_s - grandparent_s;
   const double dl0 = parent_l - grandparent_l;
   *cur_s_out = cur_s;
-  const double cost_obstacle = collision_cost(a, b, st, cells, pt, psi, pli, ct, csi, cli);
+  const double cost_obstacle = collision_cost(a, b, obb, st, cells, pt, psi, pli, ct, csi, cli);
   if (cost_obstacle >= a.w_obstacle) return a.w_obstacle;
   const double cost_lateral = fabs(cur_l);
   const double cost_lateral_change = fabs(parent_l - cur_l) / (a.lat.station_[csi] + kDpEps);
@@ -383,8 +461,8 @@ constexpr int kMaxThreads = 256;
 constexpr int kMaxKnots = 512;
 
 // shared-memory layout (bytes); K <= kMaxKnots
-__host__ __device__ inline size_t smem_bytes(int K) {
-  return sizeof(Cell) * NT * NP + sizeof(double) * NP * NP + sizeof(double) * kMaxThreads + sizeof(int) * kMaxThreads +
+__host__ __device__ inline size_t smem_bytes(int K, int n_obstacles) {
+  return sizeof(double) * 4 * (size_t)n_obstacles + sizeof(Cell) * NT * NP + sizeof(double) * NP * NP + sizeof(double) * kMaxThreads + sizeof(int) * kMaxThreads +
          sizeof(double) * 8 + sizeof(int) * 3 * NT + sizeof(double) * 10 * (size_t)K + 64;
 }
 
@@ -398,6 +476,7 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
   int* wp = red_i + kMaxThreads;                                          // [NT][3]: s index, l index, parent l index
   double* kn = reinterpret_cast<double*>(wp + 3 * NT + 1);                // 10 arrays of K doubles
   kn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(kn) + 15) & ~(uintptr_t)15);
+  double* obb = kn + 10 * (size_t)a.lat.K;                                // [n_static + n_dyn][4] obstacle bounds
   const int tid = threadIdx.x, nt = blockDim.x;
   const int K = a.lat.K;
   double *xs = kn, *ys = kn + K, *acc_s = kn + 2 * K, *speeds = kn + 3 * K, *accel = kn + 4 * K, *xds = kn + 5 * K,
@@ -406,6 +485,26 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     __syncthreads();
     const double sx = a.start[(size_t)b * 3], sy = a.start[(size_t)b * 3 + 1];
+    // ---- obstacle bounds of this scenario
+    for (int o = tid; o < a.n_static + a.n_dyn; o += nt) {
+      if (o < a.n_static) {
+        polygon_aabb(a.static_poly + ((size_t)b * a.n_static + o) * a.V * 2, a.static_nv[(size_t)b * a.n_static + o],
+                     obb + 4 * o);
+      } else {
+        const size_t ob = (size_t)b * a.n_dyn + (o - a.n_static);
+        const int ns = a.dyn_samples[ob], nv = a.dyn_nv[ob];
+        double acc[4] = {DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX};  // no sample: never reached by a box
+        for (int t = 0; t < ns; ++t) {
+          double bb[4];
+          polygon_aabb(a.dyn_poly + (ob * a.T + t) * a.V * 2, nv, bb);
+          acc[0] = fmin(acc[0], bb[0]);
+          acc[1] = fmax(acc[1], bb[1]);
+          acc[2] = fmin(acc[2], bb[2]);
+          acc[3] = fmax(acc[3], bb[3]);
+        }
+        for (int q = 0; q < 4; ++q) obb[4 * o + q] = acc[q];
+      }
+    }
     // ---- GetProjection, discretized_trajectory.cpp:156-190; QueryNearestPoint (:136-154): first minimum
     {
       double best = DBL_MAX;
@@ -461,7 +560,7 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
     // ---- first layer, dp_planner.cpp:151-158
     for (int p = tid; p < NP; p += nt) {
       double cur_s;
-      const double c = get_cost(a, b, st, cells, -1, -1, -1, 0, p / NL, p % NL, &cur_s);
+      const double c = get_cost(a, b, obb, st, cells, -1, -1, -1, 0, p / NL, p % NL, &cur_s);
       Cell cell;
       cell.cost = c;
       cell.current_s = cur_s;
@@ -475,7 +574,7 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
       for (int q = tid; q < NP * NP; q += nt) {
         const int parent = q / NP, child = q - parent * NP;
         double cur_s;
-        delta[q] = get_cost(a, b, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);
+        delta[q] = get_cost(a, b, obb, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);
       }
       __syncthreads();
       for (int child = tid; child < NP; child += nt) {

@@ -36,6 +36,10 @@ extern "C" int emul_dp(const double* cfg, const int* dims, const double* ref, co
   a.ref = ref; a.barrier = barrier; a.start = start; a.static_poly = static_poly; a.static_nv = static_nv;
   a.dyn_time = dyn_time; a.dyn_samples = dyn_samples; a.dyn_poly = dyn_poly; a.dyn_nv = dyn_nv;
   a.trajectory = trajectory; a.coarse = coarse; a.xytheta = xytheta; a.ok = ok; a.cost = cost; a.waypoints = waypoints;
+  std::vector<int> gs, gi;
+  dp::build_grid(barrier, a.NB, a.lat.radius, &a, &gs, &gi);
+  a.grid_start = gs.data();
+  a.grid_idx = gi.data();
   gridDim.x = 1;
   dp::dp_plan_kernel(a);
   return a.lat.K;
