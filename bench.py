@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-corridor", action="store_true", help="skip the corridor-builder side measurement")
+    ap.add_argument("--no-dp", action="store_true", help="skip the DP-planner side measurement")
     ap.add_argument("--corridor-base", type=int, default=2048,
                     help="scenarios generated on the host for the corridor measurement (tiled on the device)")
     return ap.parse_args()
@@ -159,6 +160,51 @@ def corridor_measurement(solver, a, dev, stream, peak):
                              "sample": f"first {n_cpu} scenarios x {K} knots, oracle/corridor_oracle.c, 1 thread, "
                                        f"{cpu_s:.2f} s; plane counts equal to the GPU's: {same}"},
             "note": f"{base} generated scenarios tiled x{rep} on the device; one thread per knot, point_cap {cfg.point_cap}"}
+
+
+def dp_measurement(solver, a, dev, stream):
+    """Side measurement (rank 0): the batched DpPlanner::Plan kernel (SURVEY 8(f) rank 2, the first stage of the
+    planner) on random_pedestrian-style scenes, next to its CPU restatement on one host core.  Not part of `value`."""
+    import torch
+    from cilqr_b200 import scenarios
+    from cilqr_b200.solver import dp_num_knots
+    from oracle import dp_binding as dpo
+    base, rep = 512, 16
+    db = scenarios.generate_dp(SEED, base, n_obs=11)
+    barrier = dpo.build_barrier(db.ref)
+    B, K = base * rep, dp_num_knots()
+    one = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    tile = lambda x: one(x).repeat(rep, *([1] * (x.ndim - 1)))  # noqa: E731
+    ref, bar = one(db.ref), one(barrier)
+    tin = [tile(x) for x in (db.start, db.static_poly, db.static_nv, db.dyn_time, db.dyn_samples, db.dyn_poly, db.dyn_nv)]
+    ok = torch.zeros(B, dtype=torch.int32, device=dev)
+    coarse = torch.zeros(B, K, 6, dtype=torch.float64, device=dev)
+    ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        solver.dp_plan_batch_device(B, len(db.ref), len(barrier), 4, db.static_poly.shape[1], db.dyn_poly.shape[1],
+                                    db.dyn_poly.shape[2], ref, bar, *tin, ok, coarse=coarse, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        ms.append(solver.dp_last_kernel_ms())
+    kms = float(np.mean(ms[1:]))
+    n_cpu = 6
+    t0 = time.perf_counter()
+    cfg = dpo.default_config()
+    okc = []
+    for b in range(n_cpu):
+        sc = dpo.Scene(db.ref, barrier, db.static_poly[b], db.static_nv[b], db.dyn_time[b], db.dyn_samples[b],
+                       db.dyn_poly[b], db.dyn_nv[b])
+        okc.append(dpo.plan(sc, *db.start[b], cfg)[0])
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(np.array(okc, bool), ok[:n_cpu].cpu().numpy().astype(bool)))
+    return {"kernel": "dp_plan_kernel", "scenes_per_launch": B, "kernel_ms": kms, "traj_per_s": B / kms * 1e3,
+            "planned_ok_fraction": float(ok.double().mean().item()),
+            "cpu_baseline": {"value": n_cpu / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"first {n_cpu} scenes, oracle/dp_oracle.c, 1 thread, {cpu_s:.2f} s; "
+                                       f"ok flags equal to the GPU's: {same}"},
+            "note": f"{base} generated scenes (11 obstacles, 81 knots, 5x7x10 lattice) tiled x{rep} on the device; one CTA "
+                    "per scene; compute bound (19 670 transitions x 16 collision-checked path points per scene), "
+                    "HBM traffic negligible"}
 
 
 def run_reference(a):
@@ -381,6 +427,9 @@ def main():
         corridor = None
         if not a.no_corridor:
             corridor = corridor_measurement(solver, a, dev, stream, peak)
+        dpm = None
+        if not a.no_dp:
+            dpm = dp_measurement(solver, a, dev, stream)
         alg_bytes = scenarios.algorithmic_bytes(N, batch.M_max, batch.S) * B
         achieved = alg_bytes / (kmean_ms * 1e-3) / 1e9
         traffic = None
@@ -417,6 +466,8 @@ def main():
             res["e2e"] = e2e
         if corridor:
             res["corridor"] = corridor
+        if dpm:
+            res["dp_planner"] = dpm
         if not a.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(res), flush=True)

@@ -365,6 +365,8 @@ class Solver:
         """Host path: ``dpb`` is a scenarios.DpBatch-like object, ``barrier`` the road barrier [NB,2] sorted by x."""
         cfg = cfg or default_dp_config()
         K = dp_num_knots(cfg)
+        if K < 2:
+            raise CilqrError(E_INVALID, "bad DP configuration (tf / delta_t)")
         B = dpb.start.shape[0]
         f64 = lambda a: np.ascontiguousarray(a, np.float64)  # noqa: E731
         i32 = lambda a: np.ascontiguousarray(a, np.int32)  # noqa: E731
