@@ -109,12 +109,12 @@ struct Args {
   double* waypoints;
 };
 
-// Host side: buckets the barrier points into square cells a little wider than the collision box, so that a box
-// reaches at most 2 x 2 cells.  cell(p) = floor((p - origin) * ginv) is monotone in p, and the kernel computes the
+// Host side: buckets the barrier points into square cells of a quarter of the collision box's side (a box reaches
+// at most 5 x 5 cells; a row of cells is one contiguous range of the CSR list).  cell(p) = floor((p - origin) * ginv) is monotone in p, and the kernel computes the
 // cells of a query with the same expression, so every point the box test can accept lies in a scanned cell.
 inline void build_grid(const double* barrier, int NB, double half, Args* a, std::vector<int>* start,
                        std::vector<int>* idx) {
-  const double cs = 2.0 * half + 1e-6;
+  const double cs = (2.0 * half + 1e-6) / 4.0;
   double minx = 0, maxx = 0, miny = 0, maxy = 0;
   for (int i = 0; i < NB; ++i) {
     const double x = barrier[2 * i], y = barrier[2 * i + 1];
@@ -151,9 +151,19 @@ struct RefPoint {
   double s, x, y, theta, kappa, lb, rb;
 };
 
+// fmod(x, y) for y > 0, bit-exact: fmod is an exact operation, and for |x| < 2y its result is x itself or
+// x -/+ y, a difference that is exactly representable (Sterbenz) -- the general (slow, iterative) routine is only
+// needed for larger arguments, which headings never are
+__device__ __forceinline__ double fmod_small(double x, double y) {
+  const double ax = fabs(x);
+  if (ax < y) return x;
+  if (ax < 2.0 * y) return copysign(ax - y, x);
+  return fmod(x, y);
+}
+
 // math_utils.cpp:53-59
 __device__ __forceinline__ double normalize_angle(double angle) {
-  double a = fmod(angle + kPi, 2.0 * kPi);
+  double a = fmod_small(angle + kPi, 2.0 * kPi);
   if (a < 0.0) a += 2.0 * kPi;
   return a - kPi;
 }
@@ -280,10 +290,10 @@ __device__ __forceinline__ int barrier_upper_bound(const double* bar, int NB, do
 // obb: per scenario, in shared memory: the bounds of every static polygon, then for every dynamic obstacle the
 // bounds of ALL its samples (a box that misses those misses every sample's own bounding box, which is the
 // reference's first test)
-__device__ bool check_static(const Args& a, int b, const double* obb, double cx, double cy, double half) {
+__device__ bool check_static(const Args& a, int b, const double* obb, bool any_near, double cx, double cy, double half) {
   const double* polys = a.static_poly + (size_t)b * a.n_static * a.V * 2;
   const int* nv = a.static_nv + (size_t)b * a.n_static;
-  for (int o = 0; o < a.n_static; ++o) {
+  for (int o = 0; any_near && o < a.n_static; ++o) {
     if (aabb_disjoint(obb + 4 * o, cx, cy, half)) continue;
     if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], obb + 4 * o, cx, cy, half)) return true;
   }
@@ -292,7 +302,7 @@ __device__ bool check_static(const Args& a, int b, const double* obb, double cx,
   if (maxx < a.barrier[0] || minx > a.barrier[(size_t)(a.NB - 1) * 2]) return false;
   // The reference tests the sorted points with index in [upper_bound(minx) - 1, upper_bound(maxx)), i.e. those with
   // minx < x <= maxx plus the last one with x <= minx.  The same points are found through the grid: only the (at
-  // most 2 x 2) cells the box can reach are scanned, a hit counts if x <= maxx and (x > minx or it is that one
+  // most 5 x 5) cells the box can reach are scanned, a hit counts if x <= maxx and (x > minx or it is that one
   // extra point -- the binary search is only run when such a candidate shows up).
   const double m = half + 1e-9;  // the box test accepts |d| <= half + 1e-10
   int ix0 = (int)floor((cx - m - a.gx0) * a.ginv), ix1 = (int)floor((cx + m - a.gx0) * a.ginv);
@@ -302,18 +312,17 @@ __device__ bool check_static(const Args& a, int b, const double* obb, double cx,
   iy0 = iy0 < 0 ? 0 : iy0;
   ix1 = ix1 >= a.gnx ? a.gnx - 1 : ix1;
   iy1 = iy1 >= a.gny ? a.gny - 1 : iy1;
-  for (int iy = iy0; iy <= iy1; ++iy)
-    for (int ix = ix0; ix <= ix1; ++ix) {
-      const int c = iy * a.gnx + ix;
-      for (int k = a.grid_start[c]; k < a.grid_start[c + 1]; ++k) {
-        const int i = a.grid_idx[k];
-        const double px = a.barrier[(size_t)i * 2], py = a.barrier[(size_t)i * 2 + 1];
-        if (!box_is_point_in(px, py, cx, cy, half)) continue;
-        if (!(px <= maxx)) continue;  // index >= upper_bound(maxx)
-        if (px > minx) return true;
-        if (i == barrier_upper_bound(a.barrier, a.NB, minx) - 1) return true;
-      }
+  for (int iy = iy0; iy <= iy1; ++iy) {
+    const int k1 = a.grid_start[iy * a.gnx + ix1 + 1];
+    for (int k = a.grid_start[iy * a.gnx + ix0]; k < k1; ++k) {
+      const int i = a.grid_idx[k];
+      const double px = a.barrier[(size_t)i * 2], py = a.barrier[(size_t)i * 2 + 1];
+      if (!box_is_point_in(px, py, cx, cy, half)) continue;
+      if (!(px <= maxx)) continue;  // index >= upper_bound(maxx)
+      if (px > minx) return true;
+      if (i == barrier_upper_bound(a.barrier, a.NB, minx) - 1) return true;
     }
+  }
   return false;
 }
 
@@ -350,8 +359,21 @@ __device__ bool check_optimization_collision(const Args& a, int b, const double*
   const double yf = y + a.lat.f2x * st, yr = y + a.lat.r2x * st;
   const double c0 = (-radius - 0.0 + (radius + 0.0)) / 2.0;
   const double fx = c0 + xf, fy = c0 + yf, rx = c0 + xr, ry = c0 + yr;
-  return check_static(a, b, obb, fx, fy, half) || check_static(a, b, obb, rx, ry, half) ||
-         check_dynamic(a, b, obb, time, fx, fy, half) || check_dynamic(a, b, obb, time, rx, ry, half);
+  // obstacles whose bounds miss the union of the two disc boxes cannot overlap either of them
+  const double ucx = 0.5 * (fx + rx), ucy = 0.5 * (fy + ry);
+  const double uhx = 0.5 * fabs(fx - rx) + half + 1e-9, uhy = 0.5 * fabs(fy - ry) + half + 1e-9;
+  unsigned near = 0;  // bit o: obstacle o is near (up to 32 obstacles are pre-screened, the rest always checked)
+  const int nobs = a.n_static + a.n_dyn;
+  for (int o = 0; o < nobs && o < 32; ++o) {
+    const double* q = obb + 4 * o;
+    if (!(ucx + uhx < q[0] || ucx - uhx > q[1] || ucy + uhy < q[2] || ucy - uhy > q[3])) near |= 1u << o;
+  }
+  if (nobs > 32) near = 0xffffffffu;
+  const unsigned near_static = a.n_static >= 32 ? near : (near & ((1u << a.n_static) - 1u));
+  const unsigned near_dyn = nobs > 32 ? 1u : (a.n_static >= 32 ? 0u : near >> a.n_static);
+  return check_static(a, b, obb, near_static != 0 || a.n_static > 32, fx, fy, half) ||
+         check_static(a, b, obb, near_static != 0 || a.n_static > 32, rx, ry, half) ||
+         (near_dyn != 0 && (check_dynamic(a, b, obb, time, fx, fy, half) || check_dynamic(a, b, obb, time, rx, ry, half)));
 }
 
 struct Start {
@@ -474,6 +496,7 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
   double* misc = red_d + kMaxThreads;                                     // start_s, start_l, min_cost
   int* red_i = reinterpret_cast<int*>(misc + 8);                          // [threads]
   int* wp = red_i + kMaxThreads;                                          // [NT][3]: s index, l index, parent l index
+  int* queue = wp + 3 * NT;                                               // next unclaimed transition of the layer
   double* kn = reinterpret_cast<double*>(wp + 3 * NT + 1);                // 10 arrays of K doubles
   kn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(kn) + 15) & ~(uintptr_t)15);
   double* obb = kn + 10 * (size_t)a.lat.K;                                // [n_static + n_dyn][4] obstacle bounds
@@ -571,7 +594,11 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
     __syncthreads();
     // ---- dynamic programming, :160-181
     for (int i = 0; i < NT - 1; ++i) {
-      for (int q = tid; q < NP * NP; q += nt) {
+      // transitions are claimed from a shared counter: one that collides at its first point costs a fraction of
+      // one that walks all its points, and a static split would leave most threads waiting for the unlucky ones
+      if (tid == 0) *queue = 0;
+      __syncthreads();
+      for (int q = atomicAdd(queue, 1); q < NP * NP; q = atomicAdd(queue, 1)) {
         const int parent = q / NP, child = q - parent * NP;
         double cur_s;
         delta[q] = get_cost(a, b, obb, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);

@@ -14,6 +14,7 @@
 #define __align__(x)
 #define __shared__
 static inline void __syncthreads() {}
+static inline int atomicAdd(int* p, int v) { const int o = *p; *p += v; return o; }
 struct emul_dim3 { int x; };
 static emul_dim3 threadIdx{0}, blockIdx{0}, blockDim{1}, gridDim{1};
 namespace dp { unsigned char dp_smem[1 << 18]; }
