@@ -89,5 +89,25 @@ def build_corridor_demo(force: bool = False) -> str:
     return CORRIDOR_DEMO
 
 
+DP_DEMO = os.path.join(LIB_DIR, "dp_demo")
+
+
+def build_dp_demo(force: bool = False) -> str:
+    """Compiles tests/adapter/dp_demo.cc -- the reference's DpPlanner call site driven through the
+    header-compatible planning::DpPlanner (include/cilqr/dp_planner_b200.h) -- against the stand-ins."""
+    root = os.path.dirname(_HERE)
+    src = os.path.join(root, "tests", "adapter", "dp_demo.cc")
+    hdr = os.path.join(root, "include", "cilqr", "dp_planner_b200.h")
+    if (not force and os.path.exists(DP_DEMO)
+            and os.path.getmtime(DP_DEMO) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB_PATH))):
+        return DP_DEMO
+    build_library()
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(root, "tests", "adapter", "stubs"), src, "-o", DP_DEMO,
+           "-L", LIB_DIR, "-lcilqr_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return DP_DEMO
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

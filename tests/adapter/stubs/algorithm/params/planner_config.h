@@ -38,3 +38,20 @@ struct CorridorConfig {
   double lane_segment_length = 5.0;
 };
 }  // namespace planning
+namespace planning {
+// Stand-in for algorithm/params/planner_config.h:88-141 (the fields planning::DpPlanner reads).
+struct PlannerConfig {
+  double delta_t = 0.1;
+  double tf = 8;
+  double dp_nominal_velocity = 10.0;
+  double dp_w_obstacle = 1000;
+  double dp_w_lateral = 0.1;
+  double dp_w_lateral_change = 0.5;
+  double dp_w_lateral_velocity_change = 1.0;
+  double dp_w_longitudinal_velocity_bias = 10.0;
+  double dp_w_longitudinal_velocity_change = 1.0;
+  VehicleParam vehicle;
+  CorridorConfig corridor_config;
+  IlqrConfig ilqr_config;
+};
+}  // namespace planning

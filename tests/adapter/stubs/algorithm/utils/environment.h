@@ -8,6 +8,8 @@
 #include <utility>
 #include <vector>
 #include "algorithm/math/line_segment2d.h"
+#include "algorithm/math/polygon2d.h"
+#include "algorithm/utils/discretized_trajectory.h"
 namespace planning {
 class Environment {
  public:
@@ -30,6 +32,14 @@ class Environment {
   }
   const std::vector<math::Vec2d>& left_road_barrier() { return left_; }
   const std::vector<math::Vec2d>& right_road_barrier() { return right_; }
+  // the accessors planning::DpPlanner reads (utils/environment.h:30-33,45-59)
+  using DynamicObstacle = std::vector<std::pair<double, math::Polygon2d>>;
+  std::vector<math::Polygon2d>& obstacles() { return obstacles_; }
+  std::vector<DynamicObstacle>& dynamic_obstacles() { return dynamic_obstacles_; }
+  const DiscretizedTrajectory& reference() const { return reference_; }
+  std::vector<math::Polygon2d> obstacles_;
+  std::vector<DynamicObstacle> dynamic_obstacles_;
+  DiscretizedTrajectory reference_;
   std::vector<math::Vec2d> static_, left_, right_;
   std::vector<DynamicObstaclePoints> dynamic_;
 };
