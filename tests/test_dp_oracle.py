@@ -135,3 +135,15 @@ def test_curved_road_follows_the_arc():
     assert np.abs(r - 40.0).max() < 1e-3
     assert np.abs(traj[20:-2, 5] - 1 / 40.0).max() < 2e-3  # kappa from ComputePathProfile
     assert np.allclose(traj[:, 9], np.arctan(traj[:, 5] * 1.0))  # delta = atan(kappa * wheel_base), :270
+
+
+def test_oracle_reproduces_the_committed_fixture():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dp_golden_v1.npz"))
+    assert np.array_equal(dp.build_barrier(z["ref"]), z["barrier"])
+    for b in range(len(z["start"])):
+        sc = dp.Scene(z["ref"], z["barrier"], z["static_poly"][b], z["static_nv"][b], z["dyn_time"][b],
+                      z["dyn_samples"][b], z["dyn_poly"][b], z["dyn_nv"][b])
+        ok, traj, cost, wp = dp.plan(sc, *z["start"][b])
+        assert ok == bool(z["ok"][b]) and cost == z["cost"][b]
+        assert np.array_equal(wp, z["waypoints"][b]) and np.array_equal(traj, z["trajectory"][b], equal_nan=True)

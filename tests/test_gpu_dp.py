@@ -146,3 +146,20 @@ def test_dp_feeds_corridor_and_solver_on_the_device(solver):
     assert not (codeh != 0).any()
     assert np.isfinite(X.cpu().numpy()).all() and (Sh[:, 0] >= 0).all()
     big.close()
+
+
+def test_dp_golden_fixture(solver):
+    """The committed oracle outputs (tests/golden/dp_golden_v1.npz) as the target."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dp_golden_v1.npz"))
+    db = scenarios.DpBatch(z["ref"], z["start"], z["static_poly"], z["static_nv"], z["dyn_time"], z["dyn_samples"],
+                           z["dyn_poly"], z["dyn_nv"])
+    got = solver.dp_plan_batch(db, z["barrier"], waypoints=True)
+    same = np.array([got["ok"][b] == z["ok"][b] and np.array_equal(got["waypoints"][b][:, :2], z["waypoints"][b][:, :2])
+                     for b in range(db.B)])
+    assert same.sum() >= db.B - 1  # a last-ulp libm difference may flip one lattice decision
+    for b in np.where(same)[0]:
+        t = z["trajectory"][b]
+        assert np.array_equal(np.isnan(got["trajectory"][b]), np.isnan(t))
+        assert np.nanmax(np.abs(got["trajectory"][b] - t) / (np.abs(t) + 1.0)) < 1e-9
+        assert abs(got["cost"][b] - z["cost"][b]) <= 1e-9 * (abs(z["cost"][b]) + 1.0)
