@@ -28,6 +28,13 @@
  *   trajectory   [B][K][13]  out     TrajectoryPoint records (discretized_trajectory.h:26-43) as
  *                                    TransformToTrajectory fills them, ilqr_optimizer.cc:771-791
  * Shrinking/normalising the constraints (ilqr_optimizer.cc:438-495) is part of the solve.
+ *
+ * Two further sections below widen the boundary to the stages that feed the solve inside
+ * TrajectoryPlanner::Plan (trajectory_planner.cpp:28-86), each with the same conventions and with
+ * outputs laid out as the next stage's inputs, so the three chain on the device:
+ *     DpPlanner::Plan   -> cilqr_dp_plan_batch(_device)        (drop-in: cilqr/dp_planner_b200.h)
+ *     Corridor::Plan    -> cilqr_corridor_batch(_device), cilqr_lane_constraints(_device)
+ *                                                              (drop-in: cilqr/corridor_b200.h)
  */
 #ifndef CILQR_B200_H_
 #define CILQR_B200_H_
