@@ -575,3 +575,25 @@ int dp_plan(const dp_config* cfg, const dp_env* env, double start_x, double star
   free(p);
   return ok;
 }
+
+/* ---- pieces exported for the pin tests against the compiled reference (oracle/_ref) ------------- */
+int dp_polygon_overlaps_box(const double* p, int nv, double cx, double cy, double half) {
+  return polygon_overlaps_box(p, nv, cx, cy, half);
+}
+int dp_polygon_is_point_in(const double* p, int nv, double x, double y) {
+  double minx = p[0], maxx = p[0], miny = p[1], maxy = p[1];
+  for (int i = 1; i < nv; ++i) {
+    minx = fmin(minx, p[2 * i]);
+    maxx = fmax(maxx, p[2 * i]);
+    miny = fmin(miny, p[2 * i + 1]);
+    maxy = fmax(maxy, p[2 * i + 1]);
+  }
+  return polygon_is_point_in(p, nv, minx, maxx, miny, maxy, x, y);
+}
+void dp_get_cartesian(int R, const double* ref, double station, double lateral, double xy[2]) {
+  get_cartesian(R, ref, station, lateral, &xy[0], &xy[1]);
+}
+void dp_path_profile(double dt, int n, const double* x, const double* y, double* speeds, double* accel, double* kappas) {
+  path_profile(dt, n, x, y, speeds, accel, kappas);
+}
+double dp_slerp(double a0, double t0, double a1, double t1, double t) { return slerp(a0, t0, a1, t1, t); }

@@ -69,6 +69,13 @@ int dp_check_optimization_collision(const dp_config* cfg, const dp_env* env, dou
                                     double theta);
 int dp_num_knots(const dp_config* cfg); /* sum of the layers' segment counts (= tf/delta_t + 1 for the defaults) */
 
+int dp_polygon_overlaps_box(const double* p, int nv, double cx, double cy, double half); /* polygon2d.cpp:150-165 */
+int dp_polygon_is_point_in(const double* p, int nv, double x, double y);                  /* polygon2d.cpp:120-140 */
+void dp_get_cartesian(int R, const double* ref, double station, double lateral, double xy[2]);
+void dp_path_profile(double dt, int n, const double* x, const double* y, double* speeds, double* accel,
+                     double* kappas);                                                     /* discrete_points_math.cc */
+double dp_slerp(double a0, double t0, double a1, double t1, double t);                    /* math_utils.h:208-225 */
+
 /* DpPlanner::Plan.  trajectory [K][13] in TrajectoryPoint field order (time, s, x, y, theta, kappa, velocity, a,
  * jerk, delta, delta_rate, left_bound, right_bound); waypoints [NT][3] = (s index, l index, current_s) of the
  * optimum (may be NULL).  Returns 1 when min_cost < dp_w_obstacle (the reference's return value), else 0. */
