@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
 ``--impl reference`` legs of bench.py.  Nothing under cilqr_b200/ imports this module.
-PARITY UNPINNED: see the header of cilqr_oracle.h.
+PARITY MOSTLY UNPINNED (two primitives are pinned against the compiled reference): see the header of
+cilqr_oracle.h.
 """
 from __future__ import annotations
 

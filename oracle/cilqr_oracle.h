@@ -7,11 +7,14 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
  * (cilqr_b200/csrc) never links, includes or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors for this path, and
- * cannot be compiled here (needs ROS, Eigen, OpenCV -- none installed).  This restatement follows
- * the reference source line by line (citations at each function); it is cross-checked against an
- * independent NumPy restatement (oracle/cilqr_numpy.py) and against analytic known-answer tests
- * (tests/test_oracle_*.py).
+ * PARITY MOSTLY UNPINNED: the reference ships no tests, fixtures or golden vectors for this path, and
+ * ilqr_optimizer.cc / vehicle_model.cc / barrier_function.h cannot be compiled here (they need ROS and Eigen --
+ * neither installed).  This restatement follows the reference source line by line (citations at each
+ * function); it is cross-checked against an independent NumPy restatement (oracle/cilqr_numpy.py) and against
+ * analytic known-answer tests (tests/test_oracle_*.py).  Pinned against the reference's own compiled code
+ * (oracle/_ref, tests/test_reference_pins.py) are the two pieces of the path that build without those
+ * libraries: NormalizeAngle (math_utils.cpp:53-59) and LineSegment2d::DistanceTo (line_segment2d.cpp:61-75),
+ * the distance FindNeastLaneSegment minimises.
  *
  * The one deliberate deviation: `iqr` declares R uninitialised and sets only its diagonal
  * (ilqr_optimizer.cc:811-813); the off-diagonals are indeterminate in the reference, 0 here.

@@ -10,9 +10,13 @@
  *
  * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (same rule as cilqr_oracle.h).
  *
- * PARITY UNPINNED: the reference ships no tests or fixtures for the DP planner and cannot be built here
- * (ROS/Eigen/OpenCV).  The restatement follows the source line by line and is checked by known-answer and
- * property tests (tests/test_dp_oracle.py).
+ * PARITY PINNED AGAINST THE REFERENCE ITSELF: the reference's own dp_planner.cpp, environment.cpp, geometry,
+ * reference-line and path-profile sources compile without ROS / Eigen / OpenCV once the visualization header is
+ * replaced by a no-op stand-in (oracle/Makefile target `_ref`, wrappers oracle/ref_*_wrapper.cc).  tests/
+ * test_reference_pins.py runs the reference's DpPlanner::Plan and Environment::CheckOptimizationCollision on the
+ * same scenes: return value and every field of every trajectory point are bit-identical, and so is the committed
+ * fixture tests/golden/dp_golden_v1.npz.  Additionally cross-checked against an independent Python restatement
+ * (oracle/dp_python.py) and known-answer tests (tests/test_dp_oracle.py).
  */
 #ifndef DP_ORACLE_H_
 #define DP_ORACLE_H_
