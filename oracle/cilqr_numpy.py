@@ -272,7 +272,12 @@ class Solver:
             self.Ks[i], self.ks[i] = K, k
             Vx = Qx + K.T @ Quu @ k + K.T @ Qu + Qux.T @ k
             Vxx = Qxx + K.T @ Quu @ K + K.T @ Qux + Qux.T @ K
-            Vxx = 0.5 * (Vxx + Vxx.T)
+            # `Vxx = 0.5 * (Vxx + Vxx.transpose())` (:381) is assigned coefficient by coefficient, column-major,
+            # without a temporary (no product in it): the upper triangle reads already-overwritten entries (Q22)
+            Vxx = Vxx.copy()
+            for q in range(6):
+                for r in range(6):
+                    Vxx[r, q] = 0.5 * (Vxx[r, q] + Vxx[q, r])
             # `auto Qu`, `auto Quu` are lazy Eigen expressions (ilqr_optimizer.cc:349,352): at
             # :383-384 they are re-evaluated with the already-updated Vx / Vxx.
             Qu_l = self.Ju[i] + B.T @ Vx

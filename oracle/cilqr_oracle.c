@@ -669,8 +669,13 @@ void cilqr_oracle_ctx_backward(cilqr_oracle_ctx* c, double lambda, double* Ks_ou
     mat_mul(QuxT, Kg, c36, 6, 2, 6);
     for (int r = 0; r < 36; ++r) Vxx_new[r] = Qxx[r] + a36[r] + b36[r] + c36[r];
     memcpy(Vx, Vx_new, sizeof(Vx));
-    for (int r = 0; r < 6; ++r)
-      for (int q = 0; q < 6; ++q) Vxx[r * 6 + q] = 0.5 * (Vxx_new[r * 6 + q] + Vxx_new[q * 6 + r]);
+    /* `Vxx = 0.5 * (Vxx + Vxx.transpose())` (:381) has no product in it, so Eigen assigns it coefficient by
+     * coefficient, column-major, WITHOUT a temporary: the upper triangle reads lower-triangle entries that have
+     * already been overwritten (quirk Q22).  The result differs from the exact mean only by the rounding-level
+     * asymmetry of Vxx, but it is what the reference computes. */
+    memcpy(Vxx, Vxx_new, sizeof(double) * 36);
+    for (int q = 0; q < 6; ++q)
+      for (int r = 0; r < 6; ++r) Vxx[r * 6 + q] = 0.5 * (Vxx[r * 6 + q] + Vxx[q * 6 + r]);
 
     /* :383-384 -- Qu and Quu are lazy expressions, re-evaluated here with the UPDATED Vx / Vxx */
     double Qu_new[2], Quu_new[4];

@@ -16,8 +16,8 @@ _lib = None
 
 
 def available() -> bool:
-    return (os.path.exists(LIB_PATH) and os.path.exists(os.path.join(_HERE, "_ref", "libcilqr_ref_dp.so"))) or \
-        os.path.isdir(REFERENCE_ROOT)
+    return all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
+               ("libcilqr_ref_geom.so", "libcilqr_ref_dp.so", "libcilqr_ref_solver.so")) or os.path.isdir(REFERENCE_ROOT)
 
 
 def lib():
@@ -144,3 +144,56 @@ def road_barrier(ref):
     n = dp_lib().ref_road_barrier(len(ref), ref.ctypes.data, out.ctypes.data, cap)
     assert n >= 0
     return out[:n]
+
+
+# ---- the reference's own CILQR solver (oracle/_ref/libcilqr_ref_solver.so, compiled against Eigen-lite) ------------
+SOLVER_LIB_PATH = os.path.join(_HERE, "_ref", "libcilqr_ref_solver.so")
+_slib = None
+
+
+def solver_lib():
+    global _slib
+    if _slib is None:
+        if not os.path.exists(SOLVER_LIB_PATH):
+            subprocess.check_call(["make", "-C", _HERE, "_ref"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(SOLVER_LIB_PATH)
+        d, i, p = C.c_double, C.c_int, C.c_void_p
+        L.ref_ilqr_solve.argtypes = [d, i, i, i, i, p, p, p, p, p, p, p, p, p, p, p, i, p, p]
+        L.ref_dynamics.argtypes = [d, p, p, p]
+        L.ref_dynamics.restype = None
+        L.ref_dynamics_jacobian.argtypes = [d, p, p, p, p]
+        L.ref_dynamics_jacobian.restype = None
+        L.ref_barrier_value.argtypes = [d]
+        L.ref_barrier_value.restype = d
+        _slib = L
+    return _slib
+
+
+def ilqr_solve(batch, b: int, dt: float = 0.1):
+    """The reference's IlqrOptimizer on scenario b of a ScenarioBatch -> dict(states, controls, init_states,
+    init_controls, cost_hist [n,5], n_iter_trajs)."""
+    N, K = batch.N, batch.N + 1
+    X, U, X0, U0 = np.zeros((K, 6)), np.zeros((N, 2)), np.zeros((K, 6)), np.zeros((N, 2))
+    ch = np.zeros((1024, 5))
+    nc, ni = C.c_int(), C.c_int()
+    arrs = [_f(batch.start[b]), _f(batch.coarse[b]), _f(batch.corridor[b]),
+            np.ascontiguousarray(batch.corridor_cnt[b], np.int32), _f(batch.lane_left[b]), _f(batch.lane_right[b])]
+    rc = solver_lib().ref_ilqr_solve(dt, N, batch.M_max, batch.lane_left.shape[1], batch.lane_right.shape[1],
+                                     *[a.ctypes.data for a in arrs], X.ctypes.data, U.ctypes.data, X0.ctypes.data,
+                                     U0.ctypes.data, ch.ctypes.data, len(ch), C.byref(nc), C.byref(ni))
+    if rc != 0:
+        raise RuntimeError(f"ref_ilqr_solve failed: {rc}")
+    return dict(states=X, controls=U, init_states=X0, init_controls=U0, cost_hist=ch[:nc.value].copy(),
+                n_iter_trajs=ni.value)
+
+
+def dynamics(x, u, dt: float = 0.1):
+    x, u, out = _f(x), _f(u), np.zeros(6)
+    solver_lib().ref_dynamics(dt, x.ctypes.data, u.ctypes.data, out.ctypes.data)
+    return out
+
+
+def dynamics_jacobian(x, u, dt: float = 0.1):
+    x, u, A, B = _f(x), _f(u), np.zeros((6, 6)), np.zeros((6, 2))
+    solver_lib().ref_dynamics_jacobian(dt, x.ctypes.data, u.ctypes.data, A.ctypes.data, B.ctypes.data)
+    return A, B

@@ -213,3 +213,62 @@ def test_known_answer_scenes_on_the_reference():
     assert ok and np.allclose(tr[17:, 6], 10.0) and np.allclose(tr[:, 3], 0.0)
     ok2, traj, cost, wp = dp.plan(dp.Scene(line), 0.0, 0.0, 0.0)
     assert ok2 and np.array_equal(tr, traj[:, :11])
+
+
+# ---- the reference's own CILQR solver (ilqr_optimizer.cc, vehicle_model.cc, barrier_function.h compiled unmodified
+# ---- against the Eigen-lite stand-in of oracle/ref_stubs) ---------------------------------------------------------
+def test_dynamics_and_jacobian_equal_the_reference(oracle):
+    L, p = oracle.lib(), oracle.default_params()
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        x = np.array([rng.normal(0, 20), rng.normal(0, 20), rng.uniform(-7, 7), rng.uniform(0, 20), rng.uniform(-5, 5),
+                      rng.uniform(-0.9, 0.9)])
+        u = np.array([rng.uniform(-10, 10), rng.uniform(-0.3, 0.3)])
+        out, A, B = np.zeros(6), np.zeros(36), np.zeros(12)
+        dp_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        L.cilqr_oracle_dynamics(C.byref(p), dp_(x), dp_(u), dp_(out))
+        assert np.array_equal(out, ref.dynamics(x, u))
+        L.cilqr_oracle_dynamics_jacobian(C.byref(p), dp_(x), dp_(u), dp_(A), dp_(B))
+        Ar, Br = ref.dynamics_jacobian(x, u)
+        assert np.array_equal(A.reshape(6, 6), Ar) and np.array_equal(B.reshape(6, 2), Br)
+
+
+def test_barrier_value_equals_the_reference(oracle):
+    L, p = oracle.lib(), oracle.default_params()
+    R = ref.solver_lib()
+    for g in np.r_[np.linspace(-5, 1, 400), [-0.01, -0.0100001, -0.0099999, 0.0, 1e-12, -1e-12]]:
+        assert L.cilqr_oracle_barrier_value(C.byref(p), float(g)) == R.ref_barrier_value(float(g))
+
+
+def _solve_both(oracle, batch, b):
+    r = ref.ilqr_solve(batch, b)
+    o = oracle.solve(batch, b, hist=True)
+    return r, o
+
+
+@pytest.mark.parametrize("seed,B,N,road", [(11, 24, 50, "gentle"), (12, 8, 100, "gentle"), (13, 12, 80, "shipped"),
+                                           (14, 6, 200, "gentle"), (15, 16, 30, "shipped")])
+def test_whole_solves_equal_the_reference_bit_for_bit(oracle, seed, B, N, road):
+    """IlqrOptimizer::Optimize of the reference itself against the oracle: the iqr initial guess, the returned
+    states and controls, and the five-component cost of every accepted iterate (cost()), all bit-identical."""
+    batch = scenarios.generate(seed, 0, B, N=N, road_name=road)
+    exits = set()
+    for b in range(B):
+        r, o = _solve_both(oracle, batch, b)
+        assert np.array_equal(r["init_states"], o["init_states"]) and np.array_equal(r["init_controls"], o["init_controls"])
+        assert len(r["cost_hist"]) == len(o["cost_hist"]) and np.array_equal(r["cost_hist"], np.array(o["cost_hist"]))
+        assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
+        exits.add(o["status"])
+    print(f"\\n[solver pin] seed {seed} N={N} {road}: {B} solves bit-identical; exits seen {sorted(exits)}")
+
+
+def test_solver_fixture_equals_the_reference():
+    """tests/golden/cilqr_golden_v1.npz (a GPU-test target) holds exactly what the reference's solver returns."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cilqr_golden_v1.npz"))
+    batch = scenarios.ScenarioBatch(int(z["N"]), int(z["M_max"]), int(z["S"]), z["start"], z["coarse"], z["corridor"],
+                                    z["corridor_cnt"], z["lane_left"], z["lane_right"])
+    for b in range(batch.B):
+        r = ref.ilqr_solve(batch, b)
+        assert np.array_equal(r["states"], z["states"][b]) and np.array_equal(r["controls"], z["controls"][b])
+        assert np.array_equal(r["init_states"], z["init_states"][b])
