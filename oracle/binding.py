@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
 ``--impl reference`` legs of bench.py.  Nothing under cilqr_b200/ imports this module.
-PARITY MOSTLY UNPINNED (two primitives are pinned against the compiled reference): see the header of
-cilqr_oracle.h.
+Parity: pinned bit for bit against the reference's own solver source compiled with an Eigen stand-in (see the
+header of cilqr_oracle.h and tests/test_reference_pins.py).
 """
 from __future__ import annotations
 

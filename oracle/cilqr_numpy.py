@@ -1,9 +1,9 @@
 """Second, independent CPU restatement of mpt0816/Cilqr's CILQR solve in NumPy float64.
 
-TEST INFRASTRUCTURE ONLY (see oracle/cilqr_oracle.h).  PARITY UNPINNED: the reference ships no
-tests or golden vectors and cannot be built here; this file exists so that two restatements written
-in different styles (the structured C in cilqr_oracle.c, dense 6x6 linear algebra here) pin each
-other.  Pure-Python loops: use it for small horizons / a handful of scenarios only.
+TEST INFRASTRUCTURE ONLY (see oracle/cilqr_oracle.h).  The reference ships no tests or golden vectors;
+this file exists so that two restatements written in different styles (the structured C in
+cilqr_oracle.c, dense 6x6 linear algebra here) check each other; the C one is additionally pinned bit
+for bit against the reference's own solver source (tests/test_reference_pins.py).  Pure-Python loops: use it for small horizons / a handful of scenarios only.
 
 Written from the reference sources, dense like the Eigen code (no sparsity shortcuts):
   algorithm/ilqr/ilqr_optimizer.cc   Plan :53-95, Optimize :154-320, Backward :334-390,

@@ -7,14 +7,18 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
  * (cilqr_b200/csrc) never links, includes or calls anything in oracle/.
  *
- * PARITY MOSTLY UNPINNED: the reference ships no tests, fixtures or golden vectors for this path, and
- * ilqr_optimizer.cc / vehicle_model.cc / barrier_function.h cannot be compiled here (they need ROS and Eigen --
- * neither installed).  This restatement follows the reference source line by line (citations at each
- * function); it is cross-checked against an independent NumPy restatement (oracle/cilqr_numpy.py) and against
- * analytic known-answer tests (tests/test_oracle_*.py).  Pinned against the reference's own compiled code
- * (oracle/_ref, tests/test_reference_pins.py) are the two pieces of the path that build without those
- * libraries: NormalizeAngle (math_utils.cpp:53-59) and LineSegment2d::DistanceTo (line_segment2d.cpp:61-75),
- * the distance FindNeastLaneSegment minimises.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCE (with one stand-in): Eigen, ROS and OpenCV are not installed,
+ * but ilqr_optimizer.cc, vehicle_model.cc and barrier_function.h compile UNMODIFIED against the stand-ins of
+ * oracle/ref_stubs (an "Eigen-lite" header reproducing the Eigen 3.4 semantics the solver depends on -- lazy `auto`
+ * expressions, coefficient order of products, assignment aliasing rules, closed-form 2x2 inverse --, no-op ROS
+ * logging macros, empty OpenCV headers): oracle/Makefile target `_ref`, wrapper oracle/ref_solver_wrapper.cc.
+ * tests/test_reference_pins.py runs the reference's IlqrOptimizer::Optimize and this restatement on the same
+ * scenarios: the iqr initial guess, the returned states and controls and the five-component cost of every accepted
+ * iterate are BIT-IDENTICAL (hundreds of solves, horizons 30-200, both roads, lambda-overflow exits included), and
+ * so are Dynamics, DynamicsJacbian, the barrier value, NormalizeAngle and LineSegment2d::DistanceTo.  What the pin
+ * cannot cover is Eigen itself: the stand-in's semantics come from knowledge of the Eigen 3.4 sources.
+ * Further cross-checks: an independent NumPy restatement (oracle/cilqr_numpy.py) and analytic known-answer tests
+ * (tests/test_oracle_*.py).
  *
  * The one deliberate deviation: `iqr` declares R uninitialised and sets only its diagonal
  * (ilqr_optimizer.cc:811-813); the off-diagonals are indeterminate in the reference, 0 here.

@@ -1,5 +1,6 @@
 """Known-answer and property tests of the DP planner oracle (oracle/dp_oracle.c; reference
-algorithm/planner/dp_planner.cpp).  The reference ships no fixtures for this path (parity unpinned)."""
+algorithm/planner/dp_planner.cpp).  The reference ships no fixtures for this path; the pin against the reference's own compiled planner is
+tests/test_reference_pins.py."""
 import numpy as np
 import pytest
 
