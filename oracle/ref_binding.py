@@ -17,7 +17,7 @@ _lib = None
 
 def available() -> bool:
     return all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
-               ("libcilqr_ref_geom.so", "libcilqr_ref_dp.so", "libcilqr_ref_solver.so")) or os.path.isdir(REFERENCE_ROOT)
+               ("libcilqr_ref_geom.so", "libcilqr_ref_dp.so", "libcilqr_ref_solver.so", "libcilqr_ref_corridor.so")) or os.path.isdir(REFERENCE_ROOT)
 
 
 def lib():
@@ -197,3 +197,38 @@ def dynamics_jacobian(x, u, dt: float = 0.1):
     x, u, A, B = _f(x), _f(u), np.zeros((6, 6)), np.zeros((6, 2))
     solver_lib().ref_dynamics_jacobian(dt, x.ctypes.data, u.ctypes.data, A.ctypes.data, B.ctypes.data)
     return A, B
+
+
+# ---- the reference's own Corridor (oracle/_ref/libcilqr_ref_corridor.so) -----------------------------------------
+CORRIDOR_LIB_PATH = os.path.join(_HERE, "_ref", "libcilqr_ref_corridor.so")
+_clib = None
+
+
+def corridor_lib():
+    global _clib
+    if _clib is None:
+        if not os.path.exists(CORRIDOR_LIB_PATH):
+            subprocess.check_call(["make", "-C", _HERE, "_ref"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(CORRIDOR_LIB_PATH)
+        d, i, p = C.c_double, C.c_int, C.c_void_p
+        L.ref_build_corridor.argtypes = [d, d, d, i, p, p, p, i]
+        L.ref_lane_constraints.argtypes = [i, p, i, p, i]
+        _clib = L
+    return _clib
+
+
+def build_corridor(x, y, theta, obstacle_points, cap: int = 128):
+    """The reference's AddCorridorPoints + BuildCorridor for one knot -> (m, constraints [m,3], polygon [m,2]);
+    m = -1 when BuildCorridor returns false."""
+    pts = _f(obstacle_points).reshape(-1, 2)
+    cons, poly = np.zeros((cap, 3)), np.zeros((cap, 2))
+    m = corridor_lib().ref_build_corridor(float(x), float(y), float(theta), len(pts), pts.ctypes.data,
+                                          cons.ctypes.data, poly.ctypes.data, cap)
+    return m, cons[:max(m, 0)].copy(), poly[:max(m, 0)].copy()
+
+
+def lane_constraints(boundary, is_left: bool, cap: int = 1024):
+    bd = _f(boundary).reshape(-1, 2)
+    out = np.zeros((cap, 7))
+    n = corridor_lib().ref_lane_constraints(len(bd), bd.ctypes.data, int(is_left), out.ctypes.data, cap)
+    return n, out[:max(n, 0)].copy()

@@ -14,7 +14,7 @@ using namespace planning;
 
 namespace planning {
 namespace visualization {
-Color Color::Grey, Color::Magenta, Color::White;
+Color Color::Grey, Color::Magenta, Color::White, Color::Cyan;
 }
 }  // namespace planning
 

@@ -1,2 +1,3 @@
-// empty stand-in: corridor.h includes OpenCV but declares nothing with it
+// see opencv2/opencv.hpp in this directory
 #pragma once
+#include <opencv2/opencv.hpp>

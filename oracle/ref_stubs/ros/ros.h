@@ -3,3 +3,9 @@
 #define ROS_ERROR(...) ((void)0)
 #define ROS_WARN(...) ((void)0)
 #define ROS_INFO(...) ((void)0)
+namespace ros {
+struct Duration {
+  explicit Duration(double) {}
+  void sleep() {}
+};
+}  // namespace ros

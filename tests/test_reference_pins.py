@@ -272,3 +272,49 @@ def test_solver_fixture_equals_the_reference():
         r = ref.ilqr_solve(batch, b)
         assert np.array_equal(r["states"], z["states"][b]) and np.array_equal(r["controls"], z["controls"][b])
         assert np.array_equal(r["init_states"], z["init_states"][b])
+
+
+# ---- the reference's own Corridor (corridor.cc compiled unmodified; cv::convexHull = the cv2-pinned restatement) ---
+def test_build_corridor_equals_the_reference():
+    from oracle import corridor_binding as cb
+    M = 64
+    knots = 0
+    for seed, B, N, n_obs in ((5, 12, 50, 20), (6, 8, 80, 11), (7, 6, 30, 5)):
+        _, ci = scenarios.generate_with_obstacles(seed, 0, B, N=N, n_obs=n_obs)
+        cor, cnt, poly, code = cb.plan_batch(ci.traj, ci.obs_points, ci.obs_cnt, M)
+        for b in range(ci.B):
+            for k in range(ci.K):
+                n = int(ci.obs_cnt[b, k])
+                m, cons, pl = ref.build_corridor(*ci.traj[b, k], ci.obs_points[b, k, :n], cap=M)
+                assert m == cnt[b, k] and code[b, k] == 0
+                assert np.array_equal(cons, cor[b, k, :m]) and np.array_equal(pl, poly[b, k, :m])
+                knots += 1
+    assert knots > 1400
+    # an empty obstacle set gives the box of AddCorridorPoints
+    m, cons, _ = ref.build_corridor(3.0, -1.0, 0.4, np.zeros((0, 2)))
+    rc, cons2, _ = cb.build_corridor(3.0, -1.0, cb.add_corridor_points(3.0, -1.0, 0.4))
+    assert m == 4 and rc == 0 and np.array_equal(cons, cons2)
+
+
+def test_corridor_fixture_equals_the_reference():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corridor_golden_v1.npz"))
+    for b in range(z["traj"].shape[0]):
+        for k in range(z["traj"].shape[1]):
+            n = int(z["obs_cnt"][b, k])
+            m, cons, pl = ref.build_corridor(*z["traj"][b, k], z["obs_points"][b, k, :n])
+            assert m == z["corridor_cnt"][b, k]
+            assert np.array_equal(cons, z["corridor"][b, k, :m]) and np.array_equal(pl, z["polygon"][b, k, :m])
+
+
+def test_lane_constraints_equal_the_reference():
+    from oracle import corridor_binding as cb
+    for name in ("gentle", "shipped"):
+        rd = scenarios.road(name)
+        s = np.arange(rd.s_min, rd.s_max + 1e-9, 0.1)
+        for lat, left in ((2.5, True), (-6.0, False), (0.7, True)):
+            bd = np.stack(rd.frenet_to_xy(s, lat), axis=1)
+            n, seg = ref.lane_constraints(bd, left)
+            n2, seg2 = cb.lane_constraints(bd, left)
+            assert n == n2 and np.array_equal(seg, seg2)
+    assert ref.lane_constraints(np.zeros((5, 2)), True)[0] == -1 == cb.lane_constraints(np.zeros((5, 2)), True)[0]
