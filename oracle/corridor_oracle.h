@@ -8,12 +8,17 @@
  *
  * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (same rule as cilqr_oracle.h).
  *
- * PINNING: the convex hull restatement (corr_convex_hull_f32) is pinned index-for-index against the
- * real OpenCV (python cv2 4.13.0 in this image) by tests/test_corridor_oracle.py on random, gridded,
- * duplicated and collinear inputs, and through committed fixtures (tests/golden/corridor_hull_v1.npz).
- * The arithmetic around the hulls cannot be pinned (the reference needs ROS/Eigen/OpenCV C++ to
- * build); it is cross-checked against an independent NumPy float32/float64 restatement that calls
- * cv2.convexHull itself (oracle/corridor_numpy.py).
+ * PINNING, in two steps that together cover the whole path:
+ *  (1) the convex hull restatement (corr_convex_hull_f32) is pinned index-for-index against the real OpenCV
+ *      (python cv2 4.13.0 in this image) by tests/test_corridor_oracle.py on random, gridded, duplicated and
+ *      collinear inputs, and through committed cv2 outputs (tests/golden/corridor_hull_v1.npz);
+ *  (2) everything around the hulls is pinned against the REFERENCE'S OWN corridor.cc, compiled unmodified into
+ *      oracle/_ref (Makefile target `_ref`, wrapper oracle/ref_corridor_wrapper.cc) against an Eigen stand-in,
+ *      no-op ROS / visualization headers and an OpenCV header whose cv::convexHull is (1):
+ *      tests/test_reference_pins.py compares AddCorridorPoints + BuildCorridor on > 1400 knots, the committed
+ *      fixture tests/golden/corridor_golden_v1.npz and the lane constraints -- all bit-identical.
+ * Additionally cross-checked against an independent NumPy float32/float64 restatement that calls cv2.convexHull
+ * itself (oracle/corridor_numpy.py).
  */
 #ifndef CORRIDOR_ORACLE_H_
 #define CORRIDOR_ORACLE_H_
