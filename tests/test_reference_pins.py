@@ -318,3 +318,16 @@ def test_lane_constraints_equal_the_reference():
             n2, seg2 = cb.lane_constraints(bd, left)
             assert n == n2 and np.array_equal(seg, seg2)
     assert ref.lane_constraints(np.zeros((5, 2)), True)[0] == -1 == cb.lane_constraints(np.zeros((5, 2)), True)[0]
+
+
+def test_solver_exits_equal_the_reference(oracle):
+    """The rarer exits of Optimize -- absolute-tolerance convergence (:281,287) and the lambda-overflow "unsolved"
+    exit (:302-307) -- pinned on scenarios selected for them (the relative-tolerance exit dominates the rest)."""
+    batch = scenarios.generate(32, 0, 2048, N=30, road_name="shipped")
+    picks = {0: [247, 959, 1022, 1550], 3: [34, 513, 1313, 1420]}
+    for status, ids in picks.items():
+        for b in ids:
+            r, o = _solve_both(oracle, batch, b)
+            assert o["status"] == status
+            assert len(r["cost_hist"]) == len(o["cost_hist"]) and np.array_equal(r["cost_hist"], np.array(o["cost_hist"]))
+            assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
