@@ -15,7 +15,8 @@ value     : converged trajectories / s, inputs resident in HBM, CUDA events arou
 e2e       : same metric through the host C ABI (cilqr_plan_batch): pinned host buffers in, H2D +
             solve + D2H inside the timed region (one launch fed by chunked copies behind a watermark)
 roofline  : algorithmic HBM bytes of the solve kernel / its CUDA-event time vs MEASURED_PEAKS.json
-cpu_baseline: the oracle (a port: the reference cannot be built here) on a bounded sample
+cpu_baseline: the oracle (a port, bit-identical to the reference's own solver source compiled against an
+            Eigen stand-in in oracle/_ref, whose rate is reported beside it) on a bounded sample
 """
 from __future__ import annotations
 
