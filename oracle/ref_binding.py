@@ -159,6 +159,7 @@ def solver_lib():
         L = C.CDLL(SOLVER_LIB_PATH)
         d, i, p = C.c_double, C.c_int, C.c_void_p
         L.ref_ilqr_solve.argtypes = [d, i, i, i, i, p, p, p, p, p, p, p, p, p, p, p, i, p, p]
+        L.ref_ilqr_solve_cfg.argtypes = [d, i, i, i, i, p, p, p, p, p, p, p, p, p, p, p, i, p, p, p]
         L.ref_dynamics.argtypes = [d, p, p, p]
         L.ref_dynamics.restype = None
         L.ref_dynamics_jacobian.argtypes = [d, p, p, p, p]
@@ -169,18 +170,20 @@ def solver_lib():
     return _slib
 
 
-def ilqr_solve(batch, b: int, dt: float = 0.1):
+def ilqr_solve(batch, b: int, dt: float = 0.1, overrides=None):
     """The reference's IlqrOptimizer on scenario b of a ScenarioBatch -> dict(states, controls, init_states,
-    init_controls, cost_hist [n,5], n_iter_trajs)."""
+    init_controls, cost_hist [n,5], n_iter_trajs).  overrides = (max_iter_num, abs_cost_tol, rel_cost_tol)."""
     N, K = batch.N, batch.N + 1
     X, U, X0, U0 = np.zeros((K, 6)), np.zeros((N, 2)), np.zeros((K, 6)), np.zeros((N, 2))
     ch = np.zeros((1024, 5))
     nc, ni = C.c_int(), C.c_int()
     arrs = [_f(batch.start[b]), _f(batch.coarse[b]), _f(batch.corridor[b]),
             np.ascontiguousarray(batch.corridor_cnt[b], np.int32), _f(batch.lane_left[b]), _f(batch.lane_right[b])]
-    rc = solver_lib().ref_ilqr_solve(dt, N, batch.M_max, batch.lane_left.shape[1], batch.lane_right.shape[1],
-                                     *[a.ctypes.data for a in arrs], X.ctypes.data, U.ctypes.data, X0.ctypes.data,
-                                     U0.ctypes.data, ch.ctypes.data, len(ch), C.byref(nc), C.byref(ni))
+    ov = _f(overrides) if overrides is not None else None
+    rc = solver_lib().ref_ilqr_solve_cfg(dt, N, batch.M_max, batch.lane_left.shape[1], batch.lane_right.shape[1],
+                                         *[a.ctypes.data for a in arrs], X.ctypes.data, U.ctypes.data, X0.ctypes.data,
+                                         U0.ctypes.data, ch.ctypes.data, len(ch), C.byref(nc), C.byref(ni),
+                                         ov.ctypes.data if ov is not None else None)
     if rc != 0:
         raise RuntimeError(f"ref_ilqr_solve failed: {rc}")
     return dict(states=X, controls=U, init_states=X0, init_controls=U0, cost_hist=ch[:nc.value].copy(),

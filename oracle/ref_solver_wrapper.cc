@@ -77,14 +77,21 @@ extern "C" {
 
 // The whole solve.  states [K][6], controls [N][2] of the returned trajectory; init_states / init_controls of
 // iter_trajs[0] (the iqr initial guess); cost_hist [cap][5] = cost(); returns 0.
-int ref_ilqr_solve(double dt, int N, int M_max, int S_left, int S_right, const double* start, const double* coarse,
-                   const double* corridor, const int* cnt, const double* lane_left, const double* lane_right,
-                   double* states, double* controls, double* init_states, double* init_controls, double* cost_hist,
-                   int cap, int* n_cost, int* n_iter_trajs) {
+// overrides: NULL, or {max_iter_num, abs_cost_tol, rel_cost_tol} (IlqrConfig, planner_config.h:63-66) to reach the
+// exits the default tolerances make rare.
+int ref_ilqr_solve_cfg(double dt, int N, int M_max, int S_left, int S_right, const double* start, const double* coarse,
+                       const double* corridor, const int* cnt, const double* lane_left, const double* lane_right,
+                       double* states, double* controls, double* init_states, double* init_controls, double* cost_hist,
+                       int cap, int* n_cost, int* n_iter_trajs, const double* overrides) {
   Quiet q;
   const int K = N + 1;
   Problem p = make_problem(N, M_max, S_left, S_right, start, coarse, corridor, cnt, lane_left, lane_right);
   IlqrConfig config;
+  if (overrides) {
+    config.max_iter_num = (int)overrides[0];
+    config.abs_cost_tol = overrides[1];
+    config.rel_cost_tol = overrides[2];
+  }
   VehicleParam vehicle;
   IlqrOptimizer opt(config, vehicle, N * dt + 0.5 * dt, dt);  // num_of_knots_ = floor(horizon / dt + 1) = N + 1
   if (opt.num_of_knots_ != K) return -1;
@@ -120,6 +127,14 @@ int ref_ilqr_solve(double dt, int N, int M_max, int S_left, int S_right, const d
     c[4] = ch[i].lane_boundary_cost;
   }
   return 0;
+}
+
+int ref_ilqr_solve(double dt, int N, int M_max, int S_left, int S_right, const double* start, const double* coarse,
+                   const double* corridor, const int* cnt, const double* lane_left, const double* lane_right,
+                   double* states, double* controls, double* init_states, double* init_controls, double* cost_hist,
+                   int cap, int* n_cost, int* n_iter_trajs) {
+  return ref_ilqr_solve_cfg(dt, N, M_max, S_left, S_right, start, coarse, corridor, cnt, lane_left, lane_right, states,
+                            controls, init_states, init_controls, cost_hist, cap, n_cost, n_iter_trajs, nullptr);
 }
 
 // VehicleModel::Dynamics / DynamicsJacbian (vehicle_model.cc:21-121)

@@ -331,3 +331,22 @@ def test_solver_exits_equal_the_reference(oracle):
             assert o["status"] == status
             assert len(r["cost_hist"]) == len(o["cost_hist"]) and np.array_equal(r["cost_hist"], np.array(o["cost_hist"]))
             assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
+
+
+def test_max_iteration_exit_and_long_solves_equal_the_reference(oracle):
+    """With the cost tolerances switched off the solve runs to `max_iter_num` (:312-316) or to the lambda-overflow
+    exit -- up to 200 iterations of accumulated rounding, still bit-identical.  (The gradient-norm exit :236-241 needs
+    lambda < 1e-5 together with a tiny gradient and was never reached on any generated scenario; it is the one exit
+    without a pin.)"""
+    batch = scenarios.generate(41, 0, 10, N=30)
+    seen = set()
+    for mi, at, rt in ((3, 1e-2, 1e-2), (200, 0.0, 0.0)):
+        p = oracle.default_params()
+        p.max_iter_num, p.abs_cost_tol, p.rel_cost_tol = mi, at, rt
+        for b in range(batch.B):
+            o = oracle.solve(batch, b, params=p, hist=True)
+            r = ref.ilqr_solve(batch, b, overrides=(mi, at, rt))
+            assert len(r["cost_hist"]) == len(o["cost_hist"]) and np.array_equal(r["cost_hist"], np.array(o["cost_hist"]))
+            assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
+            seen.add(o["status"])
+    assert 4 in seen and 3 in seen
