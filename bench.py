@@ -186,7 +186,7 @@ def corridor_measurement(solver, a, dev, stream, peak):
             "note": f"{base} generated scenarios tiled x{rep} on the device; one thread per knot, point_cap {cfg.point_cap}"}
 
 
-def dp_measurement(solver, a, dev, stream):
+def dp_measurement(solver, a, dev, stream, peak=None):
     """Side measurement (rank 0): the batched DpPlanner::Plan kernel (SURVEY 8(f) rank 2, the first stage of the
     planner) on random_pedestrian-style scenes, next to its CPU restatement on one host core.  Not part of `value`."""
     import torch
@@ -236,8 +236,18 @@ def dp_measurement(solver, a, dev, stream):
         cpu_s = time.perf_counter() - t0
     same = bool(np.array_equal(np.array(okc, bool), ok[:n_cpu].cpu().numpy().astype(bool)))
     impl = ("the reference's own DpPlanner::Plan (oracle/_ref)" if kind == "reference" else "oracle/dp_oracle.c")
+    # algorithmic bytes: a scene's start + obstacle polygons (static, and every sample of the dynamic ones) in, the
+    # coarse trajectory + flag out; the centre line and the barrier are shared by the batch (L2 resident)
+    per_scene = 24 + db.static_poly[0].nbytes + db.dyn_poly[0].nbytes + db.dyn_time[0].nbytes + K * 6 * 8 + 4
+    alg = per_scene * B + db.ref.nbytes + barrier.nbytes
+    roof = None
+    if peak:
+        roof = {"bound": "hbm", "achieved": alg / kms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / kms / 1e6 / peak,
+                "algorithmic_bytes_per_launch": int(alg), "traffic": None,
+                "note": "compute / latency bound (19 670 transitions x ~10 collision-checked points per scene); the HBM "
+                        "fraction is reported as defined, not as the limiter"}
     return {"kernel": "dp_plan_kernel", "scenes_per_launch": B, "kernel_ms": kms, "traj_per_s": B / kms * 1e3,
-            "planned_ok_fraction": float(ok.double().mean().item()),
+            "planned_ok_fraction": float(ok.double().mean().item()), "roofline": roof,
             "cpu_baseline": {"value": n_cpu / cpu_s, "unit": UNIT, "cores": 1, "kind": kind,
                              "sample": f"first {n_cpu} scenes, {impl}, 1 thread, {cpu_s:.2f} s; "
                                        f"ok flags equal to the GPU's: {same}"},
@@ -471,7 +481,7 @@ def main():
             corridor = corridor_measurement(solver, a, dev, stream, peak)
         dpm = None
         if not a.no_dp:
-            dpm = dp_measurement(solver, a, dev, stream)
+            dpm = dp_measurement(solver, a, dev, stream, peak)
         alg_bytes = scenarios.algorithmic_bytes(N, batch.M_max, batch.S) * B
         achieved = alg_bytes / (kmean_ms * 1e-3) / 1e9
         traffic = None
