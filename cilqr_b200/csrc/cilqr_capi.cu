@@ -33,7 +33,9 @@ constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granul
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  unsigned int* ticket = nullptr;
+  unsigned int* ticket = nullptr;       // device [4]: scenario counter, error bits, scenarios finished, pad
+  unsigned int* flags_host = nullptr;   // pinned [4]: the same words after the launch (host path)
+  int launched_B = -1;                  // batch size of the last launch on this slot (-1: none to check)
   unsigned long long* stats = nullptr;  // scheduler counters of the last launch (cilqr_debug_stats)
   double* ws = nullptr;
   size_t ws_bytes = 0;
@@ -62,6 +64,8 @@ struct cilqr_handle {
   int N_max = 0, M_max = 0, S_max = 0, B_max = 0;
   int chunk = kDefaultChunk;
   bool no_zero_copy = false;  // CILQR_NO_ZERO_COPY=1: always stage outputs on the device (development knob)
+  int watchdog_ms = 4000;     // how long the kernel waits for the host path's watermark (cilqr_debug_host_path)
+  int starve_after = -1;      // test hook: the host path never raises the watermark beyond this many scenarios
   Slot slots[kSlots];
   int64_t launches = 0;
   int last_slot = 0;
@@ -196,8 +200,7 @@ int plan_launch(cilqr_handle* h, int B, int N, int M_max, int S_left, int S_righ
   // warps per CTA: as many per-warp stages as fit the SM's shared memory, at most kCtaWarps
   const int W = std::min(cilqr::kCtaWarps, h->smem_optin / L.sm.total_bytes);
   if (W < 1) return CILQR_E_SMEM;
-  L.warps = W;
-  CK(cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.sm.total_bytes * W));
+  L.warps = W;  // (the kernel's dynamic shared-memory limit was raised to smem_optin once, in cilqr_create)
   // persistent grid: one CTA (W warps) per SM, each owning `ctx` scenario contexts
   L.grid = std::max(1, std::min(B, h->num_sms));
   int ctx = cilqr::kMaxCtx;  // measured best at N = 100 (profiles/): more waiting contexts -> fewer idle warps
@@ -277,7 +280,10 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.ws = s->ws;
   a.ticket = s->ticket;
   a.ready = ready;
+  a.watchdog_ns = (unsigned long long)std::max(1, h->watchdog_ms) * 1000000ull;
   a.stats = s->stats;
+  // an unsolved scenario must be recognisable: every status row starts as the sentinel (all bits set = NaN)
+  CK(cudaMemsetAsync(out->status, 0xff, (size_t)in->B * CILQR_STATUS_DOUBLES * sizeof(double), stream));
   CK(cudaMemsetAsync(s->stats, 0, kStatsWords * sizeof(unsigned long long), stream));
   CK(cudaMemsetAsync(s->stats + 8, 0xff, sizeof(unsigned long long), stream));  // start time: atomicMin
   a.debug = 0;
@@ -301,7 +307,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
     a.dbg.costn = dbg->costn;
     a.dbg.nearest = dbg->nearest;
   }
-  CK(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), stream));
+  CK(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned int), stream));
   CK(cudaEventRecord(s->ev0, stream));
   cilqr::cilqr_solve_kernel<<<L.grid, 32 * L.warps, L.sm.total_bytes * L.warps, stream>>>(a);
   CK(cudaGetLastError());
@@ -309,7 +315,21 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   h->launches += 1;
   h->last_slot = (int)(s - h->slots);
   h->timed = true;
+  s->launched_B = in->B;
   return CILQR_OK;
+}
+
+// After the launch's stream has been synchronised: did every scenario finish, did a watchdog fire?
+int check_launch(cilqr_handle* h, Slot* s, const unsigned int flags[4]) {
+  const int B = s->launched_B;
+  s->launched_B = -1;
+  if (B < 0) return CILQR_OK;
+  if (flags[1] == 0 && flags[2] == (unsigned)B) return CILQR_OK;
+  char buf[200];
+  snprintf(buf, sizeof(buf), "solve launch incomplete: %u of %d scenarios finished, error bits 0x%x (1: input transfer "
+           "starved, 2: idle watchdog, 4: help-board watchdog)", flags[2], B, flags[1]);
+  h->cuda_err = buf;
+  return CILQR_E_TIMEOUT;
 }
 
 }  // namespace
@@ -362,6 +382,8 @@ const char* cilqr_strerror(int code) {
     case CILQR_E_NO_DEVICE: return "no CUDA device of compute capability 10.x (this library has no CPU fallback)";
     case CILQR_E_CAPACITY: return "request exceeds the capacity the handle was created with";
     case CILQR_E_SMEM: return "horizon does not fit the per-warp shared-memory stage";
+    case CILQR_E_TIMEOUT: return "the solve kernel did not finish every scenario (see cilqr_last_cuda_error); "
+                                 "unsolved scenarios carry the NaN sentinel in their status row";
     default: return "unknown error";
   }
 }
@@ -404,10 +426,23 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (make_layout(N_max, M_max, S_max, S_max).total_bytes > h->smem_optin) return bail(CILQR_E_SMEM);
+  // function attributes are per-device state shared by every handle: set them once, to the maximum, so that
+  // handles of different shapes on different host threads cannot shrink each other's limit between a
+  // set-attribute and a launch
+  if (cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) !=
+      cudaSuccess)
+    return bail(CILQR_E_CUDA);
+  if (cudaFuncSetAttribute(corridor::corridor_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           h->smem_optin) != cudaSuccess ||
+      cilqr_internal_dp_set_smem(h->smem_optin) != CILQR_OK)
+    return bail(CILQR_E_CUDA);
+  if (const char* e = getenv("CILQR_WATCHDOG_MS")) h->watchdog_ms = std::max(1, atoi(e));
   for (int i = 0; i < kSlots; ++i) {
     Slot* s = &h->slots[i];
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
-    if (cudaMalloc(&s->ticket, sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->ticket, 4 * sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
+    if (cudaHostAlloc((void**)&s->flags_host, 4 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess)
+      return bail(CILQR_E_CUDA);
     if (cudaMalloc(&s->stats, kStatsWords * sizeof(unsigned long long)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
@@ -425,6 +460,7 @@ void cilqr_destroy(cilqr_handle* h) {
     Slot* s = &h->slots[i];
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ticket) cudaFree(s->ticket);
+    if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->stats) cudaFree(s->stats);
     if (s->ws) cudaFree(s->ws);
     if (s->in_buf) cudaFree(s->in_buf);
@@ -479,13 +515,32 @@ int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in, const C
   cudaFree(tmp);
   if (rc != CILQR_OK) return rc;
   if (e != cudaSuccess) return fail_cuda(h, e, "debug kernel");
-  return CILQR_OK;
+  CK(cudaMemcpy(h->slots[0].flags_host, h->slots[0].ticket, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return check_launch(h, &h->slots[0], h->slots[0].flags_host);
 }
 
 int cilqr_synchronize(cilqr_handle* h) {
   if (!h) return CILQR_E_INVALID;
   CK(cudaSetDevice(h->device));
-  for (int i = 0; i < kSlots; ++i) CK(cudaStreamSynchronize(h->slots[i].stream));
+  int rc = CILQR_OK;
+  for (int i = 0; i < kSlots; ++i) {
+    Slot* s = &h->slots[i];
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->launched_B >= 0) {
+      // (a launch enqueued on a caller stream: the copy below is ordered after it only if the caller has
+      // synchronised that stream, which is the documented contract of cilqr_plan_batch_device)
+      CK(cudaMemcpy(s->flags_host, s->ticket, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+      const int r = check_launch(h, s, s->flags_host);
+      if (r != CILQR_OK) rc = r;
+    }
+  }
+  return rc;
+}
+
+int cilqr_debug_host_path(cilqr_handle* h, int watchdog_ms, int starve_after) {
+  if (!h) return CILQR_E_INVALID;
+  if (watchdog_ms > 0) h->watchdog_ms = watchdog_ms;
+  h->starve_after = starve_after;
   return CILQR_OK;
 }
 
@@ -615,13 +670,15 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   dout.iter_states = (double*)carve(out->iter_states, b_is);
   dout.iter_controls = (double*)carve(out->iter_controls, b_ic);
   dout.hist_len = (int32_t*)carve(out->hist_len, b_hl);
-  // watermark = 0, then the kernel (which waits for the watermark), then the copies that raise it
+  // Order of enqueueing: watermark = 0, then EVERY input chunk with its watermark update on the copy stream,
+  // and only then the kernel on the solve stream.  The kernel therefore never depends on work that is
+  // enqueued after its launch: when launches are synchronous (ncu, CUDA_LAUNCH_BLOCKING=1, a debugger) the
+  // copy stream still runs to completion underneath it.  With pinned inputs the copies are asynchronous, the
+  // kernel starts as soon as the first chunk has landed and the rest of the transfer hides behind the solve;
+  // with pageable inputs cudaMemcpyAsync stages synchronously, so the call degrades to copy-then-solve.
   CK(cudaMemsetAsync(s->ready, 0, sizeof(unsigned int), s->copy_stream));
   CK(cudaEventRecord(s->ev_reset, s->copy_stream));
   CK(cudaStreamWaitEvent(s->stream, s->ev_reset, 0));
-  if (dout.cost_hist) CK(cudaMemsetAsync(dout.cost_hist, 0, b_ch * B, s->stream));
-  rc = launch_solve(h, s, s->stream, &din, &dout, nullptr, s->ready);
-  if (rc != CILQR_OK) return rc;
   cudaError_t ce = cudaSuccess;
   for (int ci = 0; ci < n_chunks && ce == cudaSuccess; ++ci) {
     const size_t b0 = ci ? chunk_end[ci - 1] : 0, nb = chunk_end[ci] - b0;
@@ -635,18 +692,23 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
     h2d(d_cnt, in->corridor_cnt, b_cnt);
     h2d(d_ll, in->lane_left, b_ll);
     h2d(d_lr, in->lane_right, b_lr);
-    s->ready_host[ci] = (unsigned int)(b0 + nb);
+    size_t mark = b0 + nb;
+    if (h->starve_after >= 0) mark = std::min<size_t>(mark, (size_t)h->starve_after);  // test hook
+    s->ready_host[ci] = (unsigned int)mark;
     if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(s->ready, &s->ready_host[ci], sizeof(unsigned int), cudaMemcpyHostToDevice, s->copy_stream);
   }
   if (ce != cudaSuccess) {
-    // release the kernel (it would otherwise wait for its watchdog), then report
-    s->ready_host[0] = 0xffffffffu;
-    cudaMemcpyAsync(s->ready, &s->ready_host[0], sizeof(unsigned int), cudaMemcpyHostToDevice, s->copy_stream);
     cudaStreamSynchronize(s->copy_stream);
-    cudaStreamSynchronize(s->stream);
     return fail_cuda(h, ce, "host-to-device copy");
   }
+  if (dout.cost_hist) CK(cudaMemsetAsync(dout.cost_hist, 0, b_ch * B, s->stream));
+  rc = launch_solve(h, s, s->stream, &din, &dout, nullptr, s->ready);
+  if (rc != CILQR_OK) {
+    cudaStreamSynchronize(s->copy_stream);
+    return rc;
+  }
+  CK(cudaMemcpyAsync(s->flags_host, s->ticket, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
   int i_out = 0;
   auto d2h = [&](void* dst, const void* dev, size_t per) -> cudaError_t {
     const bool need = staged[i_out++];
@@ -665,7 +727,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   CK(d2h(out->hist_len, dout.hist_len, b_hl));
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(s->stream));
-  return CILQR_OK;
+  return check_launch(h, s, s->flags_host);
 }
 
 int cilqr_debug_completion_histogram(cilqr_handle* h, uint64_t out[256]) {
@@ -758,7 +820,6 @@ static int corridor_launch(cilqr_handle* h, const CilqrCorridorConfig* cfg, cons
   if (threads < 32) return CILQR_E_SMEM;
   const size_t smem = per_thread * threads;
   static_assert(sizeof(float) == 4, "");
-  CK(cudaFuncSetAttribute(corridor::corridor_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)in->B * in->K;
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corridor::corridor_build_kernel, threads, smem));
@@ -803,11 +864,7 @@ int cilqr_corridor_batch_device(cilqr_handle* h, const CilqrCorridorConfig* cfg,
 
 static int corr_ensure(cilqr_handle* h, size_t bytes) {
   if (h->corr_bytes >= bytes) return CILQR_OK;
-  for (int i = 0; i < 2; ++i) {
-    if (h->aux_buf[i]) cudaFree(h->aux_buf[i]);
-    for (int j = 0; j < 2; ++j)
-      if (h->aux_ev[i][j]) cudaEventDestroy(h->aux_ev[i][j]);
-  }
+  CK(cudaStreamSynchronize(h->slots[0].stream));  // nothing enqueued may still read the old buffer
   if (h->corr_buf) cudaFree(h->corr_buf);
   h->corr_buf = nullptr;
   h->corr_bytes = 0;

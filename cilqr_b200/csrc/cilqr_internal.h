@@ -14,4 +14,6 @@ int cilqr_internal_fail(cilqr_handle* h, cudaError_t e, const char* where);
 int cilqr_internal_scratch(cilqr_handle* h, int slot, size_t bytes, char** out);
 // a pair of timing events owned by the handle, per slot
 int cilqr_internal_events(cilqr_handle* h, int slot, cudaEvent_t* e0, cudaEvent_t* e1);
+// dp_capi.cu: raises dp_plan_kernel's dynamic shared-memory limit (once per device, from cilqr_create)
+int cilqr_internal_dp_set_smem(int bytes);
 }

@@ -176,12 +176,24 @@ struct KernelArgs {
   int32_t* hist_len;
   int hist_cap;
   double* ws;            // [gridDim.x][ctx_per_cta][cl.stride]
-  unsigned int* ticket;  // scenario counter
+  unsigned int* ticket;  // [0] scenario counter, [1] error bits (kErr*), [2] scenarios finished
   const unsigned int* ready;  // host path: scenarios below *ready have arrived on the device (NULL: all)
+  unsigned long long watchdog_ns;  // how long INIT waits for the watermark before it flags kErrStarved
   unsigned long long* stats;  // optional [8 + 2 + 256]: completion-time histogram (2 ms buckets) after the counters; [8]: scheduler passes, idle polls, failed claims, phases run by type (4), type switches
   DebugPtrs dbg;
   int debug;             // 1: stop after the first line-search evaluation and dump stages
 };
+
+// error bits a launch can raise in ticket[1]; the host turns any of them into CILQR_E_TIMEOUT
+constexpr unsigned kErrStarved = 1u;   // INIT gave up waiting for the host path's watermark
+constexpr unsigned kErrIdle = 2u;      // a warp's idle poll ran into its watchdog
+constexpr unsigned kErrHelp = 4u;      // a help-board wait ran into its watchdog
+__device__ __forceinline__ void raise_error(const KernelArgs& a, unsigned bits) { atomicOr(a.ticket + 1, bits); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __constant__ double kAlphaList[kNAlpha] = {1.0000, 0.5012, 0.2512, 0.1259, 0.0631, 0.0316,
                                            0.0158, 0.0079, 0.0040, 0.0020, 0.0010};
@@ -1138,6 +1150,7 @@ __device__ __noinline__ void finish_scenario(const Ctx& c) {
     atomicAdd(a.stats + 10 + (bk < 255 ? bk : 255), 1ull);
   }
   if (lane == 0) {
+    atomicAdd(a.ticket + 2, 1u);
     double* st = a.status + b * 8;
     st[0] = h->status;
     st[1] = h->iter;
@@ -1212,10 +1225,17 @@ __device__ __noinline__ int phase_init(Ctx& c) {
   if (b >= (unsigned)a.B) return PH_DONE;
   if (a.ready) {
     // the host path streams the inputs in behind the running kernel: wait for this scenario's chunk
-    unsigned naps = 0;
+    // Watchdog: the transfer died or was never enqueued.  The scenario stays unsolved (its status row keeps
+    // the sentinel the host wrote before the launch) and the launch is flagged: cilqr_plan_batch returns
+    // CILQR_E_TIMEOUT instead of handing back a trajectory nobody computed (the reference never returns
+    // an un-filled trajectory as success, trajectory_planner.cpp:91-94).
+    const unsigned long long t_wait = global_ns();
     while (b >= *(const volatile unsigned int*)a.ready) {
       __nanosleep(2000);
-      if (++naps > 2000000u) return PH_DONE;  // (watchdog ~4 s: the transfer died; the host reports the error)
+      if (global_ns() - t_wait > a.watchdog_ns) {
+        if (lane == 0) raise_error(a, kErrStarved);
+        return PH_DONE;
+      }
     }
     __threadfence();
   }
@@ -1834,6 +1854,7 @@ __device__ __noinline__ int gang_eval(Ctx& c, HelpBoard* hb, int mine) {
       } else {
         unsigned spins = 0;
         while (hb->done[i] == 0 && ++spins < (1u << 24)) __nanosleep(200);
+        if (spins >= (1u << 24) && lane == 0) raise_error(c.a, kErrHelp);
         __threadfence_block();
 #pragma unroll
         for (int q = 0; q < 5; ++q) cost5[q] = hb->cost[i][q];
@@ -1849,6 +1870,7 @@ __device__ __noinline__ int gang_eval(Ctx& c, HelpBoard* hb, int mine) {
       for (int i = 1; i < claimed; ++i) {
         unsigned spins = 0;
         while (hb->done[i] == 0 && ++spins < (1u << 24)) __nanosleep(200);
+        if (spins >= (1u << 24) && lane == 0) raise_error(c.a, kErrHelp);
       }
       __threadfence_block();
       __syncwarp();
@@ -1896,6 +1918,7 @@ __device__ __noinline__ int gang_lin(Ctx& c, HelpBoard* hb, int mine) {
   if (lane == 0) atomicExch(&hb->next, kHelpClosed);
   unsigned spins = 0;
   while (*(volatile int*)&hb->done_cnt < n && ++spins < (1u << 24)) __nanosleep(200);
+  if (spins >= (1u << 24) && lane == 0) raise_error(a, kErrHelp);
   __threadfence();
   __syncwarp();
   if (lane == 0) atomicExch(&hb->owner, -1);
@@ -2010,7 +2033,10 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       ++naps;
       ++st_poll;
       __nanosleep(naps < 16 ? 250 : 4000);
-      if (naps > (1u << 22)) break;  // (watchdog: never spin forever)
+      if (naps > (1u << 22)) {  // (watchdog: never spin forever)
+        if (lane == 0) raise_error(a, kErrIdle);
+        break;
+      }
       continue;
     }
     naps = 0;

@@ -68,7 +68,6 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
     a.grid_idx = (const int*)(g + b0);
   }
   const size_t smem = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn);
-  CKH(cudaFuncSetAttribute(dp::dp_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp::dp_plan_kernel, dp::kMaxThreads, smem));
   if (per_sm < 1) per_sm = 1;
@@ -87,6 +86,13 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
 }  // namespace
 
 extern "C" {
+
+// called once from cilqr_create: function attributes are per-device state shared by every handle
+int cilqr_internal_dp_set_smem(int bytes) {
+  return cudaFuncSetAttribute(dp::dp_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess
+             ? CILQR_OK
+             : CILQR_E_CUDA;
+}
 
 void cilqr_dp_default_config(CilqrDpConfig* c) {
   if (!c) return;

@@ -16,7 +16,7 @@ import numpy as np
 from . import build as _build
 
 STATUS_NAMES = ["converged_abs", "converged_rel", "converged_grad", "lambda_overflow", "max_iter"]
-E_INVALID, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_SMEM = -1, -2, -3, -4, -5
+E_INVALID, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_SMEM, E_TIMEOUT = -1, -2, -3, -4, -5, -6
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -99,7 +99,7 @@ EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_d
            "cilqr_plan_batch", "cilqr_plan_batch_device", "cilqr_synchronize",
            "cilqr_kernel_launches", "cilqr_last_kernel_ms", "cilqr_occupancy", "cilqr_strerror",
            "cilqr_last_cuda_error", "cilqr_debug_first_iteration", "cilqr_debug_stats",
-           "cilqr_debug_completion_histogram", "cilqr_corridor_default_config", "cilqr_corridor_batch",
+           "cilqr_debug_completion_histogram", "cilqr_debug_host_path", "cilqr_corridor_default_config", "cilqr_corridor_batch",
            "cilqr_corridor_batch_device", "cilqr_lane_constraints", "cilqr_lane_constraints_device",
            "cilqr_corridor_last_kernel_ms", "cilqr_dp_default_config", "cilqr_dp_num_knots",
            "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms"]
@@ -142,6 +142,7 @@ def load_library(build_if_missing: bool = True):
     L.cilqr_debug_first_iteration.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(DebugOut)]
     L.cilqr_debug_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.cilqr_debug_completion_histogram.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.cilqr_debug_host_path.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.cilqr_corridor_default_config.argtypes = [C.POINTER(CorridorConfig)]
     L.cilqr_corridor_default_config.restype = None
     L.cilqr_corridor_batch.argtypes = [C.c_void_p, C.POINTER(CorridorConfig), C.POINTER(CorridorIn),
@@ -227,7 +228,7 @@ class Solver:
     def _check(self, rc: int):
         if rc != 0:
             msg = self._L.cilqr_strerror(rc).decode()
-            if rc == E_CUDA:
+            if rc in (E_CUDA, E_TIMEOUT):
                 msg += " -- " + self._L.cilqr_last_cuda_error(self._h).decode()
             raise CilqrError(rc, msg)
 
@@ -283,6 +284,10 @@ class Solver:
 
     def synchronize(self):
         self._check(self._L.cilqr_synchronize(self._h))
+
+    def debug_host_path(self, watchdog_ms: int = 0, starve_after: int = -1):
+        """Test hook: shorten the input watchdog / withhold the input watermark beyond ``starve_after``."""
+        self._check(self._L.cilqr_debug_host_path(self._h, watchdog_ms, starve_after))
 
     def kernel_launches(self) -> int:
         n = C.c_int64()

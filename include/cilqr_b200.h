@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CILQR_ABI_VERSION 3
+#define CILQR_ABI_VERSION 4
 
 /* error codes */
 #define CILQR_OK 0
@@ -54,6 +54,9 @@ extern "C" {
 #define CILQR_E_NO_DEVICE (-3) /* no sm_100 device: there is no CPU fallback */
 #define CILQR_E_CAPACITY (-4)  /* batch/horizon exceeds what the handle was created for */
 #define CILQR_E_SMEM (-5)      /* horizon does not fit the per-warp shared-memory stage */
+#define CILQR_E_TIMEOUT (-6)   /* the solve kernel gave up on some scenarios (input transfer starved / watchdog); \
+                                  their status rows keep the NaN sentinel -- never returned as success, cf. \
+                                  trajectory_planner.cpp:91-94 */
 
 /* status[b][CILQR_ST_FLAG] values: which exit of Optimize() was taken */
 #define CILQR_CONVERGED_ABS 0    /* dcost < abs_cost_tol         ilqr_optimizer.cc:281,287 */
@@ -62,7 +65,8 @@ extern "C" {
 #define CILQR_LAMBDA_OVERFLOW 3  /* "kUnsolved"                  ilqr_optimizer.cc:302-307 */
 #define CILQR_MAX_ITER 4         /* loop exhausted               ilqr_optimizer.cc:312-319 */
 
-/* layout of one status record (8 doubles) */
+/* layout of one status record (8 doubles).  Every row is pre-filled with all-ones bytes (a NaN) before the
+ * launch: a scenario the kernel did not finish is recognisable by status[b][CILQR_ST_FLAG] != itself. */
 #define CILQR_ST_FLAG 0       /* one of the values above */
 #define CILQR_ST_ITERS 1      /* loop index `iter` at exit */
 #define CILQR_ST_COST 2       /* total cost of the returned trajectory ... */
@@ -137,6 +141,8 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
  * the handle's own stream) and returns without synchronising. */
 int cilqr_plan_batch_device(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut* out,
                             void* cuda_stream);
+/* Waits for the handle's streams and checks the last launch: CILQR_E_TIMEOUT when it left scenarios
+ * unsolved.  After cilqr_plan_batch_device on a caller stream, synchronise that stream first. */
 int cilqr_synchronize(cilqr_handle* h);
 
 /* Introspection used by bench.py / tests. */
@@ -165,6 +171,10 @@ typedef struct CilqrDebugOut {
   int32_t* nearest; /* [B][K][5][2] nearest lane segment per disc/side at the initial guess */
 } CilqrDebugOut;
 int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in_dev, const CilqrDebugOut* out_dev);
+/* Test hook of the host path: watchdog_ms (> 0) = how long the kernel waits for an input chunk before it
+ * flags the launch; starve_after >= 0 = never raise the input watermark beyond that many scenarios (the
+ * rest of the batch then times out and cilqr_plan_batch must return CILQR_E_TIMEOUT); -1 = normal. */
+int cilqr_debug_host_path(cilqr_handle* h, int watchdog_ms, int starve_after);
 
 /* ------------------------------------------------------------------------------------------------
  * Safe-corridor builder: the step immediately before the solve.

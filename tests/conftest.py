@@ -15,10 +15,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
 
 
+def _cuda_visible() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
 def pytest_collection_modifyitems(config, items):
-    # GPU tests fail loudly (not skip) when selected on a box without a device: a silent skip
-    # would read as a pass of a path that never ran.
-    pass
+    # GPU tests fail loudly (not skip) when they were SELECTED (-m gpu) on a box without a device: a silent
+    # skip would read as a pass of a path that never ran.  A plain `pytest` (no -m) on a CPU box skips them
+    # with a reason instead of dying in the first one.
+    markexpr = (config.getoption("markexpr", "") or "").strip()
+    if "gpu" in markexpr or _cuda_visible():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device; run with -m gpu on a B200 (fails loudly there if absent)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

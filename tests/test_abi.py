@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", cilqr_b200.lib_path()], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", out), n
-    assert lib.cilqr_abi_version() == 3
+    assert lib.cilqr_abi_version() == 4
 
 
 def test_product_library_does_not_link_the_oracle():
