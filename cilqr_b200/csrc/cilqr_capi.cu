@@ -59,6 +59,7 @@ struct cilqr_handle {
   int device = 0;
   int num_sms = 0;
   int smem_optin = 0;
+  int solve_smem_max = 0;  // dynamic shared memory the solve kernel may use: opt-in size minus its static part
   CilqrParams params;
   DevParams dev;
   int N_max = 0, M_max = 0, S_max = 0, B_max = 0;
@@ -198,7 +199,7 @@ int plan_launch(cilqr_handle* h, int B, int N, int M_max, int S_left, int S_righ
   L.cl = make_ctx_layout(N, M_max, S_left, S_right);
   L.Kc = (N + 1 + 3) / 4 * 4;
   // warps per CTA: as many per-warp stages as fit the SM's shared memory, at most kCtaWarps
-  const int W = std::min(cilqr::kCtaWarps, h->smem_optin / L.sm.total_bytes);
+  const int W = std::min(cilqr::kCtaWarps, h->solve_smem_max / L.sm.total_bytes);
   if (W < 1) return CILQR_E_SMEM;
   L.warps = W;  // (the kernel's dynamic shared-memory limit was raised to smem_optin once, in cilqr_create)
   // persistent grid: one CTA (W warps) per SM, each owning `ctx` scenario contexts
@@ -306,6 +307,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
     a.dbg.Un = dbg->Un;
     a.dbg.costn = dbg->costn;
     a.dbg.nearest = dbg->nearest;
+    a.dbg.gnorm = dbg->gnorm;
   }
   CK(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned int), stream));
   CK(cudaEventRecord(s->ev0, stream));
@@ -425,17 +427,29 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
   if (prop.major != 10) return bail(CILQR_E_NO_DEVICE);
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-  if (make_layout(N_max, M_max, S_max, S_max).total_bytes > h->smem_optin) return bail(CILQR_E_SMEM);
+  {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void*)cilqr::cilqr_solve_kernel) != cudaSuccess) return bail(CILQR_E_CUDA);
+    h->solve_smem_max = h->smem_optin - (int)fa.sharedSizeBytes;
+  }
+  if (make_layout(N_max, M_max, S_max, S_max).total_bytes > h->solve_smem_max) return bail(CILQR_E_SMEM);
   // function attributes are per-device state shared by every handle: set them once, to the maximum, so that
   // handles of different shapes on different host threads cannot shrink each other's limit between a
   // set-attribute and a launch
-  if (cudaFuncSetAttribute(cilqr::cilqr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) !=
-      cudaSuccess)
+  // (the dynamic limit is the opt-in size minus the kernel's static shared memory)
+  auto raise_limit = [&](const void* fn) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) fail_cuda(h, e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    return e == cudaSuccess;
+  };
+  if (!raise_limit((const void*)cilqr::cilqr_solve_kernel) || !raise_limit((const void*)corridor::corridor_build_kernel) ||
+      cilqr_internal_dp_set_smem(h->smem_optin) != CILQR_OK) {
+    fprintf(stderr, "cilqr_b200: %s\n", h->cuda_err.c_str());
     return bail(CILQR_E_CUDA);
-  if (cudaFuncSetAttribute(corridor::corridor_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           h->smem_optin) != cudaSuccess ||
-      cilqr_internal_dp_set_smem(h->smem_optin) != CILQR_OK)
-    return bail(CILQR_E_CUDA);
+  }
   if (const char* e = getenv("CILQR_WATCHDOG_MS")) h->watchdog_ms = std::max(1, atoi(e));
   for (int i = 0; i < kSlots; ++i) {
     Slot* s = &h->slots[i];

@@ -148,6 +148,7 @@ static_assert(sizeof(CtxHdr) == kHdrDoubles * 8, "CtxHdr size");
 struct DebugPtrs {
   double *corridor, *lanes, *X0, *U0, *cost0, *A11, *Jx, *Ju, *Hx, *Hu, *Kg, *kg, *dV, *Xn, *Un, *costn;
   int32_t* nearest;
+  double* gnorm;
 };
 
 struct KernelArgs {
@@ -1579,6 +1580,7 @@ __device__ __noinline__ int phase_back(Ctx& c) {
     acc += fmax(v0, v1);
   }
   const double gnorm = warp_sum(acc) / N;
+  if (dbg && dbg->gnorm && lane == 0) dbg->gnorm[b] = gnorm;
   if (gnorm < 1e-6 && lambda < 1e-5) {
     if (lane == 0) h->status = 2;
     __syncwarp();

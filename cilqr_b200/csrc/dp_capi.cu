@@ -88,8 +88,11 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
 extern "C" {
 
 // called once from cilqr_create: function attributes are per-device state shared by every handle
-int cilqr_internal_dp_set_smem(int bytes) {
-  return cudaFuncSetAttribute(dp::dp_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess
+int cilqr_internal_dp_set_smem(int optin_bytes) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, (const void*)dp::dp_plan_kernel) != cudaSuccess) return CILQR_E_CUDA;
+  return cudaFuncSetAttribute((const void*)dp::dp_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              optin_bytes - (int)fa.sharedSizeBytes) == cudaSuccess
              ? CILQR_OK
              : CILQR_E_CUDA;
 }

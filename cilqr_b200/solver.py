@@ -56,7 +56,7 @@ class BatchOut(C.Structure):
 class DebugOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "corridor", "lanes", "X0", "U0", "cost0", "A11", "Jx", "Ju", "Hx", "Hu", "Kg", "kg", "dV",
-        "Xn", "Un", "costn", "nearest")]
+        "Xn", "Un", "costn", "nearest", "gnorm")]
 
 
 class CorridorConfig(C.Structure):

@@ -169,6 +169,7 @@ int cilqr_abi_version(void);
 typedef struct CilqrDebugOut {
   double *corridor, *lanes, *X0, *U0, *cost0, *A11, *Jx, *Ju, *Hx, *Hu, *Kg, *kg, *dV, *Xn, *Un, *costn;
   int32_t* nearest; /* [B][K][5][2] nearest lane segment per disc/side at the initial guess */
+  double* gnorm;    /* [B] CalGradientNorm (ilqr_optimizer.cc:322-332) of the first Backward */
 } CilqrDebugOut;
 int cilqr_debug_first_iteration(cilqr_handle* h, const CilqrBatchIn* in_dev, const CilqrDebugOut* out_dev);
 /* Test hook of the host path: watchdog_ms (> 0) = how long the kernel waits for an input chunk before it

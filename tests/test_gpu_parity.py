@@ -72,7 +72,7 @@ def test_stage_level_parity(solver, oracle):
     dbg = dict(corridor=z(B, K, batch.M_max, 3), lanes=z(B, S2, 3), X0=z(B, K, 6), U0=z(B, N, 2), cost0=z(B, 5),
                A11=z(B, N, 12), Jx=z(B, K, 6), Ju=z(B, N, 2), Hx=z(B, K, 9), Hu=z(B, N, 2), Kg=z(B, N, 12),
                kg=z(B, N, 2), dV=z(B, 2), Xn=z(B, K, 6), Un=z(B, N, 2), costn=z(B, 5),
-               nearest=torch.zeros(B, K, 5, 2, dtype=torch.int32, device=dev))
+               nearest=torch.zeros(B, K, 5, 2, dtype=torch.int32, device=dev), gnorm=z(B))
     solver.debug_first_iteration(B, N, batch.M_max, batch.S, batch.S, *_dev(batch, torch, dev), dbg)
     torch.cuda.synchronize()
     g = {k: v.cpu().numpy() for k, v in dbg.items()}
@@ -101,7 +101,9 @@ def test_stage_level_parity(solver, oracle):
                     Ju=rel(g["Ju"][b], lin["Ju"]).max(),
                     Hx=(np.abs(g["Hx"][b] - Hx9) / (np.abs(Hx9).max() + 1)).max(), Hu=rel(g["Hu"][b], Hu2).max(),
                     Kg=(np.abs(g["Kg"][b] - Ks.reshape(N, 12)) / (np.abs(Ks).max() + 1)).max(),
-                    kg=(np.abs(g["kg"][b] - ks) / (np.abs(ks).max() + 1)).max(), dV=rel(g["dV"][b], dV).max())
+                    kg=(np.abs(g["kg"][b] - ks) / (np.abs(ks).max() + 1)).max(), dV=rel(g["dV"][b], dV).max(),
+                    # CalGradientNorm (ilqr_optimizer.cc:322-332) of those gains
+                    gnorm=rel(g["gnorm"][b], np.mean(np.max(np.abs(ks) / (np.abs(U0) + 1.0), axis=1))))
         # nearest lane segment indices are integers: exact
         near = np.array([[[c.nearest(side, X0[k, 0] + off * np.cos(X0[k, 2]), X0[k, 1] + off * np.sin(X0[k, 2]))
                            for side in (0, 1)] for off in _disc_offsets()] for k in range(K)])
@@ -125,6 +127,40 @@ def test_full_solve_parity(solver, oracle, N, B, seed):
     batch = scenarios.generate(seed, 0, B, N=N)
     Xg, Ug, Sg = _solve_device(solver, batch)
     _compare(oracle, batch, Xg, Ug, Sg)
+
+
+def test_gradient_norm_exit(oracle):
+    """The gradient-norm exit (ilqr_optimizer.cc:235-241): scenarios that leave through it when both cost
+    tolerances are 0 -- the same ones tests/test_reference_pins.py pins reference <-> oracle bit for bit.  The GPU
+    must take that exit too, after the same accepts, with the trajectory of the last accept."""
+    import cilqr_b200
+    from picks import GRAD_EXIT_PICKS
+    p = cilqr_b200.solver.default_params()
+    p.abs_cost_tol = p.rel_cost_tol = 0.0
+    po = oracle.default_params()
+    po.abs_cost_tol = po.rel_cost_tol = 0.0
+    s = cilqr_b200.Solver(params=p, device=0)
+    n_grad = n_same = 0
+    for (seed, N), ids in GRAD_EXIT_PICKS.items():
+        full = scenarios.generate(seed, 0, max(ids) + 1, N=N)
+        batch = scenarios.ScenarioBatch(full.N, full.M_max, full.S, *[np.ascontiguousarray(a[ids]) for a in
+                                        (full.start, full.coarse, full.corridor, full.corridor_cnt, full.lane_left,
+                                         full.lane_right)])
+        out = s.plan_batch(batch)
+        Xo, Uo, So, _ = oracle.solve_batch(batch, params=po, nthreads=4)
+        assert (So[:, 0] == 2).all()
+        same = (out["status"][:, 0] == So[:, 0]) & (out["status"][:, 1] == So[:, 1]) & (out["status"][:, 7] == So[:, 7])
+        e = np.maximum(rel(out["states"], Xo).reshape(len(ids), -1).max(axis=1),
+                       rel(out["controls"], Uo).reshape(len(ids), -1).max(axis=1))
+        print(f"\n[grad exit] seed {seed} N={N}: GPU exits {out['status'][:, 0].astype(int).tolist()} iterations "
+              f"{out['status'][:, 1].astype(int).tolist()} (oracle {So[:, 1].astype(int).tolist()}); identical path "
+              f"{int(same.sum())}/{len(ids)}; max rel err on those {e[same].max() if same.any() else float('nan'):.2e}")
+        n_grad += int((out["status"][:, 0] == 2).sum())
+        n_same += int(same.sum())
+        assert e[same].max() < 1e-6 if same.any() else True
+    s.close()
+    # 10-49 iterations at lambda -> 1e-8 amplify rounding differences; the exit itself must be reached on most
+    assert n_grad >= 6 and n_same >= 5, (n_grad, n_same)
 
 
 def test_shipped_road_and_horizon(solver, oracle):

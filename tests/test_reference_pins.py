@@ -335,9 +335,8 @@ def test_solver_exits_equal_the_reference(oracle):
 
 def test_max_iteration_exit_and_long_solves_equal_the_reference(oracle):
     """With the cost tolerances switched off the solve runs to `max_iter_num` (:312-316) or to the lambda-overflow
-    exit -- up to 200 iterations of accumulated rounding, still bit-identical.  (The gradient-norm exit :236-241 needs
-    lambda < 1e-5 together with a tiny gradient and was never reached on any generated scenario; it is the one exit
-    without a pin.)"""
+    exit -- up to 200 iterations of accumulated rounding, still bit-identical.  (The gradient-norm exit :236-241 is
+    pinned by test_gradient_norm_exit_equals_the_reference below.)"""
     batch = scenarios.generate(41, 0, 10, N=30)
     seen = set()
     for mi, at, rt in ((3, 1e-2, 1e-2), (200, 0.0, 0.0)):
@@ -350,3 +349,28 @@ def test_max_iteration_exit_and_long_solves_equal_the_reference(oracle):
             assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
             seen.add(o["status"])
     assert 4 in seen and 3 in seen
+
+
+from picks import GRAD_EXIT_PICKS  # noqa: E402  (tests/picks.py; tests/test_gpu_parity.py solves the same ones on the GPU)
+
+
+def test_gradient_norm_exit_equals_the_reference(oracle):
+    """The gradient-norm exit (ilqr_optimizer.cc:235-241, CalGradientNorm :322-332): `gnorm < 1e-6 && lambda < 1e-5`.
+    With the default tolerances (1e-2) the cost tests always fire first; with both set to 0 the iteration runs on
+    until the feed-forward gains vanish while lambda is still small.  Reference and oracle must leave through the
+    same exit after the same accepts, bit for bit."""
+    seen = 0
+    for (seed, N), ids in GRAD_EXIT_PICKS.items():
+        batch = scenarios.generate(seed, 0, max(ids) + 1, N=N)
+        p = oracle.default_params()
+        p.abs_cost_tol = p.rel_cost_tol = 0.0
+        for b in ids:
+            o = oracle.solve(batch, b, params=p, hist=True)
+            r = ref.ilqr_solve(batch, b, overrides=(200, 0.0, 0.0))
+            assert o["status"] == 2, (seed, N, b, o["status"])
+            assert len(r["cost_hist"]) == len(o["cost_hist"]) and np.array_equal(r["cost_hist"], np.array(o["cost_hist"]))
+            assert np.array_equal(r["states"], o["states"]) and np.array_equal(r["controls"], o["controls"])
+            # the reference pushes no cost / iterate on this exit: the last cost_ entry is the last accept's
+            assert len(o["cost_hist"]) == o["accepted"] + 1
+            seen += 1
+    assert seen == 8
