@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=65536)
+    ap.add_argument("--batch-per-gpu", type=int, default=0,
+                    help="0 = BASELINE.json as written: 65 536 per GPU (configs[2]); at 8 GPUs 131 072 per GPU = the "
+                         "1 048 576-scenario batch of configs[3]")
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--obstacles", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=4096, help="scenarios in the cpu_baseline sample")
@@ -53,6 +55,7 @@ def parse():
                     help="batches in flight in the timed region (one solver handle + stream each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency measurement (configs[0])")
     ap.add_argument("--no-corridor", action="store_true", help="skip the corridor-builder side measurement")
     ap.add_argument("--no-dp", action="store_true", help="skip the DP-planner side measurement")
     ap.add_argument("--corridor-base", type=int, default=2048,
@@ -60,9 +63,34 @@ def parse():
     return ap.parse_args()
 
 
+def resolve_batch(a, world: int):
+    if a.batch_per_gpu <= 0:
+        a.batch_per_gpu = 131072 if world == 8 else 65536
+    return a.batch_per_gpu
+
+
 def workload_name(a):
-    return (f"{a.batch_per_gpu} random_pedestrian-style scenarios per GPU, horizon N={a.horizon}, "
+    cfg = {65536: "configs[2]: ", 131072: "configs[3] (1 048 576 scenarios over 8 GPUs): "}.get(a.batch_per_gpu, "")
+    return (f"{cfg}{a.batch_per_gpu} random_pedestrian-style scenarios per GPU, horizon N={a.horizon}, "
             f"{a.obstacles} obstacles (M_max=20 half-planes/knot, S=40 lane segments/side), seed {SEED}")
+
+
+def kernel_source_hash() -> str:
+    """sha1 over the solve kernel's sources: ties profiles/traffic.json to the code it was captured from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("cilqr_kernel.cuh", "cilqr_capi.cu"):
+        h.update(open(os.path.join(ROOT, "cilqr_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def fp64_peak_tflops():
+    """Non-tensor FP64 peak: measured DFMA rate of tools/microbench/fp64_peak.cu when its result is committed
+    (profiles/fp64_peak_b200.json), else 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz."""
+    pth = os.path.join(ROOT, "profiles", "fp64_peak_b200.json")
+    if os.path.exists(pth):
+        return json.load(open(pth))["dfma_tflops"], "measured (profiles/fp64_peak_b200.json, tools/microbench/fp64_peak.cu)"
+    return 148 * 64 * 2 * 1.965e9 / 1e12, "nominal: 148 SMs x 64 DFMA/clk/SM x 2 x 1.965 GHz"
 
 
 class ClockSampler:
@@ -100,8 +128,10 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def cpu_baseline(a, kind_note=""):
-    """The oracle (C restatement of the reference solver) on all host threads, bounded sample."""
+def cpu_baseline(a, gpu=None):
+    """The oracle (C restatement of the reference solver) on all host threads, bounded sample.  With `gpu` =
+    (states, controls, status) of the same scenarios from the timed CUDA path, also the parity figures of the
+    workload that was timed (-> config.parity)."""
     from cilqr_b200 import scenarios
     from oracle import binding as oracle
     n = a.cpu_sample
@@ -109,13 +139,97 @@ def cpu_baseline(a, kind_note=""):
     cores = os.cpu_count() or 1
     oracle.solve_batch(batch.slice(0, min(n, 4 * cores)), nthreads=cores)  # warm the library / caches
     t = time.perf_counter()
-    _, _, st, conv = oracle.solve_batch(batch, nthreads=cores)
+    Xo, Uo, st, conv = oracle.solve_batch(batch, nthreads=cores)
     dt = time.perf_counter() - t
+    parity = None
+    if gpu is not None:
+        def three(A, Bq):
+            (Xa, Ua, Sa), (Xb, Ub, Sb) = A, Bq
+            same = (Sa[:, 0] == Sb[:, 0]) & (Sa[:, 1] == Sb[:, 1]) & (Sa[:, 7] == Sb[:, 7])
+            rel = lambda x, y: (np.abs(x - y) / (np.abs(y) + 1.0)).reshape(n, -1).max(axis=1)  # noqa: E731
+            e = np.maximum(rel(Xa, Xb), rel(Ua, Ub))
+            bit = sum(np.array_equal(Xa[b], Xb[b], equal_nan=True) and np.array_equal(Ua[b], Ub[b], equal_nan=True)
+                      and np.array_equal(Sa[b], Sb[b], equal_nan=True) for b in range(n))
+            return {"identical_path": int(same.sum()), "of": n, "within_1e-4": int((e[same] < 1e-4).sum()),
+                    "worst": float(e[same].max()), "median": float(np.median(e[same])),
+                    "p99": float(np.quantile(e[same], 0.99)), "bit_identical": int(bit)}
+        parity = {"sample": f"first {n} scenarios of the timed workload, GPU (timed path) vs oracle"}
+        parity.update(three(gpu, (Xo, Uo, st)))
+        parity["same_exit_flag"] = int((gpu[2][:, 0] == st[:, 0]).sum())
+        parity["definition"] = ("identical_path = same (exit flag, iteration count, FNV hash of the accepted "
+                                "line-search index per iteration); within_1e-4 / worst / median / p99 = max over "
+                                "states and controls of |a - b| / (|b| + 1), on identical-path scenarios")
+        # Where the tail comes from: the same sample through (1) the strict build of the kernel (reference-ordered
+        # arithmetic, portable libm) and (2) the oracle on that same portable libm.  strict == oracle(pm) bit for bit
+        # proves the kernel's logic; oracle(pm) vs oracle(glibc) is what exchanging the libm alone does to the
+        # REFERENCE algorithm; production vs oracle(glibc) (above) is of that size.
+        try:
+            import cilqr_b200
+            from oracle import binding_pm
+            if os.path.exists(cilqr_b200.solver.lib_path("strict")) and os.path.exists(binding_pm._LIB_PATH):
+                ss = cilqr_b200.Solver(device=int(os.environ.get("LOCAL_RANK", "0")), N_max=max(a.horizon, 100),
+                                       M_max=batch.M_max, S_max=batch.S, B_max=n, variant="strict")
+                o = ss.plan_batch(batch)
+                ss.close()
+                strict = (o["states"], o["controls"], o["status"])
+                Xp, Up, Sp, _ = binding_pm.solve_batch(batch, nthreads=cores)
+                parity["separation"] = {
+                    "strict_gpu_vs_oracle_pm_libm": three(strict, (Xp, Up, Sp)),
+                    "oracle_pm_libm_vs_oracle_glibc": three((Xp, Up, Sp), (Xo, Uo, st)),
+                    "strict_gpu_vs_oracle_glibc": three(strict, (Xo, Uo, st)),
+                    "note": "strict GPU build = libcilqr_b200_strict.so (-DCILQR_STRICT=1 -fmad=false: same scheduler "
+                            "and data flow, reference-ordered arithmetic, csrc/pm_math.h); oracle_pm = "
+                            "oracle/libcilqr_oracle_pm.so (same restatement on the same pm_math.h)"}
+        except Exception as ex:  # the parity instrument is optional for the bench line
+            parity["separation"] = {"error": str(ex)[:200]}
     res = {"value": conv / dt, "unit": UNIT, "cores": cores, "kind": "port",
            "sample": f"first {n} scenarios of the bench workload, C restatement of the reference solver "
                      f"(gcc -O2, double), {cores} pthreads, {dt:.2f} s wall; mean iterations {st[:, 1].mean():.2f}"}
     res["compiled_reference"] = compiled_reference_rate(batch, st)
-    return res
+    return res, parity
+
+
+def latency_b1(repeat: int = 10, n_scen: int = 16):
+    """BASELINE.json configs[0] -- the reference's actual use: ONE ego, one IlqrOptimizer::Plan call per click
+    (planning_node.cc:82-88), N = 80, 11 obstacles, the shipped road.  Wall-clock latency of that call through the
+    drop-in C++ class (include/cilqr/ilqr_optimizer_b200.h -> cilqr_plan_batch, B = 1, pageable std::vector buffers,
+    full iter_trajs / cost() history), next to the CPU port on ONE host core on the same scenarios."""
+    import tempfile
+    from cilqr_b200 import build as cbuild
+    from cilqr_b200 import scenarios
+    from oracle import binding as oracle
+    exe = cbuild.ADAPTER_DEMO
+    if not os.path.exists(exe):
+        return None
+    N = 80
+    batch = scenarios.generate(20260101, 0, n_scen, N=N, n_obs=11, road_name="shipped")
+    with tempfile.TemporaryDirectory() as td:
+        files = []
+        for b in range(n_scen):
+            parts = [np.array([N, batch.M_max, batch.lane_left.shape[1], batch.lane_right.shape[1]], dtype=np.float64),
+                     batch.start[b].ravel(), batch.coarse[b].ravel(), batch.corridor_cnt[b].astype(np.float64).ravel(),
+                     batch.corridor[b].ravel(), batch.lane_left[b].ravel(), batch.lane_right[b].ravel()]
+            f = os.path.join(td, f"s{b}.bin")
+            np.concatenate(parts).astype(np.float64).tofile(f)
+            files.append(f)
+        r = subprocess.run([exe, "--latency", str(repeat)] + files, capture_output=True, text=True, timeout=600)
+    lat = np.array([[float(x) for x in ln.split()[1:]] for ln in r.stdout.splitlines() if ln.startswith("LAT ")])
+    if r.returncode != 0 or len(lat) == 0:
+        return {"error": (r.stdout + r.stderr)[-300:]}
+    cpu_ms = []
+    for b in range(n_scen):
+        t0 = time.perf_counter()
+        o = oracle.solve(batch, b)
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+    cpu_ms = np.array(cpu_ms)
+    g = lat[:, 1]
+    return {"config": "configs[0]: single ego, N=80, 11 obstacles, shipped road (emulated by the generator), B=1",
+            "api": "planning::IlqrOptimizer::Plan (drop-in class) -> cilqr_plan_batch, B=1",
+            "calls": int(len(g)), "scenarios": n_scen, "gpu_ms_p50": float(np.median(g)), "gpu_ms_p99": float(np.quantile(g, 0.99)),
+            "gpu_ms_mean": float(g.mean()), "gpu_ms_min": float(g.min()), "mean_iterations": float(lat[:, 3].mean()),
+            "cpu_port_ms_p50": float(np.median(cpu_ms)), "cpu_port_ms_p99": float(np.quantile(cpu_ms, 0.99)),
+            "cpu_port_ms_mean": float(cpu_ms.mean()), "cpu_cores": 1,
+            "gpu_faster": bool(np.median(g) < np.median(cpu_ms))}
 
 
 def compiled_reference_rate(batch, status, n: int = 48):
@@ -292,6 +406,7 @@ def run_reference(a):
 
 def main():
     a = parse()
+    resolve_batch(a, int(os.environ.get("WORLD_SIZE", "1")))
     if a.impl == "reference":
         run_reference(a)
         return
@@ -484,10 +599,23 @@ def main():
             dpm = dp_measurement(solver, a, dev, stream, peak)
         alg_bytes = scenarios.algorithmic_bytes(N, batch.M_max, batch.S) * B
         achieved = alg_bytes / (kmean_ms * 1e-3) / 1e9
-        traffic = None
+        # `traffic` and the FP64 operation count come from ONE ncu capture of this kernel at this shape
+        # (profiles/traffic.json, written by tools/ncu_traffic.py together with a hash of the kernel sources);
+        # a capture of different sources is stale and is reported as null, with the reason
+        traffic, flops, cap_note = None, None, "no ncu capture committed"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("kernel_source_sha1") != kernel_source_hash():
+                cap_note = (f"stale: profiles/traffic.json was captured from kernel sources {str(tj.get('kernel_source_sha1'))[:10]} "
+                            f"(commit {tj.get('commit')}), this run is {kernel_source_hash()[:10]}")
+            elif tj.get("scenarios") != B or tj.get("horizon") != N:
+                cap_note = f"capture is of {tj.get('scenarios')} scenarios, N={tj.get('horizon')}: not this shape"
+            else:
+                traffic = tj.get("dram_bytes_per_launch")
+                flops = tj.get("fp64_flops_per_launch")
+                cap_note = f"ncu --set full capture of commit {tj.get('commit')} ({tj.get('source')}), same kernel sources"
+        fp64_peak, fp64_src = fp64_peak_tflops()
         warps, smem = solver.occupancy(N, batch.S, batch.S)
         res = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -502,7 +630,17 @@ def main():
                        "converged_fraction": conv_total / total, "mean_iterations": iters_mean,
                        "warps_per_sm": warps, "smem_bytes_per_warp": smem, "scenario_gen_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "cilqr_solve_kernel",
+                         "traffic": traffic, "traffic_source": cap_note,
+                         "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                         # secondary ceiling: the kernel is fp64 issue/latency bound, so the distance
+                         # from the machine is the FP64 pipe fraction, not the HBM one
+                         "flops": {"fp64_flops_per_launch": flops,
+                                   "achieved_tflops": (flops / (kmean_ms * 1e-3) / 1e12) if flops else None,
+                                   "peak_tflops": fp64_peak, "peak_source": fp64_src,
+                                   "fp64_frac": (flops / (kmean_ms * 1e-3) / 1e12 / fp64_peak) if flops else None,
+                                   "definition": "2*DFMA + DADD + DMUL thread instructions (ncu smsp__sass_thread_inst_"
+                                                 "executed_op_d*_pred_on) of one launch / launch duration"},
+                         "peak_source": peak_src, "kernel": "cilqr_solve_kernel",
                          "kernel_ms": kmean_ms, "kernel_ms_library_events": lib_kernel_ms,
                          "kernel_ms_note": "launch duration with one batch in flight (CUDA events on the launching "
                                            "stream); with F in flight launches overlap and share the SMs",
@@ -512,8 +650,15 @@ def main():
                                  "scenario contexts live in L2/HBM between solver phases (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches),
             "kernel_ms_per_step_one_in_flight": k_ms,
-            "allgather_ms_per_step": (serial_ms - sum(k_ms)) / a.steps if world > 1 else None,
         }
+        if world > 1:
+            ag_ms = (serial_ms - sum(k_ms)) / a.steps
+            ag_bytes = blocks[0].numel() * 8 * (world - 1)  # received by every GPU per step
+            res["config"]["allgather"] = {"ms_per_step": ag_ms, "bytes_received_per_gpu": int(ag_bytes),
+                                          "achieved_gbs_per_gpu": ag_bytes / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None,
+                                          "nvlink_peak_gbs_per_direction": 900.0,
+                                          "note": "exposed time of the all-gather with one batch in flight (step time "
+                                                  "minus solve-kernel time); with batches in flight it overlaps the next solve"}
         if e2e:
             res["e2e"] = e2e
         if corridor:
@@ -521,7 +666,12 @@ def main():
         if dpm:
             res["dp_planner"] = dpm
         if not a.no_cpu_baseline:
-            res["cpu_baseline"] = cpu_baseline(a)
+            n = min(a.cpu_sample, B)
+            a.cpu_sample = n
+            gpu = (states[:n].cpu().numpy(), controls[:n].cpu().numpy(), status[:n].cpu().numpy())
+            res["cpu_baseline"], res["config"]["parity"] = cpu_baseline(a, gpu)
+        if not a.no_latency:
+            res["latency_b1"] = latency_b1()
         print(json.dumps(res), flush=True)
     if world > 1:
         dist.barrier()

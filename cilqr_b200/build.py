@@ -9,11 +9,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200.so")
+# The parity instrument: the same sources with -DCILQR_STRICT=1 -fmad=false (reference-ordered arithmetic on the
+# portable libm of csrc/pm_math.h; see the top of csrc/cilqr_kernel.cuh).  Loaded only by tests / bench parity legs
+# (cilqr_b200.Solver(variant="strict")); the product is LIB_PATH.
+STRICT_LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200_strict.so")
 # translation units: (source, extra flags).  dp_capi.cu restates double-precision decision logic of the
 # reference and is compiled without FMA contraction (-fmad=false); the solver TU keeps nvcc's default.
 UNITS = [("cilqr_capi.cu", []), ("dp_capi.cu", ["-fmad=false"])]
-DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "corridor_kernel.cuh", "dp_capi.cu", "dp_kernel.cuh", "cilqr_internal.h",
-        os.path.join("..", "..", "include", "cilqr_b200.h")]
+DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "cilqr_strict.cuh", "pm_math.h", "corridor_kernel.cuh", "dp_capi.cu",
+        "dp_kernel.cuh", "cilqr_internal.h", os.path.join("..", "..", "include", "cilqr_b200.h")]
 NVCC_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                 "-Xcompiler", "-fPIC"]
 NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "static"]
@@ -26,25 +30,29 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def is_stale(path: str = LIB_PATH) -> bool:
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB_PATH
+def build_library(force: bool = False, verbose: bool = False, strict: bool = False) -> str:
+    out = STRICT_LIB_PATH if strict else LIB_PATH
+    if not force and not is_stale(out):
+        return out
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     for src, extra in UNITS:
-        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        tag = "_strict" if strict else ""
+        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + tag + ".o")
+        if strict:
+            extra = [e for e in extra if e != "-fmad=false"] + ["-DCILQR_STRICT=1", "-fmad=false"]
         cmd = [_nvcc()] + NVCC_COMPILE + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         subprocess.check_call(cmd, cwd=CSRC)
         objs.append(obj)
-    subprocess.check_call([_nvcc()] + NVCC_LINK + ["-o", LIB_PATH] + objs, cwd=CSRC)
-    return LIB_PATH
+    subprocess.check_call([_nvcc()] + NVCC_LINK + ["-o", out] + objs, cwd=CSRC)
+    return out
 
 
 ADAPTER_DEMO = os.path.join(LIB_DIR, "adapter_demo")
@@ -110,4 +118,5 @@ def build_dp_demo(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+    print(build_library(force=True, verbose=True, strict="strict" in sys.argv[1:]))

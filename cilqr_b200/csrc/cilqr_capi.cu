@@ -108,7 +108,16 @@ void make_dev_params(const CilqrParams& p, DevParams* d) {
   d->eps = p.barrier_eps;
   d->inv_eps = 1.0 / p.barrier_eps;
   d->inv_eps2 = 1.0 / (p.barrier_eps * p.barrier_eps);
-  d->relax_c = -0.5 * d->rt - d->rt * log(p.barrier_eps);
+#if CILQR_STRICT
+  // the strict build shares its libm with oracle/libcilqr_oracle_pm.so on the host side too
+#define CILQR_HOST_LOG pm_log
+#define CILQR_HOST_HYPOT pm_hypot
+#else
+#define CILQR_HOST_LOG log
+#define CILQR_HOST_HYPOT hypot
+#endif
+  d->relax_c = -0.5 * d->rt - d->rt * CILQR_HOST_LOG(p.barrier_eps);
+  d->rt_log_eps = d->rt * CILQR_HOST_LOG(p.barrier_eps);
   d->vmax = p.max_velocity;
   d->amin = p.min_acceleration;
   d->amax = p.max_acceleration;
@@ -133,7 +142,7 @@ void make_dev_params(const CilqrParams& p, DevParams* d) {
   for (int j = 0; j < cilqr::kDisc; ++j) d->off[j] = (Ld * (j - 0.5) - p.rear_hang_length);
   // CalculateDiscRadius, ilqr_optimizer.cc:97-104
   const double length = p.front_hang_length + p.wheel_base + p.rear_hang_length;
-  const double r = hypot(p.width / 2.0, length / 2.0 / p.num_of_disc);
+  const double r = CILQR_HOST_HYPOT(p.width / 2.0, length / 2.0 / p.num_of_disc);
   d->shrink_corr = r + p.safe_margin;
   d->shrink_lane = r;
   d->max_iter = p.max_iter_num;
@@ -149,7 +158,11 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   L.grp = S * cilqr::kSegStride;
   L.trig = even(L.grp + ng * 3);
   L.pl_e = even(L.trig + 2 * K);
+#if CILQR_STRICT
+  const int e_end = L.pl_e + 32 * cilqr::strict_row_width(M_max);  // the term buffer of the ordered cost sums
+#else
   const int e_end = L.pl_e + cilqr::kTileBufs * M_max * cilqr::kPlaneTile;
+#endif
   // LIN: lin window, plane tiles.  BACK: record ring, scr.  INIT builds seg/grp while iqr uses scr, so scr
   // lies behind both
   L.lin = 0;

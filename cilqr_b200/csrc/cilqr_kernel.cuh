@@ -37,6 +37,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// CILQR_STRICT = 1 builds the PARITY INSTRUMENT (libcilqr_b200_strict.so, compiled with -fmad=false): the same
+// scheduler, contexts, line search and data flow as the production kernel, but every floating-point expression is
+// evaluated in the reference's own order (sequential sums over knots / discs / planes, one log per barrier term,
+// IEEE division, the dense Eigen-ordered Riccati step with the in-place symmetrisation Q22, the reference's iqr
+// update) and the five libm functions come from the portable pm_math.h that the oracle build
+// libcilqr_oracle_pm.so shares -- so its output can be compared with that oracle BIT FOR BIT
+// (tests/test_gpu_strict.py).  It proves the kernel's logic; the production build (0) re-associates sums, fuses
+// multiply-adds and uses CUDA's libm, which moves results by rounding only.
+#ifndef CILQR_STRICT
+#define CILQR_STRICT 0
+#endif
+#if CILQR_STRICT
+#include "pm_math.h"
+#define CILQR_FMA(a, b, c) ((a) * (b) + (c))
+#define CILQR_DIVL(P, x) ((x) / (P).L)
+#else
+#define CILQR_FMA(a, b, c) fma((a), (b), (c))
+#define CILQR_DIVL(P, x) ((x) * (P).inv_L)
+#endif
+
 namespace cilqr {
 
 constexpr int kNX = 6;
@@ -45,7 +65,11 @@ constexpr int kDisc = 5;
 constexpr int kNAlpha = 11;
 constexpr int kSpec = 4;          // step sizes rolled out speculatively per ROLL phase
 constexpr int kTrajSlots = kSpec + 1;  // iterate + candidates
+#if CILQR_STRICT
+constexpr int kLinStride = 40;    // strict: the lower triangle of Hx's 3x3 block is carried too (it is not bit-symmetric)
+#else
 constexpr int kLinStride = 37;    // doubles per knot in the linearisation window
+#endif
 constexpr int kSegStride = 10;    // sx sy ex ey ux uy len a b c
 constexpr int kGainStride = 16;   // K (2x6), k (2), pad (2): one 128-byte record per knot
 constexpr int kRollChunk = 4;     // knots per cp.async stage of the rollout ring
@@ -56,7 +80,11 @@ constexpr int kRingDoubles = 2 * (8 * kRollChunk + kGainStride * kRollChunk);
 #define CILQR_GROUP 8
 #endif
 constexpr int kGroup = CILQR_GROUP;  // lane segments per bounding-circle group of the pruned nearest search
+#if CILQR_STRICT
+constexpr int kScratch = 768;     // strict: dense 6x6 temporaries of the Eigen-ordered Riccati step
+#else
 constexpr int kScratch = 192;     // doubles of per-warp Riccati scratch
+#endif
 constexpr int kPlaneKnots = 8;    // knots per staged tile of corridor planes
 constexpr int kPlaneTile = 3 * kPlaneKnots;  // doubles per plane (a, b, c rows) in a tile; x M_max per buffer
 #ifndef CILQR_TILE_BUFS
@@ -99,9 +127,14 @@ constexpr int LDT = 33;
 constexpr int LB30 = 34;
 constexpr int LSN = 35;  // sin, cos of the heading (consumed by linearize_discs)
 constexpr int LCS = 36;
+constexpr int LH10 = 37;  // strict build only: H10 H20 H21
+// strict build: doubles per lane of the term buffer of eval_cost (corridor terms + two lane terms, at least the
+// seven per-knot terms of the first pass)
+__host__ __device__ constexpr int strict_row_width(int M_max) { return M_max + 2 < 8 ? 8 : M_max + 2; }
 
 struct DevParams {
   double dt, L, inv_L, rt, eps, inv_eps, inv_eps2, relax_c;  // relax_c = -0.5*rt - rt*log(eps)
+  double rt_log_eps;  // rt * log(eps): the constant of the relaxed barrier branch as the reference writes it (strict build)
   double vmax, amin, amax, dmin, dmax, jmin, jmax, drmin, drmax;
   double wx, wy, wth, wv, wa, wd, wj, wdr;
   double abs_tol, rel_tol;
@@ -209,6 +242,17 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---- out-of-line math: ONE copy of each double-precision libdevice routine in the kernel.
 // Inlined at every call site they made the kernel ~300 KB of SASS, which thrashed the instruction
 // cache (ncu: stall_no_instruction 5.4 cycles per issued instruction); see DESIGN.md.
+#if CILQR_STRICT
+__device__ __noinline__ double nt_tan(double x) { return pm_tan(x); }
+__device__ __noinline__ double2 nt_tan2(double x, double y) { return make_double2(pm_tan(x), pm_tan(y)); }
+__device__ __noinline__ double nt_log(double x) { return pm_log(x); }
+__device__ __noinline__ double nt_hypot(double x, double y) { return pm_hypot(x, y); }
+__device__ __noinline__ double2 nt_sincos(double x) {
+  double s, c;
+  pm_sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+#else
 __device__ __noinline__ double nt_tan(double x) { return tan(x); }
 // two independent tangents in one call: the two polynomial chains interleave (the rollout is a serial
 // dependency chain, so instruction-level parallelism inside a step is all there is)
@@ -220,6 +264,7 @@ __device__ __noinline__ double2 nt_sincos(double x) {
   sincos(x, &s, &c);
   return make_double2(s, c);
 }
+#endif
 // general branch of NormalizeAngle (math_utils.cpp:53-59) on a = angle + pi
 __device__ __noinline__ double nt_wrap_general(double a) {
   const double kTwoPi = 2.0 * 3.14159265358979323846;
@@ -257,11 +302,11 @@ __device__ __forceinline__ void rollout_step(const DevParams& P, double* x, doub
   const double de = wrap_angle(x[5], allow_general, slow);
   const double dem = wrap_angle(m5, allow_general, slow);
   const double2 tt = nt_tan2(de, dem);
-  const double k1t = x[3] * tt.x * P.inv_L;
+  const double k1t = CILQR_DIVL(P, x[3] * tt.x);
   const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0;
   const double thm = wrap_angle(m2, allow_general, slow);
   const double2 sc = nt_sincos(thm);
-  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = m3 * tt.y * P.inv_L;
+  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = CILQR_DIVL(P, m3 * tt.y);
   x[0] = x[0] + P.dt * k2x;
   x[1] = x[1] + P.dt * k2y;
   x[2] = wrap_angle(x[2] + P.dt * k2t, allow_general, slow);
@@ -273,31 +318,31 @@ __device__ __forceinline__ void rollout_step(const DevParams& P, double* x, doub
 // vehicle_model.cc:21-86.  Writes the 11 state-dependent entries of A and B(2,1).
 __device__ __noinline__ void dynamics_jacobian(const DevParams& P, const double* x, double u1,
                                                double* A11, double* b21) {
-  const double iL = P.inv_L, dt = P.dt;
+  const double dt = P.dt;
   const double v = x[3];
   const double theta = normalize_angle(x[2]);
   const double delta = normalize_angle(x[5]);
   const double a = x[4];
   const double2 tt = nt_tan2(delta, delta + 0.5 * dt * u1);
   const double tan_delta = tt.x, tan_dr = tt.y;
-  const double theta_mid = theta + 0.5 * dt * v * tan_delta * iL;
+  const double theta_mid = theta + CILQR_DIVL(P, 0.5 * dt * v * tan_delta);
   const double2 scm = nt_sincos(theta_mid);
   const double sm = scm.x, cm = scm.y;
   const double td2 = tan_delta * tan_delta;
   const double tr2 = tan_dr * tan_dr;
   const double vm = 0.5 * a * dt + v;
   A11[0] = -dt * vm * sm;
-  A11[1] = dt * cm - 0.5 * dt * dt * vm * sm * tan_delta * iL;
+  A11[1] = dt * cm - CILQR_DIVL(P, 0.5 * dt * dt * vm * sm * tan_delta);
   A11[2] = 0.5 * dt * dt * cm;
-  A11[3] = -0.5 * dt * dt * v * vm * (td2 + 1) * sm * iL;
+  A11[3] = CILQR_DIVL(P, -0.5 * dt * dt * v * vm * (td2 + 1) * sm);
   A11[4] = dt * vm * cm;
-  A11[5] = dt * sm + 0.5 * dt * dt * vm * cm * tan_delta * iL;
+  A11[5] = dt * sm + CILQR_DIVL(P, 0.5 * dt * dt * vm * cm * tan_delta);
   A11[6] = 0.5 * dt * dt * sm;
-  A11[7] = 0.5 * dt * dt * v * vm * (td2 + 1) * cm * iL;
-  A11[8] = dt * tan_dr * iL;
-  A11[9] = 0.5 * dt * dt * tan_dr * iL;
-  A11[10] = dt * (v * (tr2 + 1)) * iL;
-  *b21 = 0.5 * dt * dt * v * (tr2 + 1) * iL;
+  A11[7] = CILQR_DIVL(P, 0.5 * dt * dt * v * vm * (td2 + 1) * cm);
+  A11[8] = CILQR_DIVL(P, dt * tan_dr);
+  A11[9] = CILQR_DIVL(P, 0.5 * dt * dt * tan_dr);
+  A11[10] = CILQR_DIVL(P, dt * (v * (tr2 + 1)));
+  *b21 = CILQR_DIVL(P, 0.5 * dt * dt * v * (tr2 + 1));
 }
 
 // Barrier value accumulator: sum of -rt*log(-g) over the log branch is -rt*log(prod(-g)).
@@ -461,6 +506,7 @@ __device__ __forceinline__ int nearest_segment(const double* sg0, const double* 
   return bi;
 }
 
+#if !CILQR_STRICT
 // ------------------------------------------------------------------------------------------
 // TotalCost of the trajectory in slot Xs (ilqr_optimizer.cc:417-436), [8][Kc]: x0..x5, u0, u1, in two
 // passes:
@@ -780,6 +826,8 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
   }
 }
 
+#endif  // !CILQR_STRICT
+
 // ---- Backward (ilqr_optimizer.cc:334-390) in augmented, lane-uniform form --------------------
 // With z = (x, 1) and F = [A | B] (6 x 8) one knot of the recursion is
 //   M   = [Vxx ; Vx^T]                       7 x 6   value function (row 6 = gradient)
@@ -815,6 +863,9 @@ __device__ __forceinline__ int h_off(int p, int q) {  // offset of Hh[p][q], p <
   return LZ;
 }
 
+#if CILQR_STRICT
+#include "cilqr_strict.cuh"
+#else
 constexpr int SM_ = 0;    // 42  M   [7][6]
 constexpr int SG = 42;    // 56  G   [7][8]
 constexpr int SQH = 98;   // 64  Qh  [8][8]
@@ -1045,6 +1096,8 @@ __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double d
   dV[1] = warp_sum(acc1);
 }
 
+#endif  // CILQR_STRICT
+
 // iqr, ilqr_optimizer.cc:793-824: time-varying LQR about the goals (zero control), Q = diag(1e-3, 1e-3,
 // 1e-3, 1e-3, 1e-2, 5e-3), R = diag(0.2, 0.05) (off-diagonals 0, quirk Q4).  It is the Riccati recursion of
 // Backward with Jx = Ju = 0, Hx = Q, Hu = R, lambda = 0 -- K_k = (R + B'PB)^-1 B'PA, P = Q + A'P(A - BK) is
@@ -1084,6 +1137,11 @@ __device__ void iqr_records(const Ctx& c, double* Xs) {
     rec[LHX + 8] = Qd[5];
     rec[LHU] = 0.2;
     rec[LHU + 1] = 0.05;
+#if CILQR_STRICT
+    rec[LH10] = 0.0;
+    rec[LH10 + 1] = 0.0;
+    rec[LH10 + 2] = 0.0;
+#endif
     rec[LZ] = 0.0;
     rec[LO] = 1.0;
     rec[LDT] = P.dt;
@@ -1457,8 +1515,8 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, double*
       double s0 = Kk[0] * dx[0], s1 = Kk[6] * dx[0];
 #pragma unroll
       for (int i = 1; i < 6; ++i) {
-        s0 = fma(Kk[i], dx[i], s0);
-        s1 = fma(Kk[6 + i], dx[i], s1);
+        s0 = CILQR_FMA(Kk[i], dx[i], s0);
+        s1 = CILQR_FMA(Kk[6 + i], dx[i], s1);
       }
       double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
       double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
@@ -1551,7 +1609,12 @@ __device__ __noinline__ int phase_back(Ctx& c) {
   const double lambda = iqr ? 0.0 : h->lambda;
   const double* Xs = c.slot(h->cur);
   double dV[2];
+#if CILQR_STRICT
+  if (iqr) s_iqr_sweep(c);
+  else backward_pass(c, lambda, dV);
+#else
   backward_pass(c, lambda, dV);
+#endif
   __syncwarp();
   if (iqr) {  // gains of the LQR initial guess (:793-824) are in place: roll it out (:830-841)
     if (lane == 0) {
@@ -1572,6 +1635,9 @@ __device__ __noinline__ int phase_back(Ctx& c) {
     }
   }
   // CalGradientNorm (:322-332)
+#if CILQR_STRICT
+  const double gnorm = s_gradient_norm(c, Xs);
+#else
   double acc = 0.0;
 #pragma unroll 1
   for (int k = lane; k < N; k += 32) {
@@ -1580,6 +1646,7 @@ __device__ __noinline__ int phase_back(Ctx& c) {
     acc += fmax(v0, v1);
   }
   const double gnorm = warp_sum(acc) / N;
+#endif
   if (dbg && dbg->gnorm && lane == 0) dbg->gnorm[b] = gnorm;
   if (gnorm < 1e-6 && lambda < 1e-5) {
     if (lane == 0) h->status = 2;

@@ -104,24 +104,25 @@ EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_d
            "cilqr_corridor_last_kernel_ms", "cilqr_dp_default_config", "cilqr_dp_num_knots",
            "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms"]
 
-_lib = None
+_libs = {}
 
 
-def lib_path() -> str:
-    return _build.LIB_PATH
+def lib_path(variant: str = "") -> str:
+    return _build.STRICT_LIB_PATH if variant == "strict" else _build.LIB_PATH
 
 
-def load_library(build_if_missing: bool = True):
-    """Loads libcilqr_b200.so (building it with nvcc when absent).  Raises if that fails."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if build_if_missing and _build.is_stale():
-        _build.build_library()
-    if not os.path.exists(_build.LIB_PATH):
-        raise CilqrError(E_NO_DEVICE, f"{_build.LIB_PATH} is missing and could not be built; "
+def load_library(build_if_missing: bool = True, variant: str = ""):
+    """Loads libcilqr_b200.so (building it with nvcc when absent).  Raises if that fails.
+    variant="strict" loads the parity instrument libcilqr_b200_strict.so instead (tests / bench parity legs only)."""
+    if variant in _libs:
+        return _libs[variant]
+    path = lib_path(variant)
+    if build_if_missing and _build.is_stale(path):
+        _build.build_library(strict=variant == "strict")
+    if not os.path.exists(path):
+        raise CilqrError(E_NO_DEVICE, f"{path} is missing and could not be built; "
                          "the CUDA extension is required (no CPU fallback)")
-    L = C.CDLL(_build.LIB_PATH)
+    L = C.CDLL(path)
     L.cilqr_abi_version.restype = C.c_int
     L.cilqr_default_params.argtypes = [C.POINTER(Params)]
     L.cilqr_default_params.restype = None
@@ -161,7 +162,7 @@ def load_library(build_if_missing: bool = True):
     L.cilqr_dp_plan_batch_device.argtypes = [C.c_void_p, C.POINTER(DpConfig), C.POINTER(DpIn), C.POINTER(DpOut),
                                              C.c_void_p]
     L.cilqr_dp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-    _lib = L
+    _libs[variant] = L
     return L
 
 
@@ -204,8 +205,8 @@ class Solver:
     """Owns one cilqr_handle (device buffers + streams) on ``device``."""
 
     def __init__(self, params: Params | None = None, device: int = 0, N_max: int = 200,
-                 M_max: int = 32, S_max: int = 64, B_max: int = 1 << 21):
-        self._L = load_library()
+                 M_max: int = 32, S_max: int = 64, B_max: int = 1 << 21, variant: str = ""):
+        self._L = load_library(variant=variant)
         self.params = params or default_params()
         h = C.c_void_p()
         rc = self._L.cilqr_create(C.byref(self.params), device, N_max, M_max, S_max, B_max, C.byref(h))

@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libcilqr_oracle.so")
+_MAKE_TARGET = "libcilqr_oracle.so"  # (oracle/binding_pm.py re-executes this module for libcilqr_oracle_pm.so)
 
 STATUS_NAMES = ["converged_abs", "converged_rel", "converged_grad", "lambda_overflow", "max_iter"]
 
@@ -51,10 +52,9 @@ class Result(C.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "cilqr_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "cilqr_oracle.h"))):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libcilqr_oracle.so"],
-                              stdout=subprocess.DEVNULL)
+    deps = [src, os.path.join(_HERE, "cilqr_oracle.h"), os.path.join(_HERE, "..", "cilqr_b200", "csrc", "pm_math.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["make", "-C", _HERE, "-B", _MAKE_TARGET], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 

@@ -24,6 +24,21 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef CILQR_PM_LIBM
+/* libcilqr_oracle_pm.so: the same restatement with sin / cos / tan / log / hypot taken from the portable libm that
+ * the STRICT build of the CUDA kernel uses too (cilqr_b200/csrc/pm_math.h: same source on host and device, hence
+ * bit-identical results on both).  Strict GPU output is compared with THIS build bit for bit; the default build
+ * (glibc libm, pinned against the compiled reference) differs from it only through the last bits of those five
+ * functions -- tests/test_oracle_golden.py measures how far that moves whole solves.  fmod, sqrt, fabs, fmin, fmax are
+ * exact / IEEE in glibc and in CUDA and stay as they are. */
+#include "../cilqr_b200/csrc/pm_math.h"
+#define sin pm_sin
+#define cos pm_cos
+#define tan pm_tan
+#define log pm_log
+#define hypot pm_hypot
+#endif
+
 #define NX 6
 #define NU 2
 

@@ -4,24 +4,32 @@
 // iter_trajs[0] and cost().
 //
 //   adapter_demo <scenario.bin> <result.bin>
+//   adapter_demo --latency <repeat> <scenario.bin>...   one IlqrOptimizer, `repeat` timed Plan calls per scenario
+//                                                       (after one warm-up call); prints "LAT <file#> <ms>" lines
 // scenario.bin (doubles): N, M_max, S_left, S_right, start[4], coarse[K][6], cnt[K], corridor[K][M_max][3],
 //                         lane_left[S_left][7], lane_right[S_right][7]
 // result.bin   (doubles): ok, status, iters, n_cost, n_iter_trajs, opt[K][13], iter0[K][13], cost[n_cost][5]
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cilqr/ilqr_optimizer_b200.h"
 
 using namespace planning;
 
-int main(int argc, char** argv) {
-  if (argc < 3) {
-    std::fprintf(stderr, "usage: %s scenario.bin result.bin\n", argv[0]);
-    return 2;
-  }
-  FILE* f = std::fopen(argv[1], "rb");
-  if (!f) return 2;
+struct Scenario {
+  int N = 0, M_max = 0, K = 0;
+  TrajectoryPoint start_state;
+  std::vector<TrajectoryPoint> coarse;
+  CorridorConstraints corridor;
+  LaneConstraints left, right;
+};
+
+static bool load_scenario(const char* path, Scenario* sc) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return false;
   std::vector<double> d;
   double buf[1024];
   size_t n;
@@ -30,20 +38,24 @@ int main(int argc, char** argv) {
   size_t o = 0;
   const int N = (int)d[o++], M_max = (int)d[o++], S_left = (int)d[o++], S_right = (int)d[o++];
   const int K = N + 1;
-  TrajectoryPoint start_state;
+  sc->N = N;
+  sc->M_max = M_max;
+  sc->K = K;
+  TrajectoryPoint& start_state = sc->start_state;
   start_state.x = d[o]; start_state.y = d[o + 1]; start_state.theta = d[o + 2]; start_state.velocity = d[o + 3];
   o += 4;
-  std::vector<TrajectoryPoint> coarse(K);
+  std::vector<TrajectoryPoint>& coarse = sc->coarse;
+  coarse.resize(K);
   for (int k = 0; k < K; ++k, o += 6) {
     coarse[k].x = d[o]; coarse[k].y = d[o + 1]; coarse[k].theta = d[o + 2];
     coarse[k].velocity = d[o + 3]; coarse[k].a = d[o + 4]; coarse[k].delta = d[o + 5];
   }
   std::vector<int> cnt(K);
   for (int k = 0; k < K; ++k) cnt[k] = (int)d[o++];
-  CorridorConstraints corridor(K);
+  sc->corridor = CorridorConstraints(K);
   for (int k = 0; k < K; ++k)
     for (int m = 0; m < M_max; ++m, o += 3)
-      if (m < cnt[k]) corridor[k].push_back(Eigen::Vector3d(d[o], d[o + 1], d[o + 2]));
+      if (m < cnt[k]) sc->corridor[k].push_back(Eigen::Vector3d(d[o], d[o + 1], d[o + 2]));
   auto read_lane = [&](int S) {
     LaneConstraints lane;
     for (int s = 0; s < S; ++s, o += 7)
@@ -51,7 +63,55 @@ int main(int argc, char** argv) {
                         math::LineSegment2d(math::Vec2d(d[o + 3], d[o + 4]), math::Vec2d(d[o + 5], d[o + 6])));
     return lane;
   };
-  LaneConstraints left = read_lane(S_left), right = read_lane(S_right);
+  sc->left = read_lane(S_left);
+  sc->right = read_lane(S_right);
+  return true;
+}
+
+// config 0 of BASELINE.json is the reference's actual use: one ego, one Plan call per click
+// (planning_node.cc:82-88).  Wall-clock latency of that call through the drop-in class.
+static int latency_mode(int repeat, int nfiles, char** files) {
+  std::vector<Scenario> scs(nfiles);
+  for (int i = 0; i < nfiles; ++i)
+    if (!load_scenario(files[i], &scs[i])) return 2;
+  IlqrConfig config;
+  VehicleParam vehicle;
+  const double dt = 0.1;
+  IlqrOptimizer opt(config, vehicle, scs[0].N * dt, dt);
+  DiscretizedTrajectory out;
+  std::vector<DiscretizedTrajectory> iters;
+  if (!opt.Plan(scs[0].start_state, DiscretizedTrajectory(scs[0].coarse), scs[0].corridor, scs[0].left, scs[0].right,
+                &out, &iters))
+    return 1;  // warm-up: creates the handle, allocates the staging buffers
+  for (int i = 0; i < nfiles; ++i) {
+    const Scenario& sc = scs[i];
+    const DiscretizedTrajectory coarse(sc.coarse);
+    for (int r = 0; r < repeat; ++r) {
+      iters.clear();
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool ok = opt.Plan(sc.start_state, coarse, sc.corridor, sc.left, sc.right, &out, &iters);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (!ok) return 1;
+      std::printf("LAT %d %.6f %d %d\n", i, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                  opt.last_status(), opt.last_iterations());
+    }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 4 && std::strcmp(argv[1], "--latency") == 0) return latency_mode(std::atoi(argv[2]), argc - 3, argv + 3);
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s scenario.bin result.bin\n", argv[0]);
+    return 2;
+  }
+  Scenario sc;
+  if (!load_scenario(argv[1], &sc)) return 2;
+  const int N = sc.N, K = sc.K;
+  const TrajectoryPoint& start_state = sc.start_state;
+  const std::vector<TrajectoryPoint>& coarse = sc.coarse;
+  const CorridorConstraints& corridor = sc.corridor;
+  const LaneConstraints &left = sc.left, &right = sc.right;
 
   IlqrConfig config;
   VehicleParam vehicle;

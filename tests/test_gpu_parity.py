@@ -1,15 +1,20 @@
-"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+"""GPU parity: the PRODUCTION CUDA path (through the C ABI) against the CPU oracle on identical inputs.
 
-Tolerances.  The reference computes in IEEE double and so does the kernel, but the kernel sums in a
-different order (warp reductions over knots, FMA contraction, log of a product instead of a sum of
-logs), i.e. results differ at the 1e-16 relative level per operation.  The solve itself is a chain
-of accept/reject decisions and, on a few ill-conditioned scenarios, amplifies such differences by
-many orders of magnitude (the oracle does the same to itself when recompiled with FMA contraction:
-test_rounding_noise_floor_of_the_oracle).  Hence:
+What is compared with what.  The kernel's LOGIC is proven separately and exactly: the strict build of the same
+kernel (reference-ordered arithmetic, portable libm) reproduces the oracle bit for bit on every scenario
+(tests/test_gpu_strict.py).  The production build evaluates the same expressions with re-associated sums (warp
+reductions over knots, log of a product instead of a sum of logs), fused multiply-adds and CUDA's libm, i.e. it
+differs from the reference by ~1e-16 relative per operation.  A CILQR solve is a chain of accept / reject decisions
+with a stiff barrier; on a few ill-conditioned scenarios it amplifies such rounding by many orders of magnitude.
+That tail is a property of the reference algorithm, not of this kernel: the oracle shows the same tail against
+ITSELF when only its libm is exchanged (glibc -> pm_math.h: 2043/2048 identical paths, 8 of those beyond 1e-4) or only
+FMA contraction is enabled (2044/2048, 13 beyond 1e-4) -- tests/test_oracle_golden.py.  Hence, for the production build:
   * stage level (one linearisation / backward / forward / cost on the same iterate): 1e-9 relative;
-  * full solves: identical (status, iteration count, line-search sequence) on >= 97 % of scenarios,
-    and on those states/controls within 1e-4 relative (the north-star tolerance) for >= 99 %,
-    median below 1e-10; every mismatch is counted and printed, never hidden.
+  * full solves: identical (status, iteration count, line-search sequence) and, on those, states/controls within
+    1e-4 relative (the north-star tolerance) on all but a measured tail.  Measured on B200 (profiles/r02_*):
+    N=30 256/256 and 1.0000; N=50 1023/1024 and 0.9990; N=100 510/512 and 0.9980; N=200 64/64 and 1.0000;
+    shipped road N=80 127/128 and 0.9921; the 4 096-scenario sample of the bench workload 4085/4096 and 0.9973.
+    The thresholds below are those figures minus a small margin; every mismatch is counted and printed, never hidden.
 """
 import ctypes as C
 
@@ -43,7 +48,7 @@ def _solve_device(solver, batch):
     return X.cpu().numpy(), U.cpu().numpy(), S.cpu().numpy()
 
 
-def _compare(oracle, batch, Xg, Ug, Sg, min_same=0.97, min_within=0.99):
+def _compare(oracle, batch, Xg, Ug, Sg, min_same=0.985, min_within=0.985):
     import os
     Xo, Uo, So, _ = oracle.solve_batch(batch, nthreads=os.cpu_count() or 1)
     same = (Sg[:, 0] == So[:, 0]) & (Sg[:, 1] == So[:, 1]) & (Sg[:, 7] == So[:, 7])
@@ -168,7 +173,7 @@ def test_shipped_road_and_horizon(solver, oracle):
     the relative-cost test after 0-2 iterations with a huge cost -- same exits as the oracle."""
     batch = scenarios.generate(20260101, 0, 128, N=80, n_obs=11, road_name="shipped")
     Xg, Ug, Sg = _solve_device(solver, batch)
-    _compare(oracle, batch, Xg, Ug, Sg, min_same=0.95, min_within=0.97)
+    _compare(oracle, batch, Xg, Ug, Sg, min_same=0.97, min_within=0.97)
 
 
 def test_golden_fixture(solver):
@@ -305,11 +310,11 @@ def test_edge_cases(solver, oracle):
     rb = scenarios.ScenarioBatch(batch.N, batch.M_max, batch.S, batch.start, batch.coarse, batch.corridor,
                                  batch.corridor_cnt, np.ascontiguousarray(batch.lane_left[:, 3:4]), batch.lane_right)
     Xg, Ug, Sg = _solve_device(solver, rb)
-    _compare(oracle, rb, Xg, Ug, Sg, min_same=0.8)
+    _compare(oracle, rb, Xg, Ug, Sg, min_same=0.875)  # measured 8/8
     # shortest horizon
     b1 = scenarios.generate(22, 0, 4, N=1)
     Xg, Ug, Sg = _solve_device(solver, b1)
-    _compare(oracle, b1, Xg, Ug, Sg, min_same=0.75)
+    _compare(oracle, b1, Xg, Ug, Sg, min_same=0.75)  # measured 4/4
     # empty batch is a no-op
     e = batch.slice(0, 0)
     out = solver.plan_batch(e)
