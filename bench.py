@@ -522,6 +522,7 @@ def main():
         k_ms.append(ek0.elapsed_time(ek1))
         serial_ms += ek0.elapsed_time(eg)
     lib_kernel_ms = solver.last_kernel_ms()  # the library's own event pair around its last solve launch
+    sched = solver.debug_stats()             # scheduler counters of that launch (summed over all warps)
     # ---- (2) the timed region: K steps, up to F batches in flight
     clocks = ClockSampler(local)
     clocks.start()
@@ -628,7 +629,8 @@ def main():
                                      "each waited for before the next is enqueued",
                        "l2_policy": f"inputs ({batch.input_bytes() / 1e9:.2f} GB per GPU) exceed the 126 MB L2; no flush",
                        "converged_fraction": conv_total / total, "mean_iterations": iters_mean,
-                       "warps_per_sm": warps, "smem_bytes_per_warp": smem, "scenario_gen_s": round(gen_s, 1)},
+                       "warps_per_sm": warps, "smem_bytes_per_warp": smem, "scenario_gen_s": round(gen_s, 1),
+                       "scheduler": {**sched, "per_trajectory": {k: round(v / B, 2) for k, v in sched.items()}}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": cap_note,
                          "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,

@@ -30,11 +30,13 @@ namespace {
 constexpr int kSlots = 2;           // double buffering of the host path
 constexpr int kStatsWords = 8 + 2 + 256 + 12;  // scheduler counters, start time, completion histogram (2 ms buckets)
 constexpr int kDefaultChunk = 4096; // scenarios per H2D chunk (watermark granularity) on the host path
+constexpr int kRelayCap = 8192;     // entries per hand-over list of the drain relay (>= 1 + SMs * first threshold)
 
 struct Slot {
   cudaStream_t stream = nullptr;
   unsigned int* ticket = nullptr;       // device [4]: scenario counter, error bits, scenarios finished, pad
   unsigned int* flags_host = nullptr;   // pinned [4]: the same words after the launch (host path)
+  unsigned int* relay = nullptr;        // device [2][kRelayCap]: the two hand-over lists of the drain relay
   int launched_B = -1;                  // batch size of the last launch on this slot (-1: none to check)
   unsigned long long* stats = nullptr;  // scheduler counters of the last launch (cilqr_debug_stats)
   double* ws = nullptr;
@@ -284,6 +286,7 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.controls = out->controls;
   a.status = out->status;
   a.trajectory = out->trajectory;
+  a.result = out->result;
   a.init_states = out->init_states;
   a.init_controls = out->init_controls;
   a.cost_hist = out->cost_hist;
@@ -323,11 +326,55 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
     a.dbg.gnorm = dbg->gnorm;
   }
   CK(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned int), stream));
+  // Drain relay (optional, full grids only; OFF by default -- see DESIGN.md section 2.5 for the measurements).
+  // Stage 1 solves the batch until a CTA is down to thr[0] unfinished contexts and hands those over; every later
+  // stage packs the leftovers of the previous one kMaxCtx per CTA into a smaller grid and hands over again at its
+  // own threshold; the last stage runs to the end.  It trades single-batch latency (a stage starts when the
+  // previous one has ended everywhere) for SMs that are free for the next batch's kernel during the drain.
+  // Results do not depend on it: a context is self-contained and every phase of it is run by exactly one warp
+  // with the same code.  CILQR_B200_RELAY="t1,t2,..." (development knob).
+  int thr[6] = {0, 0, 0, 0, 0, 0}, n_thr = 0;
+  if (const char* e = getenv("CILQR_B200_RELAY")) {
+    const char* p = e;
+    while (n_thr < 6 && *p) {
+      thr[n_thr++] = atoi(p);
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  }
+  bool relay = !dbg && n_thr > 0 && thr[0] > 0 && L.grid == h->num_sms && L.ctx > thr[0] &&
+               1 + (long long)L.grid * thr[0] <= kRelayCap;
+  for (int i = 1; relay && i < n_thr; ++i) relay = thr[i] < thr[i - 1];
+  unsigned int* lists[2] = {s->relay, s->relay + kRelayCap};
+  if (relay) CK(cudaMemsetAsync(s->relay, 0, 2 * kRelayCap * sizeof(unsigned int), stream));
+  a.donate_thr = relay ? thr[0] : 0;
+  a.donate = relay ? lists[0] : nullptr;
+  a.resume = nullptr;
+  a.resume_per_cta = 0;
   CK(cudaEventRecord(s->ev0, stream));
   cilqr::cilqr_solve_kernel<<<L.grid, 32 * L.warps, L.sm.total_bytes * L.warps, stream>>>(a);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(s->ev1, stream));
   h->launches += 1;
+  if (relay) {
+    KernelArgs r = a;
+    int prev_grid = L.grid;
+    for (int st = 0; st < n_thr && thr[st] > 0; ++st) {
+      const int per = cilqr::kMaxCtx;
+      const int grid = (prev_grid * thr[st] + per - 1) / per;  // upper bound of the entries / per
+      const int next_thr = st + 1 < n_thr ? thr[st + 1] : 0;
+      r.ctx_per_cta = per;
+      r.resume = lists[st & 1];
+      r.resume_per_cta = per;
+      r.donate_thr = next_thr;
+      r.donate = next_thr > 0 ? lists[(st + 1) & 1] : nullptr;
+      if (next_thr > 0) CK(cudaMemsetAsync(lists[(st + 1) & 1], 0, sizeof(unsigned int), stream));
+      cilqr::cilqr_solve_kernel<<<grid, 32 * L.warps, L.sm.total_bytes * L.warps, stream>>>(r);
+      CK(cudaGetLastError());
+      h->launches += 1;
+      prev_grid = grid;
+    }
+  }
+  CK(cudaEventRecord(s->ev1, stream));
   h->last_slot = (int)(s - h->slots);
   h->timed = true;
   s->launched_B = in->B;
@@ -397,6 +444,7 @@ const char* cilqr_strerror(int code) {
     case CILQR_E_NO_DEVICE: return "no CUDA device of compute capability 10.x (this library has no CPU fallback)";
     case CILQR_E_CAPACITY: return "request exceeds the capacity the handle was created with";
     case CILQR_E_SMEM: return "horizon does not fit the per-warp shared-memory stage";
+    case CILQR_E_NCCL: return "NCCL is missing or failed (only the gathered copy of cilqr_plan_sharded needs it)";
     case CILQR_E_TIMEOUT: return "the solve kernel did not finish every scenario (see cilqr_last_cuda_error); "
                                  "unsolved scenarios carry the NaN sentinel in their status row";
     default: return "unknown error";
@@ -470,6 +518,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
     if (cudaMalloc(&s->ticket, 4 * sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaHostAlloc((void**)&s->flags_host, 4 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess)
       return bail(CILQR_E_CUDA);
+    if (cudaMalloc(&s->relay, 2 * kRelayCap * sizeof(unsigned int)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaMalloc(&s->stats, kStatsWords * sizeof(unsigned long long)) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(CILQR_E_CUDA);
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(CILQR_E_CUDA);
@@ -488,6 +537,7 @@ void cilqr_destroy(cilqr_handle* h) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ticket) cudaFree(s->ticket);
     if (s->flags_host) cudaFreeHost(s->flags_host);
+    if (s->relay) cudaFree(s->relay);
     if (s->stats) cudaFree(s->stats);
     if (s->ws) cudaFree(s->ws);
     if (s->in_buf) cudaFree(s->in_buf);
@@ -604,6 +654,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   const size_t in_need = up(b_start * B) + up(b_coarse * B) + up(b_corr * B) + up(b_cnt * B) + up(b_ll * B) + up(b_lr * B);
   size_t out_need = up(b_st * B) + up(b_ct * B) + up(b_status * B);
   if (out->trajectory) out_need += up(b_traj * B);
+  if (out->result) out_need += up(b_traj * B);
   if (out->init_states) out_need += up(b_st * B);
   if (out->init_controls) out_need += up(b_ct * B);
   if (out->cost_hist) out_need += up(b_ch * B);
@@ -667,7 +718,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
     }
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
   };
-  bool staged[10];
+  bool staged[11];
   int n_out = 0;
   auto carve = [&](void* host, size_t per) -> char* {
     staged[n_out] = false;
@@ -697,6 +748,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   dout.iter_states = (double*)carve(out->iter_states, b_is);
   dout.iter_controls = (double*)carve(out->iter_controls, b_ic);
   dout.hist_len = (int32_t*)carve(out->hist_len, b_hl);
+  dout.result = (double*)carve(out->result, b_traj);
   // Order of enqueueing: watermark = 0, then EVERY input chunk with its watermark update on the copy stream,
   // and only then the kernel on the solve stream.  The kernel therefore never depends on work that is
   // enqueued after its launch: when launches are synchronous (ncu, CUDA_LAUNCH_BLOCKING=1, a debugger) the
@@ -752,6 +804,7 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   CK(d2h(out->iter_states, dout.iter_states, b_is));
   CK(d2h(out->iter_controls, dout.iter_controls, b_ic));
   CK(d2h(out->hist_len, dout.hist_len, b_hl));
+  CK(d2h(out->result, dout.result, b_traj));
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(s->stream));
   return check_launch(h, s, s->flags_host);

@@ -174,7 +174,7 @@ struct CtxHdr {
   int iter, status, cur, nflip, ai, gb, rmode, emode, n_cost, n_iter_traj;
   unsigned int retired, deferred;  // line-search lanes whose rollout blew up / needs the general wrap
   int imode;  // 1 while the context builds its initial guess (the BACK phase then runs the iqr sweep)
-  int pad_;
+  int wait;   // the phase this context waits for, written when it is handed to a later launch (drain relay)
 };
 static_assert(sizeof(CtxHdr) == kHdrDoubles * 8, "CtxHdr size");
 
@@ -202,6 +202,7 @@ struct KernelArgs {
   double* controls;
   double* status;
   double* trajectory;
+  double* result;
   double* init_states;
   double* init_controls;
   double* cost_hist;
@@ -213,6 +214,13 @@ struct KernelArgs {
   unsigned int* ticket;  // [0] scenario counter, [1] error bits (kErr*), [2] scenarios finished
   const unsigned int* ready;  // host path: scenarios below *ready have arrived on the device (NULL: all)
   unsigned long long watchdog_ns;  // how long INIT waits for the watermark before it flags kErrStarved
+  // Drain relay (see cilqr_solve_kernel): once the batch's ticket is exhausted and a CTA has at most donate_thr
+  // unfinished contexts left, it appends them to `donate` ([0] = count, then global context indices) and exits;
+  // the next launch of the relay adopts `resume` (same layout), resume_per_cta contexts per CTA.
+  int donate_thr;
+  unsigned int* donate;
+  const unsigned int* resume;
+  int resume_per_cta;
   unsigned long long* stats;  // optional [8 + 2 + 256]: completion-time histogram (2 ms buckets) after the counters; [8]: scheduler passes, idle polls, failed claims, phases run by type (4), type switches
   DebugPtrs dbg;
   int debug;             // 1: stop after the first line-search evaluation and dump stages
@@ -1220,6 +1228,38 @@ __device__ __noinline__ void finish_scenario(const Ctx& c) {
       a.hist_len[b * 2 + 1] = h->n_iter_traj;
     }
   }
+  if (a.result) {
+    // TrajectoryPlanner::Plan's post-processing of opt_trajectory (trajectory_planner.cpp:103-125): the same
+    // record with the station accumulated point by point (sequentially, like the reference's running sum)
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+      double* tp = a.result + (b * K + k) * 13;
+      const double de = Xs[5 * a.Kc + k];
+      tp[0] = P.dt * k;
+      tp[1] = k > 0 ? nt_hypot(Xs[k] - Xs[k - 1], Xs[a.Kc + k] - Xs[a.Kc + k - 1]) : 0.0;  // segment length for now
+      tp[2] = Xs[k];
+      tp[3] = Xs[a.Kc + k];
+      tp[4] = Xs[2 * a.Kc + k];
+      tp[5] = nt_tan(de) / P.L;
+      tp[6] = Xs[3 * a.Kc + k];
+      tp[7] = Xs[4 * a.Kc + k];
+      tp[8] = k < N ? Xs[6 * a.Kc + k] : 0.0;
+      tp[9] = de;
+      tp[10] = k < N ? Xs[7 * a.Kc + k] : 0.0;
+      tp[11] = 0.0;
+      tp[12] = 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double acc = 0.0;
+      double* tp = a.result + b * K * 13;
+      for (int k = 0; k < K; ++k) {
+        acc += k > 0 ? tp[k * 13 + 1] : 0.0;
+        tp[k * 13 + 1] = acc;
+      }
+    }
+    __syncwarp();
+  }
   if (a.trajectory) {
     // TransformToTrajectory (:771-791): time, s, x, y, theta, kappa, velocity, a, jerk, delta, delta_rate, lb, rb
 #pragma unroll 1
@@ -1445,12 +1485,15 @@ __device__ __noinline__ int phase_init(Ctx& c) {
 // A lane whose state stops being finite is RETIRED: every later state of that rollout would be non-finite
 // too, its cost NaN/inf, and the reference rejects such a step (the comparisons of :258 are false).
 constexpr int kRollGroups = 8;
-__device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, double* cta_ws, int my_id, int lane) {
+__device__ __forceinline__ double* ctx_base(const KernelArgs& a, const int* gidx, int id) {
+  return a.ws + (size_t)gidx[id] * a.cl.stride;  // gidx: the CTA's slot -> global context index table (shared memory)
+}
+__device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const int* gidx, int my_id, int lane) {
   const DevParams& P = a.P;
   const int g = lane >> 2, ai = lane & 3;
   const bool valid = my_id >= 0;
   const int id0 = __shfl_sync(kFull, my_id, 0);  // group 0 is always valid: benign operands for empty groups
-  double* cx = cta_ws + (size_t)(valid ? my_id : id0) * a.cl.stride;
+  double* cx = ctx_base(a, gidx, valid ? my_id : id0);
   CtxHdr* h = reinterpret_cast<CtxHdr*>(cx + a.cl.hdr);
   const int cur = h->cur, rmode = h->rmode;
   const int gb = rmode == 0 ? 0 : h->gb;
@@ -1569,7 +1612,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, double*
     for (int gg = 0; gg < kRollGroups; ++gg) {
       const int id = __shfl_sync(kFull, my_id, gg * 4), rm = __shfl_sync(kFull, rmode, gg * 4);
       if (id < 0 || rm != 0) continue;
-      double* cg = cta_ws + (size_t)id * a.cl.stride;
+      double* cg = ctx_base(a, gidx, id);
       const CtxHdr* hg = reinterpret_cast<const CtxHdr*>(cg + a.cl.hdr);
       const int curg = __shfl_sync(kFull, cur, gg * 4);
       const double* src = cg + a.cl.slots + cand_slot(curg, 0) * 8 * a.Kc;
@@ -1996,7 +2039,7 @@ __device__ __noinline__ int gang_lin(Ctx& c, HelpBoard* hb, int mine) {
 }
 
 // An idle warp looks at the board; returns true if it evaluated a candidate for somebody.
-__device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, double* cta_ws, HelpBoard* hb, int lane) {
+__device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, const int* gidx, HelpBoard* hb, int lane) {
   const int owner = *(volatile int*)&hb->owner;
   const int nx = *(volatile int*)&hb->next;
   if (owner < 0 || nx >= *(volatile int*)&hb->n || nx >= kHelpClosed) return false;
@@ -2008,7 +2051,7 @@ __device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, double
   // the request is stable from here on: its owner waits for done[k] before it changes anything
   const int id = *(volatile int*)&hb->owner;
   const int cur = hb->cur;
-  Ctx c(a, smem, cta_ws + (size_t)id * a.cl.stride, lane);
+  Ctx c(a, smem, ctx_base(a, gidx, id), lane);
   c.bind(c.h->b);
   if (*(volatile int*)&hb->kind == 1) {
     linearize_window(c, k * kWin, c.slot(cur), c.nidx(cur), nullptr, 0);
@@ -2047,17 +2090,42 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   __shared__ int s_iter[kMaxCtx];  // iterations run so far by the scenario in each context (claim priority)
   __shared__ HelpBoard s_help;
   __shared__ int s_type;
+  __shared__ int s_gidx[kMaxCtx];  // slot -> global context index (contexts live at a.ws + index * stride)
+  __shared__ int s_drained;        // the batch's ticket is exhausted: no INIT will produce work any more
+  __shared__ int s_donating;       // this CTA is handing its unfinished contexts to the next launch of the relay
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int C = a.ctx_per_cta;
   double* smem = smem_cta + (size_t)warp * (a.sm.total_bytes / 8);
-  double* cta_ws = a.ws + (size_t)blockIdx.x * C * a.cl.stride;
-  for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
-    s_state[i] = i < C ? PH_INIT : PH_DONE;
-    s_iter[i] = 0;
+  if (a.resume) {
+    // a later launch of the drain relay: adopt up to resume_per_cta contexts that the previous launch left
+    // unfinished, wherever in the workspace they live; they resume at the phase they were waiting for
+    const unsigned n = a.resume[0];
+    const unsigned first = (unsigned)blockIdx.x * (unsigned)a.resume_per_cta;
+    if (first >= n) return;  // (uniform for the CTA)
+    for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
+      int st = PH_DONE, it = 0, g = 0;
+      if (i < a.resume_per_cta && first + i < n) {
+        g = (int)a.resume[1 + first + i];
+        const CtxHdr* hd = reinterpret_cast<const CtxHdr*>(a.ws + (size_t)g * a.cl.stride + a.cl.hdr);
+        st = hd->wait;
+        it = hd->iter;
+      }
+      s_gidx[i] = g;
+      s_state[i] = st;
+      s_iter[i] = it;
+    }
+  } else {
+    for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
+      s_gidx[i] = blockIdx.x * C + i;
+      s_state[i] = i < C ? PH_INIT : PH_DONE;
+      s_iter[i] = 0;
+    }
   }
   if (threadIdx.x == 0) {
-    s_type = PH_INIT;
+    s_type = a.resume ? PH_BACK : PH_INIT;
+    s_drained = a.resume ? 1 : 0;
+    s_donating = 0;
     s_help.owner = -1;
     s_help.next = kHelpClosed;
     s_help.n = 0;
@@ -2068,7 +2136,6 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     atomicMin(a.stats + 8, now);
   }
   __syncthreads();
-  // typical duration of the phases relative to one another: INIT 5, BACK 4, ROLL 5, EVAL 3
   // typical duration of the phases relative to one another: INIT 5, BACK 2, ROLL 5, EVAL 3, LIN 3
   const int wt[kNumTypes] = {5, 2, 5, 3, 3};
   unsigned naps = 0;
@@ -2094,7 +2161,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       for (int w = 0; w < kCtxWords; ++w) b |= sl[w] == ST_BUSY;
       if (!__any_sync(kFull, b)) break;  // every context is DONE
       // the remaining contexts are all being run by other warps: help one of them if it asks ...
-      if (help_once(a, smem, cta_ws, &s_help, lane)) {
+      if (help_once(a, smem, s_gidx, &s_help, lane)) {
         naps = 0;
         continue;
       }
@@ -2109,6 +2176,41 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       continue;
     }
     naps = 0;
+    // ---- drain relay: the ticket is exhausted (contexts waiting for INIT are dead) and this CTA is down to its
+    // last few contexts -- too few to keep sixteen warps busy, yet they would hold the SM (all of its registers)
+    // for as long as the slowest of them runs.  Hand them to the next launch of the relay, which packs the
+    // leftovers of all CTAs into a few CTAs, and leave the SM to the next batch's kernel.  A context carries its
+    // whole state in the workspace; the phase it waits for goes into its header.
+    if (a.donate_thr > 0 && *(const volatile int*)&s_drained) {
+      int nb = 0;
+#pragma unroll
+      for (int w = 0; w < kCtxWords; ++w) nb += __popc(__ballot_sync(kFull, sl[w] == ST_BUSY));
+      const int live_d = nb + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+      if (live_d <= a.donate_thr || *(const volatile int*)&s_donating) {
+        if (lane == 0) s_donating = 1;
+#pragma unroll
+        for (int w = 0; w < kCtxWords; ++w) {
+          const int idx = lane + 32 * w;
+          const int stw = sl[w];
+          if (stw == PH_INIT) {
+            atomicCAS(&s_state[idx], PH_INIT, PH_DONE);
+          } else if (stw >= PH_BACK && stw <= PH_LIN) {
+            if (atomicCAS(&s_state[idx], stw, ST_BUSY) == stw) {
+              __threadfence();  // acquire the context, then publish it with its waiting phase
+              CtxHdr* hd = reinterpret_cast<CtxHdr*>(ctx_base(a, s_gidx, idx) + a.cl.hdr);
+              hd->wait = stw;
+              __threadfence();
+              const unsigned pos = atomicAdd(a.donate, 1u);
+              a.donate[1 + pos] = (unsigned)s_gidx[idx];
+              *(volatile int*)&s_state[idx] = PH_DONE;
+            }
+          }
+        }
+        __syncwarp();
+        __nanosleep(500);
+        continue;  // busy contexts are donated when their warps release them; then every slot is DONE
+      }
+    }
     // ---- hot contexts first: a scenario far beyond the mean iteration count (the batch has a few with 10x)
     // would otherwise advance one phase per epoch and finish long after everything else; it is taken
     // whatever it waits for and keeps its warp, phase after phase, until it exits
@@ -2143,7 +2245,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
         ok = __shfl_sync(kFull, ok, 0);
         if (ok) {
           __threadfence();  // acquire
-          Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
+          Ctx c(a, smem, ctx_base(a, s_gidx, mine), lane);
           int next = want_state;
           do {
             c.seg_staged = c.seg_staged && next == PH_EVAL;
@@ -2155,7 +2257,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
             if (next == PH_BACK) next = phase_back(c);
             else if (next == PH_LIN) next = gang_lin(c, &s_help, mine);
             else if (next == PH_ROLL) {
-              roll_multi(a, smem, cta_ws, lane < 4 ? mine : -1, lane);
+              roll_multi(a, smem, s_gidx, lane < 4 ? mine : -1, lane);
               __threadfence_block();
               next = PH_EVAL;
             } else if (c.h->emode == 1 && !a.debug) {
@@ -2170,10 +2272,11 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
               atomicAdd(a.stats + 272 + ph_now, 1ull);
             }
 #endif
-          } while (next != PH_INIT && next < PH_DONE);
+          } while (next != PH_INIT && next < PH_DONE && !*(const volatile int*)&s_donating);
           __threadfence();  // release
           if (lane == 0) {
-            s_iter[mine] = 0;
+            s_iter[mine] = (next == PH_INIT || next >= PH_DONE) ? 0 : c.h->iter;
+            if (next == PH_DONE) s_drained = 1;
             *(volatile int*)&s_state[mine] = next;
           }
           __syncwarp();
@@ -2246,7 +2349,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       }
       __threadfence();  // acquire
       st_ph[PH_ROLL] += got_n;
-      roll_multi(a, smem, cta_ws, my_id, lane);
+      roll_multi(a, smem, s_gidx, my_id, lane);
       __threadfence();  // release
       __syncwarp();
       if ((lane & 3) == 0 && my_id >= 0) *(volatile int*)&s_state[my_id] = PH_EVAL;
@@ -2262,7 +2365,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
       continue;
     }
     __threadfence();  // acquire: the context was last written by another warp (plain stores, read back by cp.async too)
-    Ctx c(a, smem, cta_ws + (size_t)mine * a.cl.stride, lane);
+    Ctx c(a, smem, ctx_base(a, s_gidx, mine), lane);
     int next = type;
     do {
       if (next == PH_ROLL) break;  // rollouts are batched eight contexts per warp: back to the scheduler
@@ -2277,6 +2380,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
     __threadfence();  // release
     if (lane == 0) {
       s_iter[mine] = next == PH_INIT || next == PH_DONE ? 0 : c.h->iter;
+      if (next == PH_DONE) s_drained = 1;  // phase_init found the ticket exhausted
       *(volatile int*)&s_state[mine] = next;
     }
     __syncwarp();

@@ -67,7 +67,9 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
     a.grid_start = (const int*)g;
     a.grid_idx = (const int*)(g + b0);
   }
-  const size_t smem = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn);
+  // the per-sample bounds of the dynamic obstacles go to shared memory while two CTAs per SM still fit (~110 KB each)
+  a.use_sample_bounds = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn, in->n_dyn, in->T, true) <= 110 * 1024 ? 1 : 0;
+  const size_t smem = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn, in->n_dyn, in->T, a.use_sample_bounds != 0);
   int per_sm = 1;
   CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp::dp_plan_kernel, dp::kMaxThreads, smem));
   if (per_sm < 1) per_sm = 1;

@@ -107,6 +107,7 @@ struct Args {
   int* ok;
   double* cost;
   double* waypoints;
+  int use_sample_bounds;  // the bounds of every sample of every dynamic obstacle fit the CTA's shared memory
 };
 
 // Host side: buckets the barrier points into square cells of a quarter of the collision box's side (a box reaches
@@ -327,31 +328,42 @@ __device__ bool check_static(const Args& a, int b, const double* obb, bool any_n
 }
 
 // Environment::CheckDynamicCollision, environment.cpp:124-141 (query time == last sample time: the reference
-// dereferences end(); the last sample is used)
-__device__ bool check_dynamic(const Args& a, int b, const double* obb, double time, double cx, double cy, double half) {
+// dereferences end(); the last sample is used).  The sample a query time selects (upper_bound over the obstacle's
+// sample times, :131-137) depends only on (obstacle, time); all transitions of a lattice layer query the same
+// nseg times, so the selection is tabulated once per layer (sidx[o * kMaxSeg + point], -1: outside the obstacle's
+// time range), and the bounds of every sample once per scenario (sbb, when they fit shared memory).
+constexpr int kMaxSeg = 32;  // points of one lattice segment (InterpolateLinearly): 16-17 for the shipped configuration
+__device__ __forceinline__ int dynamic_sample(const Args& a, size_t ob, double time) {
+  const int ns = a.dyn_samples[ob];
+  if (ns <= 0) return -1;
+  const double* tt = a.dyn_time + ob * a.T;
+  if (tt[0] > time || tt[ns - 1] < time) return -1;
+  int lo = 0, hi = ns;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    if (time < tt[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo >= ns ? ns - 1 : lo;
+}
+__device__ bool check_dynamic(const Args& a, int b, const double* obb, const double* sbb, const int* sidx, int point,
+                              double time, double cx, double cy, double half) {
   for (int o = 0; o < a.n_dyn; ++o) {
     if (aabb_disjoint(obb + 4 * (a.n_static + o), cx, cy, half)) continue;
     const size_t ob = (size_t)b * a.n_dyn + o;
-    const int ns = a.dyn_samples[ob];
-    if (ns <= 0) continue;
-    const double* tt = a.dyn_time + ob * a.T;
-    if (tt[0] > time || tt[ns - 1] < time) continue;
-    int lo = 0, hi = ns;
-    while (lo < hi) {
-      const int mid = lo + (hi - lo) / 2;
-      if (time < tt[mid]) hi = mid; else lo = mid + 1;
-    }
-    if (lo >= ns) lo = ns - 1;
-    double bb[4];
-    polygon_aabb(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], bb);
+    const int lo = sidx ? sidx[o * kMaxSeg + point] : dynamic_sample(a, ob, time);
+    if (lo < 0) continue;
+    double bb_local[4];
+    const double* bb = bb_local;
+    if (sbb) bb = sbb + ((size_t)o * a.T + lo) * 4;
+    else polygon_aabb(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], bb_local);
     if (polygon_overlaps_box(a.dyn_poly + (ob * a.T + lo) * a.V * 2, a.dyn_nv[ob], bb, cx, cy, half)) return true;
   }
   return false;
 }
 
 // Environment::CheckOptimizationCollision, environment.cpp:99-122; GetDiscPositions, vehicle_param.h:88-95
-__device__ bool check_optimization_collision(const Args& a, int b, const double* obb, double time, double x, double y,
-                                             double theta) {
+__device__ bool check_optimization_collision(const Args& a, int b, const double* obb, const double* sbb, const int* sidx,
+                                             int point, double time, double x, double y, double theta) {
   const double radius = a.lat.radius;
   const double half = (radius + 0.0 - (-radius - 0.0)) / 2.0;
   const double ct = cos(theta), st = sin(theta);
@@ -373,7 +385,8 @@ __device__ bool check_optimization_collision(const Args& a, int b, const double*
   const unsigned near_dyn = nobs > 32 ? 1u : (a.n_static >= 32 ? 0u : near >> a.n_static);
   return check_static(a, b, obb, near_static != 0 || a.n_static > 32, fx, fy, half) ||
          check_static(a, b, obb, near_static != 0 || a.n_static > 32, rx, ry, half) ||
-         (near_dyn != 0 && (check_dynamic(a, b, obb, time, fx, fy, half) || check_dynamic(a, b, obb, time, rx, ry, half)));
+         (near_dyn != 0 && (check_dynamic(a, b, obb, sbb, sidx, point, time, fx, fy, half) ||
+                            check_dynamic(a, b, obb, sbb, sidx, point, time, rx, ry, half)));
 }
 
 struct Start {
@@ -412,8 +425,8 @@ __device__ __forceinline__ Segment make_segment(const Args& a, const Start& st, 
 }
 
 // GetCollisionCost, dp_planner.cpp:40-85; pt < 0: the parent is the start state
-__device__ double collision_cost(const Args& a, int b, const double* obb, const Start& st, const Cell* cells, int pt,
-                                 int psi, int pli, int ct, int csi, int cli) {
+__device__ double collision_cost(const Args& a, int b, const double* obb, const double* sbb, const int* sidx,
+                                 const Start& st, const Cell* cells, int pt, int psi, int pli, int ct, int csi, int cli) {
   double parent_s = st.s, grandparent_s = st.s;
   double last_l = st.l, last_s = st.s;
   if (pt >= 0) {
@@ -440,14 +453,14 @@ __device__ double collision_cost(const Args& a, int b, const double* obb, const 
     if (pl < lb - kDpEps || pl > ub + kDpEps) return a.w_obstacle;
     const double heading = r.theta + atan((dl / ds) / (1 - r.kappa * pl));
     const double time = parent_time + i * (a.lat.unit_time / g.nseg);
-    if (check_optimization_collision(a, b, obb, time, cx, cy, heading)) return a.w_obstacle;
+    if (check_optimization_collision(a, b, obb, sbb, sidx, i, time, cx, cy, heading)) return a.w_obstacle;
   }
   return 0.0;
 }
 
 // GetCost, dp_planner.cpp:87-133
-__device__ double get_cost(const Args& a, int b, const double* obb, const Start& st, const Cell* cells, int pt, int psi,
-                           int pli, int ct, int csi, int cli, double* cur_s_out) {
+__device__ double get_cost(const Args& a, int b, const double* obb, const double* sbb, const int* sidx, const Start& st,
+                           const Cell* cells, int pt, int psi, int pli, int ct, int csi, int cli, double* cur_s_out) {
   double parent_s = st.s, grandparent_s = st.s;
   double parent_l = st.l, grandparent_l = st.l;
   if (pt >= 0) {
@@ -466,7 +479,7 @@ __device__ double get_cost(const Args& a, int b, const double* obb, const Start&
   const double ds0 = parent_s - grandparent_s;
   const double dl0 = parent_l - grandparent_l;
   *cur_s_out = cur_s;
-  const double cost_obstacle = collision_cost(a, b, obb, st, cells, pt, psi, pli, ct, csi, cli);
+  const double cost_obstacle = collision_cost(a, b, obb, sbb, sidx, st, cells, pt, psi, pli, ct, csi, cli);
   if (cost_obstacle >= a.w_obstacle) return a.w_obstacle;
   const double cost_lateral = fabs(cur_l);
   const double cost_lateral_change = fabs(parent_l - cur_l) / (a.lat.station_[csi] + kDpEps);
@@ -483,9 +496,10 @@ constexpr int kMaxThreads = 256;
 constexpr int kMaxKnots = 512;
 
 // shared-memory layout (bytes); K <= kMaxKnots
-__host__ __device__ inline size_t smem_bytes(int K, int n_obstacles) {
+__host__ __device__ inline size_t smem_bytes(int K, int n_obstacles, int n_dyn, int T, bool sample_bounds) {
   return sizeof(double) * 4 * (size_t)n_obstacles + sizeof(Cell) * NT * NP + sizeof(double) * NP * NP + sizeof(double) * kMaxThreads + sizeof(int) * kMaxThreads +
-         sizeof(double) * 8 + sizeof(int) * 3 * NT + sizeof(double) * 10 * (size_t)K + 64;
+         sizeof(double) * 8 + sizeof(int) * 3 * NT + sizeof(double) * 10 * (size_t)K + 64 +
+         sizeof(int) * kMaxSeg * (size_t)n_dyn + 16 + (sample_bounds ? sizeof(double) * 4 * (size_t)n_dyn * T : 0);
 }
 
 __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
@@ -500,6 +514,10 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
   double* kn = reinterpret_cast<double*>(wp + 3 * NT + 1);                // 10 arrays of K doubles
   kn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(kn) + 15) & ~(uintptr_t)15);
   double* obb = kn + 10 * (size_t)a.lat.K;                                // [n_static + n_dyn][4] obstacle bounds
+  double* sbb = a.use_sample_bounds ? obb + 4 * (size_t)(a.n_static + a.n_dyn) : nullptr;  // [n_dyn][T][4]
+  int* sidx = reinterpret_cast<int*>(obb + 4 * (size_t)(a.n_static + a.n_dyn) + (a.use_sample_bounds ? 4 * (size_t)a.n_dyn * a.T : 0));  // [n_dyn][kMaxSeg]
+  bool use_sidx = true;
+  for (int k = 0; k < NT; ++k) use_sidx = use_sidx && a.lat.nseg[k] <= kMaxSeg;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int K = a.lat.K;
   double *xs = kn, *ys = kn + K, *acc_s = kn + 2 * K, *speeds = kn + 3 * K, *accel = kn + 4 * K, *xds = kn + 5 * K,
@@ -526,6 +544,14 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
           acc[3] = fmax(acc[3], bb[3]);
         }
         for (int q = 0; q < 4; ++q) obb[4 * o + q] = acc[q];
+      }
+    }
+    // ---- bounds of every sample of every dynamic obstacle (Polygon2d::BuildFromPoints, polygon2d.cpp:246-256)
+    if (sbb) {
+      for (int i = tid; i < a.n_dyn * a.T; i += nt) {
+        const int o = i / a.T, t = i - o * a.T;
+        const size_t ob = (size_t)b * a.n_dyn + o;
+        if (t < a.dyn_samples[ob]) polygon_aabb(a.dyn_poly + (ob * a.T + t) * a.V * 2, a.dyn_nv[ob], sbb + (size_t)i * 4);
       }
     }
     // ---- GetProjection, discretized_trajectory.cpp:156-190; QueryNearestPoint (:136-154): first minimum
@@ -580,10 +606,25 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
     st.s = misc[0];
     st.l = misc[1];
 
+    // the sample every dynamic obstacle shows at each of a layer's query times (GetCollisionCost :76: time =
+    // parent_time + i * unit_time / nseg)
+    auto tabulate_samples = [&](int layer) {
+      if (!use_sidx) return;
+      const int ns = a.lat.nseg[layer];
+      const double parent_time = layer == 0 ? 0.0 : a.lat.time_[layer - 1];
+      for (int q = tid; q < a.n_dyn * ns; q += nt) {
+        const int o = q / ns, i = q - o * ns;
+        const double time = parent_time + i * (a.lat.unit_time / ns);
+        sidx[o * kMaxSeg + i] = dynamic_sample(a, (size_t)b * a.n_dyn + o, time);
+      }
+    };
+    const int* sidx_c = use_sidx ? sidx : nullptr;
+    tabulate_samples(0);
+    __syncthreads();
     // ---- first layer, dp_planner.cpp:151-158
     for (int p = tid; p < NP; p += nt) {
       double cur_s;
-      const double c = get_cost(a, b, obb, st, cells, -1, -1, -1, 0, p / NL, p % NL, &cur_s);
+      const double c = get_cost(a, b, obb, sbb, sidx_c, st, cells, -1, -1, -1, 0, p / NL, p % NL, &cur_s);
       Cell cell;
       cell.cost = c;
       cell.current_s = cur_s;
@@ -597,11 +638,12 @@ __global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const Args a) {
       // transitions are claimed from a shared counter: one that collides at its first point costs a fraction of
       // one that walks all its points, and a static split would leave most threads waiting for the unlucky ones
       if (tid == 0) *queue = 0;
+      tabulate_samples(i + 1);
       __syncthreads();
       for (int q = atomicAdd(queue, 1); q < NP * NP; q = atomicAdd(queue, 1)) {
         const int parent = q / NP, child = q - parent * NP;
         double cur_s;
-        delta[q] = get_cost(a, b, obb, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);
+        delta[q] = get_cost(a, b, obb, sbb, sidx_c, st, cells, i, parent / NL, parent % NL, i + 1, child / NL, child % NL, &cur_s);
       }
       __syncthreads();
       for (int child = tid; child < NP; child += nt) {

@@ -16,7 +16,7 @@ import numpy as np
 from . import build as _build
 
 STATUS_NAMES = ["converged_abs", "converged_rel", "converged_grad", "lambda_overflow", "max_iter"]
-E_INVALID, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_SMEM, E_TIMEOUT = -1, -2, -3, -4, -5, -6
+E_INVALID, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_SMEM, E_TIMEOUT, E_NCCL = -1, -2, -3, -4, -5, -6, -7
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -50,7 +50,7 @@ class BatchIn(C.Structure):
 class BatchOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "states", "controls", "status", "trajectory", "init_states", "init_controls", "cost_hist",
-        "iter_states", "iter_controls", "hist_len")] + [("hist_cap", C.c_int32)]
+        "iter_states", "iter_controls", "hist_len")] + [("hist_cap", C.c_int32), ("result", C.c_void_p)]
 
 
 class DebugOut(C.Structure):
@@ -102,7 +102,9 @@ EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_d
            "cilqr_debug_completion_histogram", "cilqr_debug_host_path", "cilqr_corridor_default_config", "cilqr_corridor_batch",
            "cilqr_corridor_batch_device", "cilqr_lane_constraints", "cilqr_lane_constraints_device",
            "cilqr_corridor_last_kernel_ms", "cilqr_dp_default_config", "cilqr_dp_num_knots",
-           "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms"]
+           "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms",
+           "cilqr_multi_create", "cilqr_multi_destroy", "cilqr_multi_devices", "cilqr_multi_shard_size",
+           "cilqr_multi_last_error", "cilqr_plan_sharded"]
 
 _libs = {}
 
@@ -162,6 +164,15 @@ def load_library(build_if_missing: bool = True, variant: str = ""):
     L.cilqr_dp_plan_batch_device.argtypes = [C.c_void_p, C.POINTER(DpConfig), C.POINTER(DpIn), C.POINTER(DpOut),
                                              C.c_void_p]
     L.cilqr_dp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cilqr_multi_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]
+    L.cilqr_multi_destroy.argtypes = [C.c_void_p]
+    L.cilqr_multi_destroy.restype = None
+    L.cilqr_multi_devices.argtypes = [C.c_void_p]
+    L.cilqr_multi_shard_size.argtypes = [C.c_void_p, C.c_int]
+    L.cilqr_multi_last_error.argtypes = [C.c_void_p]
+    L.cilqr_multi_last_error.restype = C.c_char_p
+    L.cilqr_plan_sharded.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut), C.POINTER(C.c_void_p)]
     _libs[variant] = L
     return L
 
@@ -239,7 +250,7 @@ class Solver:
                        _ptr(corridor_cnt), _ptr(lane_left), _ptr(lane_right))
 
     def plan_batch(self, batch, trajectory: bool = False, init_guess: bool = False, hist_cap: int = 0,
-                   out: dict | None = None) -> dict:
+                   out: dict | None = None, result: bool = False) -> dict:
         """Host path.  ``batch`` is a ScenarioBatch-like object with numpy arrays (pinned memory
         gives asynchronous copies).  Returns numpy outputs (or fills the arrays given in ``out``)."""
         B, N, K = batch.B, batch.N, batch.N + 1
@@ -253,6 +264,8 @@ class Solver:
         o.setdefault("status", np.empty((B, 8)))
         if trajectory:
             o.setdefault("trajectory", np.empty((B, K, 13)))
+        if result:
+            o.setdefault("result", np.empty((B, K, 13)))
         if init_guess:
             o.setdefault("init_states", np.empty((B, K, 6)))
             o.setdefault("init_controls", np.empty((B, N, 2)))
@@ -263,18 +276,18 @@ class Solver:
             o.setdefault("hist_len", np.zeros((B, 2), dtype=np.int32))
         bo = BatchOut(*[_ptr(o.get(n)) for n in ("states", "controls", "status", "trajectory", "init_states",
                                                   "init_controls", "cost_hist", "iter_states", "iter_controls",
-                                                  "hist_len")], hist_cap)
+                                                  "hist_len")], hist_cap, _ptr(o.get("result")))
         self._check(self._L.cilqr_plan_batch(self._h, C.byref(bi), C.byref(bo)))
         return o
 
     def plan_batch_device(self, B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt,
                           lane_left, lane_right, states, controls, status, trajectory=None,
-                          init_states=None, init_controls=None, stream: int | None = None):
+                          init_states=None, init_controls=None, stream: int | None = None, result=None):
         """Device path: every array argument is a device pointer (int) or a CUDA torch tensor.
         Enqueues the solve kernel and returns immediately."""
         bi = self._make_in(B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt, lane_left, lane_right)
         bo = BatchOut(_ptr(states), _ptr(controls), _ptr(status), _ptr(trajectory), _ptr(init_states),
-                      _ptr(init_controls), None, None, None, None, 0)
+                      _ptr(init_controls), None, None, None, None, 0, _ptr(result))
         self._check(self._L.cilqr_plan_batch_device(self._h, C.byref(bi), C.byref(bo), stream))
 
     def debug_first_iteration(self, B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt,
@@ -403,3 +416,57 @@ class Solver:
         ms = C.c_float()
         self._check(self._L.cilqr_dp_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class MultiSolver:
+    """Owns one cilqr_multi (one solver handle per GPU of this box, one host process): ``plan_sharded`` solves a host
+    batch as contiguous shards, optionally leaving every shard's result block on every GPU (one NCCL all-gather)."""
+
+    def __init__(self, n_devices: int, params: Params | None = None, devices=None, N_max: int = 200, M_max: int = 32,
+                 S_max: int = 64, B_max_per_device: int = 1 << 20):
+        self._L = load_library()
+        self.params = params or default_params()
+        h = C.c_void_p()
+        devs = (C.c_int * n_devices)(*devices) if devices is not None else None
+        rc = self._L.cilqr_multi_create(C.byref(self.params), n_devices, devs, N_max, M_max, S_max, B_max_per_device,
+                                        C.byref(h))
+        if rc != 0:
+            raise CilqrError(rc, self._L.cilqr_strerror(rc).decode())
+        self._h = h
+        self.n_devices = n_devices
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cilqr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard_size(self, B: int) -> int:
+        return self._L.cilqr_multi_shard_size(self._h, B)
+
+    def plan_sharded(self, batch, gathered=None, result: bool = False) -> dict:
+        """``gathered``: optional list of n_devices device pointers / CUDA tensors (one per GPU, each
+        n_devices * shard_size * (6K + 2N + 8) doubles) that receive all result blocks."""
+        B, N, K = batch.B, batch.N, batch.N + 1
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        arrs = [f64(batch.start), f64(batch.coarse), f64(batch.corridor),
+                np.ascontiguousarray(batch.corridor_cnt, dtype=np.int32), f64(batch.lane_left), f64(batch.lane_right)]
+        bi = BatchIn(B, N, batch.M_max, arrs[4].shape[1], arrs[5].shape[1], *[_ptr(a) for a in arrs])
+        o = {"states": np.empty((B, K, 6)), "controls": np.empty((B, N, 2)), "status": np.empty((B, 8))}
+        if result:
+            o["result"] = np.empty((B, K, 13))
+        bo = BatchOut(_ptr(o["states"]), _ptr(o["controls"]), _ptr(o["status"]), None, None, None, None, None, None, None, 0,
+                      _ptr(o.get("result")))
+        g = None
+        if gathered is not None:
+            g = (C.c_void_p * self.n_devices)(*[_ptr(x) for x in gathered])
+        rc = self._L.cilqr_plan_sharded(self._h, C.byref(bi), C.byref(bo), g)
+        if rc != 0:
+            raise CilqrError(rc, self._L.cilqr_strerror(rc).decode() + " -- " +
+                             self._L.cilqr_multi_last_error(self._h).decode())
+        return o

@@ -168,7 +168,7 @@ class IlqrOptimizer {
     out.states = states.data(); out.controls = controls.data(); out.status = status.data();
     out.trajectory = traj.data(); out.init_states = nullptr; out.init_controls = nullptr;
     out.cost_hist = cost_hist.data(); out.iter_states = it_x.data(); out.iter_controls = it_u.data();
-    out.hist_len = hist_len; out.hist_cap = H;
+    out.hist_len = hist_len; out.hist_cap = H; out.result = nullptr;
     const int rc = cilqr_plan_batch(handle_, &in, &out);
     if (rc != CILQR_OK) {
       std::fprintf(stderr, "cilqr_b200: %s (%s)\n", cilqr_strerror(rc), cilqr_last_cuda_error(handle_));

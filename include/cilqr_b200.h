@@ -27,6 +27,8 @@
  *   status       [B][8]      out     see CILQR_ST_* below
  *   trajectory   [B][K][13]  out     TrajectoryPoint records (discretized_trajectory.h:26-43) as
  *                                    TransformToTrajectory fills them, ilqr_optimizer.cc:771-791
+ *   result       [B][K][13]  out     the same records after TrajectoryPlanner::Plan's post-processing
+ *                                    (station accumulated, trajectory_planner.cpp:103-125)
  * Shrinking/normalising the constraints (ilqr_optimizer.cc:438-495) is part of the solve.
  *
  * Two further sections below widen the boundary to the stages that feed the solve inside
@@ -57,6 +59,8 @@ extern "C" {
 #define CILQR_E_TIMEOUT (-6)   /* the solve kernel gave up on some scenarios (input transfer starved / watchdog); \
                                   their status rows keep the NaN sentinel -- never returned as success, cf. \
                                   trajectory_planner.cpp:91-94 */
+
+#define CILQR_E_NCCL (-7)      /* the gathered copy of cilqr_plan_sharded was requested but NCCL failed / is missing */
 
 /* status[b][CILQR_ST_FLAG] values: which exit of Optimize() was taken */
 #define CILQR_CONVERGED_ABS 0    /* dcost < abs_cost_tol         ilqr_optimizer.cc:281,287 */
@@ -119,6 +123,11 @@ typedef struct CilqrBatchOut {
   double* iter_controls;
   int32_t* hist_len;
   int32_t hist_cap;
+  /* optional: [B][K][13] the records TrajectoryPlanner::Plan builds from opt_trajectory AFTER the solve
+   * (trajectory_planner.cpp:103-125): like `trajectory`, with s = accumulated hypot of consecutive (x, y)
+   * (sequential sum, :110-112) and kappa = tan(delta) / wheel_base (:118); time = delta_t * k.  This is the
+   * planner's published result (PlanningNode::PlanCallback, planning_node.cc:82-88). */
+  double* result;
 } CilqrBatchOut;
 
 typedef struct cilqr_handle cilqr_handle;
@@ -144,6 +153,25 @@ int cilqr_plan_batch_device(cilqr_handle* h, const CilqrBatchIn* in, const Cilqr
 /* Waits for the handle's streams and checks the last launch: CILQR_E_TIMEOUT when it left scenarios
  * unsolved.  After cilqr_plan_batch_device on a caller stream, synchronise that stream first. */
 int cilqr_synchronize(cilqr_handle* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: the batch of independent scenarios sharded over the GPUs of one box from ONE host
+ * process (the reference's host is one C++ process, planning_node.cc).  Device r of G solves the contiguous ids
+ * [r * per, (r + 1) * per), per = cilqr_multi_shard_size(B) = ceil(B / G): no exchange inside the solve.
+ * cilqr_plan_sharded takes HOST pointers for the whole batch (states / controls / status and optionally `result`;
+ * the other optional outputs must be NULL) and blocks until they are filled.  gathered_dev, when not NULL, is an
+ * array of G DEVICE pointers, one per GPU, each with room for G * per * (6K + 2N + 8) doubles: after the solve ONE
+ * ncclAllGather over NVLink leaves every shard's result block [states per x K x 6 | controls per x N x 2 |
+ * status per x 8] on every GPU (block r at offset r * per * (6K + 2N + 8); rows beyond B are zero).  NCCL is
+ * loaded at run time (libnccl.so.2); without it only the gathered copy is unavailable (CILQR_E_NCCL). */
+typedef struct cilqr_multi cilqr_multi;
+int cilqr_multi_create(const CilqrParams* params, int n_devices, const int* devices /* NULL: 0..n-1 */, int N_max,
+                       int M_max, int S_max, int B_max_per_device, cilqr_multi** out);
+void cilqr_multi_destroy(cilqr_multi* m);
+int cilqr_multi_devices(const cilqr_multi* m);
+int cilqr_multi_shard_size(const cilqr_multi* m, int B);
+const char* cilqr_multi_last_error(const cilqr_multi* m);
+int cilqr_plan_sharded(cilqr_multi* m, const CilqrBatchIn* in, const CilqrBatchOut* out, double* const* gathered_dev);
 
 /* Introspection used by bench.py / tests. */
 int cilqr_kernel_launches(const cilqr_handle* h, int64_t* solve_launches);

@@ -194,8 +194,15 @@ def test_host_path_equals_device_path_and_is_deterministic(solver):
     X1, U1, S1 = _solve_device(solver, batch)
     X2, U2, S2 = _solve_device(solver, batch)
     assert np.array_equal(X1, X2) and np.array_equal(U1, U2) and np.array_equal(S1, S2)  # bitwise
-    out = solver.plan_batch(batch, trajectory=True, init_guess=True)
+    out = solver.plan_batch(batch, trajectory=True, init_guess=True, result=True)
     assert np.array_equal(out["states"], X1) and np.array_equal(out["controls"], U1) and np.array_equal(out["status"], S1)
+    # TrajectoryPlanner::Plan's post-processing (trajectory_planner.cpp:103-125): s = running sum of hypot, the
+    # rest as TransformToTrajectory
+    res, trj = out["result"], out["trajectory"]
+    seg = np.hypot(np.diff(X1[:, :, 0], axis=1), np.diff(X1[:, :, 1], axis=1))
+    s_ref = np.concatenate([np.zeros((batch.B, 1)), np.cumsum(seg, axis=1)], axis=1)  # sequential, like :110-112
+    np.testing.assert_allclose(res[:, :, 1], s_ref, rtol=1e-14, atol=0)
+    assert np.array_equal(np.delete(res, 1, axis=2), np.delete(trj, 1, axis=2)) and np.all(trj[:, :, 1] == 0)
     # order independence: scenario b's result does not depend on its position in the batch
     perm = np.random.default_rng(0).permutation(batch.B)
     pb = scenarios.ScenarioBatch(batch.N, batch.M_max, batch.S, *[np.ascontiguousarray(a[perm]) for a in
@@ -322,9 +329,9 @@ def test_edge_cases(solver, oracle):
     # guards of IlqrOptimizer::Plan (ilqr_optimizer.cc:64-78) -> CILQR_E_INVALID; capacity -> CILQR_E_CAPACITY
     L = cilqr_b200.load_library()
     bi = cilqr_b200.solver.BatchIn(1, 20, batch.M_max, 0, batch.S, 1, 1, 1, 1, 1, 1)  # empty left lane set
-    bo = cilqr_b200.solver.BatchOut(1, 1, 1, None, None, None, None, None, None, None, 0)
+    bo = cilqr_b200.solver.BatchOut(1, 1, 1, None, None, None, None, None, None, None, 0, None)
     assert L.cilqr_plan_batch(solver._h, C.byref(bi), C.byref(bo)) == -1
-    bo2 = cilqr_b200.solver.BatchOut(None, 1, 1, None, None, None, None, None, None, None, 0)  # null output
+    bo2 = cilqr_b200.solver.BatchOut(None, 1, 1, None, None, None, None, None, None, None, 0, None)  # null output
     bi2 = cilqr_b200.solver.BatchIn(1, 20, batch.M_max, batch.S, batch.S, 1, 1, 1, 1, 1, 1)
     assert L.cilqr_plan_batch(solver._h, C.byref(bi2), C.byref(bo2)) == -1
     bi3 = cilqr_b200.solver.BatchIn(1, 100000, batch.M_max, batch.S, batch.S, 1, 1, 1, 1, 1, 1)

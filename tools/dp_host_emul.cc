@@ -41,6 +41,7 @@ extern "C" int emul_dp(const double* cfg, const int* dims, const double* ref, co
   dp::build_grid(barrier, a.NB, a.lat.radius, &a, &gs, &gi);
   a.grid_start = gs.data();
   a.grid_idx = gi.data();
+  a.use_sample_bounds = dp::smem_bytes(a.lat.K, a.n_static + a.n_dyn, a.n_dyn, a.T, true) <= sizeof(dp::dp_smem) ? 1 : 0;
   gridDim.x = 1;
   dp::dp_plan_kernel(a);
   return a.lat.K;
