@@ -158,7 +158,7 @@ SmemLayout make_layout(int N, int M_max, int S_left, int S_right) {
   // EVAL: seg, grp, trig
   L.seg = 0;
   L.grp = S * cilqr::kSegStride;
-  L.trig = even(L.grp + ng * 3);
+  L.trig = even(L.grp + ng * 3 + S);  // group circles, then the certificate radii of the nearest-segment search
   L.pl_e = even(L.trig + 2 * K);
 #if CILQR_STRICT
   const int e_end = L.pl_e + 32 * cilqr::strict_row_width(M_max);  // the term buffer of the ordered cost sums
@@ -192,7 +192,7 @@ CtxLayout make_ctx_layout(int N, int M_max, int S_left, int S_right) {
   C.lin = C.gains + (N + cilqr::kRollChunk - 1) / cilqr::kRollChunk * cilqr::kRollChunk * cilqr::kGainStride;
   C.seg = C.lin + (K + cilqr::kBackChunk - 1) / cilqr::kBackChunk * cilqr::kBackChunk * cilqr::kRecStride;
   C.grp = C.seg + S * cilqr::kSegStride;
-  C.nidx = even(C.grp + ng * 3);
+  C.nidx = even(C.grp + ng * 3 + S);
   C.nidx_bytes = (K * 10 + 7) / 8 * 8;
   C.hdr = C.nidx + cilqr::kTrajSlots * C.nidx_bytes / 8;
   C.stride = (C.hdr + cilqr::kHdrDoubles + 15) / 16 * 16;
@@ -249,6 +249,9 @@ int validate(const cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOut*
   if (in->N > h->N_max || in->M_max > h->M_max || in->S_left > h->S_max || in->S_right > h->S_max)
     return CILQR_E_CAPACITY;
   if ((out->iter_states || out->cost_hist) && out->hist_cap < 1) return CILQR_E_INVALID;
+  if (in->init_mode < CILQR_INIT_IQR || in->init_mode > CILQR_INIT_GUESS) return CILQR_E_INVALID;
+  if (in->init_mode != CILQR_INIT_IQR && !in->init_controls) return CILQR_E_INVALID;
+  if (in->init_mode == CILQR_INIT_GUESS && !in->init_states) return CILQR_E_INVALID;
   return CILQR_OK;
 }
 
@@ -282,6 +285,9 @@ int launch_solve(cilqr_handle* h, Slot* s, cudaStream_t stream, const CilqrBatch
   a.corridor_cnt = in->corridor_cnt;
   a.lane_left = in->lane_left;
   a.lane_right = in->lane_right;
+  a.init_mode = in->init_mode;
+  a.guess_states = in->init_states;
+  a.guess_controls = in->init_controls;
   a.states = out->states;
   a.controls = out->controls;
   a.status = out->status;
@@ -651,7 +657,9 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   const size_t b_st = K * 6 * 8, b_ct = N * 2 * 8, b_status = 8 * 8, b_traj = K * 13 * 8;
   const size_t b_ch = (size_t)H * 5 * 8, b_is = (size_t)H * K * 6 * 8, b_ic = (size_t)H * N * 2 * 8, b_hl = 2 * 4;
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t in_need = up(b_start * B) + up(b_coarse * B) + up(b_corr * B) + up(b_cnt * B) + up(b_ll * B) + up(b_lr * B);
+  const bool has_gx = in->init_mode == CILQR_INIT_GUESS, has_gu = in->init_mode != CILQR_INIT_IQR;
+  const size_t in_need = up(b_start * B) + up(b_coarse * B) + up(b_corr * B) + up(b_cnt * B) + up(b_ll * B) + up(b_lr * B) +
+                         (has_gx ? up(b_st * B) : 0) + (has_gu ? up(b_ct * B) : 0);
   size_t out_need = up(b_st * B) + up(b_ct * B) + up(b_status * B);
   if (out->trajectory) out_need += up(b_traj * B);
   if (out->result) out_need += up(b_traj * B);
@@ -698,6 +706,8 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   char* d_cnt = carve_in(b_cnt);
   char* d_ll = carve_in(b_ll);
   char* d_lr = carve_in(b_lr);
+  char* d_gx = has_gx ? carve_in(b_st) : nullptr;
+  char* d_gu = has_gu ? carve_in(b_ct) : nullptr;
   CilqrBatchIn din = *in;
   din.start = (const double*)d_start;
   din.coarse = (const double*)d_coarse;
@@ -705,6 +715,8 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
   din.corridor_cnt = (const int32_t*)d_cnt;
   din.lane_left = (const double*)d_ll;
   din.lane_right = (const double*)d_lr;
+  din.init_states = (const double*)d_gx;
+  din.init_controls = (const double*)d_gu;
   // Outputs: a caller buffer in pinned (page-locked, device-mapped) host memory is written by the kernel
   // directly as scenarios finish -- the results cross PCIe during the solve and need no D2H pass; any other
   // buffer gets a device staging area and one copy after the kernel.
@@ -771,6 +783,8 @@ int cilqr_plan_batch(cilqr_handle* h, const CilqrBatchIn* in, const CilqrBatchOu
     h2d(d_cnt, in->corridor_cnt, b_cnt);
     h2d(d_ll, in->lane_left, b_ll);
     h2d(d_lr, in->lane_right, b_lr);
+    if (d_gx) h2d(d_gx, in->init_states, b_st);
+    if (d_gu) h2d(d_gu, in->init_controls, b_ct);
     size_t mark = b0 + nb;
     if (h->starve_after >= 0) mark = std::min<size_t>(mark, (size_t)h->starve_after);  // test hook
     s->ready_host[ci] = (unsigned int)mark;

@@ -198,6 +198,9 @@ struct KernelArgs {
   const int32_t* corridor_cnt;
   const double* lane_left;
   const double* lane_right;
+  int init_mode;                 // 0 iqr, 1 open-loop rollout of guess_controls, 2 (guess_states, guess_controls) as given
+  const double* guess_states;    // [B][K][6]
+  const double* guess_controls;  // [B][N][2]
   double* states;
   double* controls;
   double* status;
@@ -489,10 +492,35 @@ __device__ __forceinline__ void stage_planes(const Ctx& c, double* buf, int k_lo
 // centre than ub + radius cannot contain the minimiser -- nor tie with it -- and is skipped.  Surviving
 // groups are scanned in index order with the reference's strict '<', so the arg-min (first minimum)
 // is the brute-force one.
-__device__ __forceinline__ int nearest_segment(const double* sg0, const double* gp, int S, int guess, double xd,
-                                               double yd) {
+// Fast path ("certificate"): cert[s] (built at scenario load, see phase_init) is the square of half a LOWER bound on
+// the distance between segment s and every segment more than kNearWin indices away from it.  If the disc centre p
+// is closer than that to the guess segment g, then for any point r of such a far segment
+//     |p - r| >= dist(seg g, seg j) - dist(p, seg g) > dist(p, seg g) >= min over all segments,
+// strictly -- a far segment can neither be the minimiser nor tie with it -- so the first minimum of the brute-force
+// scan lies in the window [g - kNearWin, g + kNearWin], which is scanned in index order with the reference's
+// strict '<'.  The bounds are deflated by 1e-9 relative + 1e-9 absolute, nine orders above the rounding of the
+// distances that are compared.
+constexpr int kNearWin = 3;
+__device__ __forceinline__ int nearest_segment(const double* sg0, const double* gp, const double* cert, int S, int guess,
+                                               double xd, double yd) {
   const int gi = guess < S ? guess : S - 1;
-  const double ub = sqrt(seg_dist2(sg0 + gi * kSegStride, xd, yd));
+  const double ddg = seg_dist2(sg0 + gi * kSegStride, xd, yd);
+  if (ddg < cert[gi]) {  // (NaN compares false: the general search below handles it)
+    const int lo = gi - kNearWin > 0 ? gi - kNearWin : 0;
+    const int hi = gi + kNearWin < S - 1 ? gi + kNearWin : S - 1;
+    double best = 1.7976931348623157e308;
+    int bi = gi;
+#pragma unroll 1
+    for (int s = lo; s <= hi; ++s) {
+      const double dd = s == gi ? ddg : seg_dist2(sg0 + s * kSegStride, xd, yd);
+      if (dd < best) {
+        best = dd;
+        bi = s;
+      }
+    }
+    return bi;
+  }
+  const double ub = sqrt(ddg);
   const int ng = (S + kGroup - 1) / kGroup;
   double best = 1.7976931348623157e308;
   int bi = 0;
@@ -561,8 +589,9 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   }
   __syncwarp();
   const int items = K * kDisc;
-  const int ngl = (a.S_left + kGroup - 1) / kGroup;
+  const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
   const double* grp = c.sm + a.sm.grp;
+  const double* cert = grp + (ngl + ngr) * 3;  // [S_left + S_right] certificate radii, behind the group circles
   double* pbuf = c.sm + a.sm.pl_e;
   const int pstride = a.M_max * kPlaneTile;
   // tile of chunk j0: knots j0/5 .. (j0+31)/5 (at most kPlaneKnots), planes below the chunk's largest count
@@ -642,7 +671,8 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
     for (int side = 0; side < 2; ++side) {
       const int S = side == 0 ? a.S_left : a.S_right;
       const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
-      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, S, side == 0 ? (g2 & 0xff) : (g2 >> 8), xd, yd);
+      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, cert + (side == 0 ? 0 : a.S_left), S,
+                                     side == 0 ? (g2 & 0xff) : (g2 >> 8), xd, yd);
       const double* sg = sg0 + bi * kSegStride;
       bar_add(bl, fma(sg[8], yd, sg[7] * xd) - sg[9], P);
       if (act) nidx[jj * 2 + side] = (unsigned char)bi;
@@ -1191,7 +1221,7 @@ __device__ __noinline__ void stage_segments(Ctx& c) {
   double* dst = c.sm + a.sm.seg;
   for (int i = c.lane; i < n16; i += 32) cp_async16(dst + i * 2, src + i * 2);
   const int ng = (a.S_left + kGroup - 1) / kGroup + (a.S_right + kGroup - 1) / kGroup;
-  const int g16 = (ng * 3 + 1) / 2;
+  const int g16 = (ng * 3 + a.S_left + a.S_right + 1) / 2;  // group circles + certificate radii
   const double* gs = c.ggrp();
   double* gd = c.sm + a.sm.grp;
   for (int i = c.lane; i < g16; i += 32) cp_async16(gd + i * 2, gs + i * 2);
@@ -1457,13 +1487,72 @@ __device__ __noinline__ int phase_init(Ctx& c) {
       // radius, inflated so that rounding can only make the pruning test more conservative
       grp[g * 3 + 2] = sqrt(r2) * (1.0 + 1e-9) + 1e-9;
     }
+    // certificate radii of the nearest-segment fast path (see nearest_segment): for segment s, half of
+    // min over |j - s| > kNearWin of (|mid_s - mid_j| - (len_s + len_j) / 2) -- a lower bound on the distance
+    // between the two segments --, deflated, squared
+    double* cert = grp + (ngl + ngr) * 3;
+#pragma unroll 1
+    for (int s = lane; s < ST_; s += 32) {
+      const int side = s < a.S_left ? 0 : 1;
+      const int s0 = side == 0 ? 0 : a.S_left, S = side == 0 ? a.S_left : a.S_right;
+      const double* me = seg + s * kSegStride;
+      const double mx = 0.5 * (me[0] + me[2]), my = 0.5 * (me[1] + me[3]);
+      double D = 1.7976931348623157e308;
+#pragma unroll 1
+      for (int j = 0; j < S; ++j) {
+        const int dj = j - (s - s0);
+        if (dj >= -kNearWin && dj <= kNearWin) continue;
+        const double* o = seg + (s0 + j) * kSegStride;
+        const double ex = mx - 0.5 * (o[0] + o[2]), ey = my - 0.5 * (o[1] + o[3]);
+        D = fmin(D, sqrt(ex * ex + ey * ey) - 0.5 * (me[6] + o[6]));
+      }
+      const double h = 0.5 * D * (1.0 - 1e-9) - 1e-9;
+      cert[s] = h > 0.0 ? (h < 1e150 ? h * h * (1.0 - 1e-9) : 1.7976931348623157e308) : 0.0;
+    }
   }
   __syncwarp();
-  iqr_records(c, c.slot(0));
   // no previous iterate: any valid index is an upper bound for the nearest-segment search
   unsigned char* n0 = c.nidx(0);
 #pragma unroll 1
   for (int i = lane; i < a.cl.nidx_bytes; i += 32) n0[i] = 0;
+  if (a.init_mode != 0) {
+    // the caller's initial guess instead of iqr (ilqr_optimizer.cc:168): slot 0 <- (X, U) as given (mode 2: the
+    // InitGuess copy, :107-139), or <- (0, U) with zero gains so that the rollout phase reproduces
+    // x_{k+1} = Dynamics(x_k, u_k) from goals_[0] (mode 1: OpenLoopRollout, slover/ilqr.h:362-370)
+    double* Xs = c.slot(0);
+    const double* gu = a.guess_controls + (size_t)b * N * 2;
+    const double* gx = a.init_mode == 2 ? a.guess_states + (size_t)b * K * 6 : nullptr;
+    double* gains = c.gains();
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Xs[i * a.Kc + k] = gx ? gx[k * 6 + i] : 0.0;
+      Xs[6 * a.Kc + k] = k < N ? gu[k * 2] : 0.0;
+      Xs[7 * a.Kc + k] = k < N ? gu[k * 2 + 1] : 0.0;
+      if (k < N && !gx)
+        for (int i = 0; i < kGainStride; ++i) gains[k * kGainStride + i] = 0.0;
+    }
+    if (gx && (a.init_states || a.init_controls)) {  // iter_trajs[0] for the adapter (:170)
+#pragma unroll 1
+      for (int k = lane; k <= N; k += 32) {
+        if (a.init_states)
+          for (int i = 0; i < 6; ++i) a.init_states[((size_t)b * K + k) * 6 + i] = gx[k * 6 + i];
+        if (a.init_controls && k < N) {
+          a.init_controls[((size_t)b * N + k) * 2] = gu[k * 2];
+          a.init_controls[((size_t)b * N + k) * 2 + 1] = gu[k * 2 + 1];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      h->imode = 0;
+      h->emode = 0;
+      h->rmode = gx ? 0 : 3;
+    }
+    __syncwarp();
+    return gx ? PH_EVAL : PH_ROLL;
+  }
+  iqr_records(c, c.slot(0));
   __syncwarp();
   return PH_BACK;  // the iqr sweep
 }
@@ -1496,14 +1585,15 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const i
   double* cx = ctx_base(a, gidx, valid ? my_id : id0);
   CtxHdr* h = reinterpret_cast<CtxHdr*>(cx + a.cl.hdr);
   const int cur = h->cur, rmode = h->rmode;
-  const int gb = rmode == 0 ? 0 : h->gb;
+  const int gb = (rmode == 0 || rmode == 3) ? 0 : h->gb;
   unsigned want = 1u;
   if (rmode == 1) want = (1u << (kNAlpha - gb < kSpec ? kNAlpha - gb : kSpec)) - 1u;
   else if (rmode == 2) want = (h->deferred >> gb) & ((1u << kSpec) - 1u);
   if (want == 0) want = 1u;  // (cannot happen; keeps the shadow index valid)
   // a scenario far beyond the mean iteration count usually blows up its largest step sizes: take the
   // general wrap at once instead of deferring it to a second pass (it runs alone in this warp anyway)
-  const bool iqr = rmode == 0, allow_general = rmode != 1 || h->iter >= a.hot_iter;
+  // rmode 3: open-loop rollout of the caller's controls (no clamp, no wrap: OpenLoopRollout, slover/ilqr.h:362-370)
+  const bool iqr = rmode == 0 || rmode == 3, clamp_u = rmode == 0, allow_general = rmode != 1 || h->iter >= a.hot_iter;
   const bool wanted = (want >> ai) & 1u;
   const bool owner = valid && wanted;
   const int ca = wanted ? ai : 31 - __clz(want);
@@ -1563,9 +1653,11 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const i
       }
       double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
       double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
-      if (iqr) {
+      if (clamp_u) {
         u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
         u1 = fmin(P.drmax, fmax(u1, P.drmin));
+      } else if (iqr) {
+        // open loop: the caller's controls as they are
       } else {
         u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
       }
@@ -1593,7 +1685,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const i
   const unsigned ret = (db >> (4 * g)) & want, def = (fb >> (4 * g)) & want;
   __syncwarp();
   if (valid && ai == 0) {
-    if (rmode == 0) {
+    if (rmode == 0 || rmode == 3) {
       h->cur = cand_slot(cur, 0);
       h->emode = 0;
     } else if (rmode == 1) {
@@ -1611,7 +1703,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const i
     __syncwarp();
     for (int gg = 0; gg < kRollGroups; ++gg) {
       const int id = __shfl_sync(kFull, my_id, gg * 4), rm = __shfl_sync(kFull, rmode, gg * 4);
-      if (id < 0 || rm != 0) continue;
+      if (id < 0 || (rm != 0 && rm != 3)) continue;
       double* cg = ctx_base(a, gidx, id);
       const CtxHdr* hg = reinterpret_cast<const CtxHdr*>(cg + a.cl.hdr);
       const int curg = __shfl_sync(kFull, cur, gg * 4);

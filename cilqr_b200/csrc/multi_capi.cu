@@ -197,7 +197,7 @@ int cilqr_plan_sharded(cilqr_multi* m, const CilqrBatchIn* in, const CilqrBatchO
   if (out->trajectory || out->init_states || out->init_controls || out->cost_hist || out->iter_states ||
       out->iter_controls || out->hist_len)
     return CILQR_E_INVALID;  // the sharded path returns states / controls / status (+ result)
-  if (in->B < 0) return CILQR_E_INVALID;
+  if (in->B < 0 || in->init_mode != CILQR_INIT_IQR) return CILQR_E_INVALID;  // (caller guesses: single-GPU entry points)
   if (in->B == 0) return CILQR_OK;
   const int G = m->G, B = in->B, per = (B + G - 1) / G;
   const size_t K = in->N + 1, N = in->N;

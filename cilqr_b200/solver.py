@@ -44,7 +44,8 @@ class BatchIn(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("M_max", C.c_int32), ("S_left", C.c_int32),
                 ("S_right", C.c_int32), ("start", C.c_void_p), ("coarse", C.c_void_p),
                 ("corridor", C.c_void_p), ("corridor_cnt", C.c_void_p), ("lane_left", C.c_void_p),
-                ("lane_right", C.c_void_p)]
+                ("lane_right", C.c_void_p), ("init_mode", C.c_int32), ("init_states", C.c_void_p),
+                ("init_controls", C.c_void_p)]
 
 
 class BatchOut(C.Structure):
@@ -250,14 +251,22 @@ class Solver:
                        _ptr(corridor_cnt), _ptr(lane_left), _ptr(lane_right))
 
     def plan_batch(self, batch, trajectory: bool = False, init_guess: bool = False, hist_cap: int = 0,
-                   out: dict | None = None, result: bool = False) -> dict:
+                   out: dict | None = None, result: bool = False, init_mode: int = 0, init_states=None,
+                   init_controls=None) -> dict:
         """Host path.  ``batch`` is a ScenarioBatch-like object with numpy arrays (pinned memory
-        gives asynchronous copies).  Returns numpy outputs (or fills the arrays given in ``out``)."""
+        gives asynchronous copies).  Returns numpy outputs (or fills the arrays given in ``out``).
+        init_mode 1: open-loop rollout of ``init_controls`` [B,N,2]; 2: (``init_states`` [B,K,6], ``init_controls``)
+        as the initial guess instead of iqr (ilqr_optimizer.cc:168-169)."""
         B, N, K = batch.B, batch.N, batch.N + 1
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
         arrs = [f64(batch.start), f64(batch.coarse), f64(batch.corridor),
                 np.ascontiguousarray(batch.corridor_cnt, dtype=np.int32), f64(batch.lane_left), f64(batch.lane_right)]
         bi = self._make_in(B, N, batch.M_max, arrs[4].shape[1], arrs[5].shape[1], *arrs)
+        if init_mode:
+            gx = f64(init_states) if init_states is not None else None
+            gu = f64(init_controls)
+            arrs += [gx, gu]  # keep alive
+            bi.init_mode, bi.init_states, bi.init_controls = init_mode, _ptr(gx), _ptr(gu)
         o = out if out is not None else {}
         o.setdefault("states", np.empty((B, K, 6)))
         o.setdefault("controls", np.empty((B, N, 2)))

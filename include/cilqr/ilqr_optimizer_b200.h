@@ -164,6 +164,7 @@ class IlqrOptimizer {
     in.B = 1; in.N = N; in.M_max = M_max; in.S_left = S_left; in.S_right = S_right;
     in.start = start; in.coarse = coarse.data(); in.corridor = planes.data(); in.corridor_cnt = cnt.data();
     in.lane_left = ll.data(); in.lane_right = lr.data();
+    in.init_mode = CILQR_INIT_IQR; in.init_states = nullptr; in.init_controls = nullptr;  // the live line :169
     CilqrBatchOut out;
     out.states = states.data(); out.controls = controls.data(); out.status = status.data();
     out.trajectory = traj.data(); out.init_states = nullptr; out.init_controls = nullptr;

@@ -105,7 +105,18 @@ typedef struct CilqrBatchIn {
   const int32_t* corridor_cnt;
   const double* lane_left;
   const double* lane_right;
+  /* Initial guess of Optimize (ilqr_optimizer.cc:168-169).  CILQR_INIT_IQR (0, default): the live line :169, the
+   * LQR tracking guess `iqr` (:793-842).  CILQR_INIT_OPEN_LOOP: roll init_controls [B][N][2] out from the start
+   * state (OpenLoopRollout, algorithm/slover/ilqr.h:362-370).  CILQR_INIT_GUESS: init_states [B][K][6] and
+   * init_controls [B][N][2] as given -- what InitGuess (:107-139; the commented-out alternative on line :168)
+   * copies out of the Tracker's trajectory; the tracker itself (algorithm/ilqr/tracker.cc) stays with the caller. */
+  int32_t init_mode;
+  const double* init_states;
+  const double* init_controls;
 } CilqrBatchIn;
+#define CILQR_INIT_IQR 0
+#define CILQR_INIT_OPEN_LOOP 1
+#define CILQR_INIT_GUESS 2
 
 typedef struct CilqrBatchOut {
   double* states;        /* required */

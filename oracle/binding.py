@@ -38,7 +38,8 @@ _ip = C.POINTER(C.c_int)
 class Problem(C.Structure):
     _fields_ = [("N", C.c_int), ("M_max", C.c_int), ("S_left", C.c_int), ("S_right", C.c_int),
                 ("start", _dp), ("coarse", _dp), ("corridor", _dp), ("corridor_cnt", _ip),
-                ("lane_left", _dp), ("lane_right", _dp)]
+                ("lane_left", _dp), ("lane_right", _dp), ("init_mode", C.c_int), ("init_states", _dp),
+                ("init_controls", _dp)]
 
 
 class Result(C.Structure):
@@ -72,6 +73,9 @@ def lib():
         L.cilqr_oracle_solve_batch.argtypes = [C.POINTER(Params)] + [C.c_int] * 5 + [
             _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]
         L.cilqr_oracle_solve_batch.restype = C.c_int
+        L.cilqr_oracle_solve_batch_init.argtypes = [C.POINTER(Params)] + [C.c_int] * 5 + [
+            _dp, _dp, _dp, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
+        L.cilqr_oracle_solve_batch_init.restype = C.c_int
         L.cilqr_oracle_normalize_angle.argtypes = [C.c_double]
         L.cilqr_oracle_normalize_angle.restype = C.c_double
         L.cilqr_oracle_dynamics.argtypes = [C.POINTER(Params), _dp, _dp, _dp]
@@ -155,8 +159,10 @@ def solve(batch, b: int, params: Params | None = None, trace: bool = False, hist
     return out
 
 
-def solve_batch(batch, params: Params | None = None, nthreads: int = 1):
-    """-> states[B,K,6], controls[B,N,2], status[B,8] (status, iters, cost5, alpha_hash), n_converged."""
+def solve_batch(batch, params: Params | None = None, nthreads: int = 1, init_mode: int = 0, init_states=None,
+                init_controls=None):
+    """-> states[B,K,6], controls[B,N,2], status[B,8] (status, iters, cost5, alpha_hash), n_converged.
+    init_mode 1: open-loop rollout of init_controls; 2: (init_states, init_controls) as the initial guess."""
     p = params or default_params()
     B, K, N = batch.B, batch.N + 1, batch.N
     states = np.zeros((B, K, 6))
@@ -165,9 +171,12 @@ def solve_batch(batch, params: Params | None = None, nthreads: int = 1):
     start, coarse, corridor = _f64(batch.start), _f64(batch.coarse), _f64(batch.corridor)
     cnt = np.ascontiguousarray(batch.corridor_cnt, dtype=np.int32)
     ll, lr = _f64(batch.lane_left), _f64(batch.lane_right)
-    conv = lib().cilqr_oracle_solve_batch(
+    ix = _f64(init_states) if init_states is not None else None
+    iu = _f64(init_controls) if init_controls is not None else None
+    conv = lib().cilqr_oracle_solve_batch_init(
         C.byref(p), B, N, batch.M_max, ll.shape[1], lr.shape[1], _d(start), _d(coarse), _d(corridor),
-        cnt.ctypes.data_as(_ip), _d(ll), _d(lr), _d(states), _d(controls), _d(status), nthreads)
+        cnt.ctypes.data_as(_ip), _d(ll), _d(lr), init_mode, _d(ix) if ix is not None else None,
+        _d(iu) if iu is not None else None, _d(states), _d(controls), _d(status), nthreads)
     return states, controls, status, conv
 
 

@@ -834,7 +834,16 @@ int cilqr_oracle_solve(const cilqr_oracle_params* p, const cilqr_oracle_problem*
   out->accepted = 0;
   out->alpha_hash = 2166136261u;
 
-  cilqr_oracle_ctx_iqr(c, X, U); /* :169 */
+  if (pb->init_mode == 2 && pb->init_states && pb->init_controls) { /* InitGuess, :168 (commented out there) */
+    memcpy(X, pb->init_states, sizeof(double) * K * 6);
+    memcpy(U, pb->init_controls, sizeof(double) * N * 2);
+  } else if (pb->init_mode == 1 && pb->init_controls) { /* OpenLoopRollout, slover/ilqr.h:362-370 */
+    memcpy(U, pb->init_controls, sizeof(double) * N * 2);
+    memcpy(X, c->goals, sizeof(double) * 6);
+    for (int i = 0; i < N; ++i) cilqr_oracle_dynamics(p, X + i * 6, U + i * 2, X + (i + 1) * 6);
+  } else {
+    cilqr_oracle_ctx_iqr(c, X, U); /* :169 */
+  }
   if (out->init_states) memcpy(out->init_states, X, sizeof(double) * K * 6);
   if (out->init_controls) memcpy(out->init_controls, U, sizeof(double) * N * 2);
 
@@ -943,6 +952,8 @@ typedef struct {
   const int* corridor_cnt;
   double *states, *controls, *status_out;
   int converged;
+  int init_mode;
+  const double *init_states, *init_controls;
 } batch_job;
 
 static void* batch_worker(void* arg) {
@@ -961,6 +972,9 @@ static void* batch_worker(void* arg) {
     pb.corridor_cnt = j->corridor_cnt + (size_t)b * K;
     pb.lane_left = j->lane_left + (size_t)b * j->S_left * 7;
     pb.lane_right = j->lane_right + (size_t)b * j->S_right * 7;
+    pb.init_mode = j->init_mode;
+    pb.init_states = j->init_states ? j->init_states + (size_t)b * K * 6 : 0;
+    pb.init_controls = j->init_controls ? j->init_controls + (size_t)b * j->N * 2 : 0;
     cilqr_oracle_result r;
     memset(&r, 0, sizeof(r));
     r.states = j->states + (size_t)b * K * 6;
@@ -983,6 +997,16 @@ int cilqr_oracle_solve_batch(const cilqr_oracle_params* p, int B, int N, int M_m
                              const double* corridor, const int* corridor_cnt,
                              const double* lane_left, const double* lane_right, double* states,
                              double* controls, double* status_out, int nthreads) {
+  return cilqr_oracle_solve_batch_init(p, B, N, M_max, S_left, S_right, start, coarse, corridor, corridor_cnt, lane_left,
+                                       lane_right, 0, 0, 0, states, controls, status_out, nthreads);
+}
+
+int cilqr_oracle_solve_batch_init(const cilqr_oracle_params* p, int B, int N, int M_max, int S_left,
+                                  int S_right, const double* start, const double* coarse,
+                                  const double* corridor, const int* corridor_cnt,
+                                  const double* lane_left, const double* lane_right, int init_mode,
+                                  const double* init_states, const double* init_controls, double* states,
+                                  double* controls, double* status_out, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > B) nthreads = B > 0 ? B : 1;
   batch_job* jobs = (batch_job*)calloc(nthreads, sizeof(batch_job));
@@ -1006,6 +1030,9 @@ int cilqr_oracle_solve_batch(const cilqr_oracle_params* p, int B, int N, int M_m
     j->states = states;
     j->controls = controls;
     j->status_out = status_out;
+    j->init_mode = init_mode;
+    j->init_states = init_states;
+    j->init_controls = init_controls;
     if (nthreads == 1) {
       batch_worker(j);
     } else {

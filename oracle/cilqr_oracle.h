@@ -64,6 +64,13 @@ typedef struct cilqr_oracle_problem {
   const int* corridor_cnt;   /* [K] planes used at knot k                    */
   const double* lane_left;   /* [S_left][7]  a, b, c, x0, y0, x1, y1         */
   const double* lane_right;  /* [S_right][7]                                 */
+  /* initial guess of Optimize (ilqr_optimizer.cc:168-169): 0 = iqr (the live line :169);
+   * 1 = open-loop rollout of init_controls from goals_[0] (OpenLoopRollout, algorithm/slover/ilqr.h:362-370);
+   * 2 = init_states / init_controls as given -- what InitGuess (:107-139, the commented-out line :168) copies out
+   *     of the tracker's trajectory */
+  int init_mode;
+  const double* init_states;   /* [K][6] (mode 2) */
+  const double* init_controls; /* [N][2] (modes 1, 2) */
 } cilqr_oracle_problem;
 
 enum {
@@ -111,6 +118,14 @@ int cilqr_oracle_solve_batch(const cilqr_oracle_params* p, int B, int N, int M_m
                              const double* corridor, const int* corridor_cnt,
                              const double* lane_left, const double* lane_right, double* states,
                              double* controls, double* status_out, int nthreads);
+/* the same with the initial guess of cilqr_oracle_problem::init_mode for every scenario: init_states [B][K][6],
+ * init_controls [B][N][2] */
+int cilqr_oracle_solve_batch_init(const cilqr_oracle_params* p, int B, int N, int M_max, int S_left,
+                                  int S_right, const double* start, const double* coarse,
+                                  const double* corridor, const int* corridor_cnt,
+                                  const double* lane_left, const double* lane_right, int init_mode,
+                                  const double* init_states, const double* init_controls, double* states,
+                                  double* controls, double* status_out, int nthreads);
 
 /* ---- primitives, exported for unit tests and stage-level GPU parity ---- */
 double cilqr_oracle_normalize_angle(double a);                       /* math_utils.cpp:53-59 */

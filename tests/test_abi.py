@@ -59,7 +59,7 @@ def test_product_library_does_not_link_the_oracle():
 def test_struct_layout_matches_header():
     # CilqrParams: 27 doubles + 2 int32; CilqrBatchIn: 5 int32 (+pad) + 6 pointers; CilqrBatchOut: 10 pointers + int32 (+pad) + 1 pointer
     assert C.sizeof(S.Params) == 27 * 8 + 8
-    assert C.sizeof(S.BatchIn) == 24 + 6 * 8
+    assert C.sizeof(S.BatchIn) == 24 + 6 * 8 + 8 + 2 * 8
     assert C.sizeof(S.BatchOut) == 10 * 8 + 8 + 8
     assert C.sizeof(S.DebugOut) == 18 * 8
     # CilqrCorridorConfig: 6 doubles + int32 (+pad); CilqrCorridorIn: 4 int32 + 3 pointers; CilqrCorridorOut: 4 pointers

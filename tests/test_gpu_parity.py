@@ -168,6 +168,26 @@ def test_gradient_norm_exit(oracle):
     assert n_grad >= 6 and n_same >= 5, (n_grad, n_same)
 
 
+def test_initial_guess_modes(solver, oracle):
+    """init_mode of CilqrBatchIn on the production build: open-loop rollout of the caller's controls, and a caller's
+    (states, controls) guess in place of iqr (ilqr_optimizer.cc:168-169)."""
+    batch = scenarios.generate(23, 0, 256, N=50)
+    rng = np.random.default_rng(0)
+    Xg = batch.coarse.copy()
+    Xg[:, 0, :4] = batch.start
+    Xg[:, 0, 4:] = 0.0
+    Ug = rng.normal(0.0, 0.05, size=(batch.B, batch.N, 2))
+    import os
+    for mode, kw in ((1, dict(init_controls=Ug)), (2, dict(init_states=Xg, init_controls=Ug))):
+        out = solver.plan_batch(batch, init_mode=mode, **kw)
+        Xo, Uo, So, _ = oracle.solve_batch(batch, nthreads=os.cpu_count() or 1, init_mode=mode, **kw)
+        same = (out["status"][:, 0] == So[:, 0]) & (out["status"][:, 1] == So[:, 1]) & (out["status"][:, 7] == So[:, 7])
+        e = np.maximum(rel(out["states"], Xo).reshape(batch.B, -1).max(axis=1), rel(out["controls"], Uo).reshape(batch.B, -1).max(axis=1))
+        print(f"\n[init_mode {mode}] identical decision path {same.sum()}/{batch.B}; within 1e-4 on those {(e[same] < 1e-4).mean():.4f}; "
+              f"median {np.median(e[same]):.2e}; mean iterations {So[:, 1].mean():.2f}")
+        assert same.mean() >= 0.97 and (e[same] < 1e-4).mean() >= 0.97 and np.median(e[same]) < 1e-10
+
+
 def test_shipped_road_and_horizon(solver, oracle):
     """configs[0] emulated: N = 80, 11 obstacles, the shipped (tight) road radii; many of these end on
     the relative-cost test after 0-2 iterations with a huge cost -- same exits as the oracle."""

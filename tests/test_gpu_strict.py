@@ -130,3 +130,26 @@ def test_strict_gradient_exit_and_tolerance_free_solves(oracle_pm):
     print(f"\n[strict, tolerances 0] bit-identical {int(same.sum())}/{batch.B}; exits {np.bincount(So[:, 0].astype(int), minlength=5).tolist()}, "
           f"max iterations {int(So[:, 1].max())}")
     assert same.all()
+
+
+def test_strict_initial_guess_modes_are_bit_identical(strict, oracle_pm):
+    """init_mode (CilqrBatchIn): a caller-provided initial guess instead of iqr -- open-loop rollout of given controls
+    (OpenLoopRollout, slover/ilqr.h:362-370) and (states, controls) as given (InitGuess, ilqr_optimizer.cc:107-139,
+    the commented-out alternative on line :168).  Same bar: bit for bit."""
+    batch = scenarios.generate(23, 0, 128, N=50)
+    B, N = batch.B, batch.N
+    rng = np.random.default_rng(0)
+    Xg = batch.coarse.copy()           # what a tracker would hand over: states near the coarse trajectory ...
+    Xg[:, 0, :4] = batch.start
+    Xg[:, 0, 4:] = 0.0
+    Ug = rng.normal(0.0, 0.05, size=(B, N, 2))  # ... and small controls
+    for mode, kw in ((1, dict(init_controls=Ug)), (2, dict(init_states=Xg, init_controls=Ug))):
+        out = strict.plan_batch(batch, init_mode=mode, init_guess=True, **kw)
+        Xo, Uo, So, _ = oracle_pm.solve_batch(batch, nthreads=os.cpu_count() or 1, init_mode=mode, **kw)
+        same = np.array([np.array_equal(out["states"][b], Xo[b], equal_nan=True) and np.array_equal(out["controls"][b], Uo[b], equal_nan=True)
+                         and np.array_equal(out["status"][b], So[b], equal_nan=True) for b in range(B)])
+        print(f"\n[strict, init_mode {mode}] bit-identical {int(same.sum())}/{B}; exits {np.bincount(So[:, 0].astype(int), minlength=5).tolist()}, "
+              f"mean iterations {So[:, 1].mean():.2f}")
+        assert same.all()
+        if mode == 2:  # iter_trajs[0] is the caller's guess
+            assert np.array_equal(out["init_states"], Xg) and np.array_equal(out["init_controls"], Ug)

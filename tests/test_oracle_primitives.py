@@ -150,3 +150,24 @@ def test_nearest_segment_first_minimum_wins(oracle, small_batch):
         mx, my = 0.5 * (lane[3, 3] + lane[3, 5]), 0.5 * (lane[3, 4] + lane[3, 6])
         assert ctx.nearest(side, mx + 0.3, my - 0.2) == 3
     ctx.close()
+
+
+def test_initial_guess_modes_are_consistent_with_iqr(oracle):
+    """init_mode (oracle cilqr_oracle_problem): handing the solver iqr's own result back as the caller's guess
+    (mode 2: InitGuess, ilqr_optimizer.cc:107-139 / the commented-out line :168) or as controls to roll out open loop
+    (mode 1: OpenLoopRollout, slover/ilqr.h:362-370 -- iqr's rollout IS Dynamics applied to its clamped controls,
+    :830-841) must reproduce the default solve bit for bit; a different guess must change the solve."""
+    import numpy as np
+    from cilqr_b200 import scenarios
+    batch = scenarios.generate(19, 0, 16, N=40)
+    X, U, S, _ = oracle.solve_batch(batch, nthreads=4)
+    X0 = np.stack([oracle.solve(batch, b)["init_states"] for b in range(batch.B)])
+    U0 = np.stack([oracle.solve(batch, b)["init_controls"] for b in range(batch.B)])
+    X2, U2, S2, _ = oracle.solve_batch(batch, nthreads=4, init_mode=2, init_states=X0, init_controls=U0)
+    assert np.array_equal(X2, X) and np.array_equal(U2, U) and np.array_equal(S2, S)
+    X1, U1, S1, _ = oracle.solve_batch(batch, nthreads=4, init_mode=1, init_controls=U0)
+    assert np.array_equal(X1, X) and np.array_equal(U1, U) and np.array_equal(S1, S)
+    Xz, Uz, Sz, _ = oracle.solve_batch(batch, nthreads=4, init_mode=1, init_controls=np.zeros_like(U0))
+    assert not np.array_equal(Xz, X) and np.isfinite(Xz).all()
+    # the open-loop guess with zero controls coasts: its first cost entry differs from iqr's, the solve still improves it
+    assert (Sz[:, 0] <= 4).all()
