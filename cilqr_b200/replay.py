@@ -197,7 +197,7 @@ def replay(scenes, starts=None, solver=None, tf: float = 8.0, dt: float = 0.1, M
             for k, q in enumerate(pk):
                 pts[j, k, :len(q)], cnt[j, k] = q, len(q)
         xyt = np.nan_to_num(dp["xytheta"])
-        cor = solver.corridor_batch(xyt, pts, cnt, M_max=M_max, cfg=cilqr_b200.solver.default_corridor_config(point_cap=min(250, P + 8)))
+        cor = solver.corridor_batch(xyt, pts, cnt, M_max=M_max, cfg=cilqr_b200.solver.default_corridor_config(point_cap=min(250, max(64, P + 16))))
         cor_ok = (cor["code"] == 0).all(axis=1)
         S_cap = 255  # the solver caches nearest-segment indices as bytes
         ll, nl = solver.lane_constraints(left[None], True, S_cap)
