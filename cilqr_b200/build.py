@@ -15,9 +15,9 @@ LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200.so")
 STRICT_LIB_PATH = os.path.join(LIB_DIR, "libcilqr_b200_strict.so")
 # translation units: (source, extra flags).  dp_capi.cu restates double-precision decision logic of the
 # reference and is compiled without FMA contraction (-fmad=false); the solver TU keeps nvcc's default.
-UNITS = [("cilqr_capi.cu", []), ("dp_capi.cu", ["-fmad=false"]), ("multi_capi.cu", [])]
+UNITS = [("cilqr_capi.cu", []), ("dp_capi.cu", ["-fmad=false"]), ("tracker_capi.cu", ["-fmad=false"]), ("multi_capi.cu", [])]
 DEPS = ["cilqr_capi.cu", "cilqr_kernel.cuh", "cilqr_strict.cuh", "pm_math.h", "corridor_kernel.cuh", "dp_capi.cu",
-        "dp_kernel.cuh", "cilqr_internal.h", "multi_capi.cu", os.path.join("..", "..", "include", "cilqr_b200.h")]
+        "dp_kernel.cuh", "cilqr_internal.h", "multi_capi.cu", "tracker_capi.cu", "tracker_kernel.cuh", os.path.join("..", "..", "include", "cilqr_b200.h")]
 NVCC_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                 "-Xcompiler", "-fPIC"]
 NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "static", "-ldl", "-lpthread"]

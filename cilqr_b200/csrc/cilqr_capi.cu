@@ -81,9 +81,9 @@ struct cilqr_handle {
   bool corr_timed = false;
   int64_t corr_launches = 0;
   // scratch / events of the other translation units (cilqr_internal.h)
-  char* aux_buf[2] = {nullptr, nullptr};
-  size_t aux_bytes[2] = {0, 0};
-  cudaEvent_t aux_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  char* aux_buf[3] = {nullptr, nullptr, nullptr};
+  size_t aux_bytes[3] = {0, 0, 0};
+  cudaEvent_t aux_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 namespace {
@@ -513,7 +513,7 @@ int cilqr_create(const CilqrParams* params, int device, int N_max, int M_max, in
     return e == cudaSuccess;
   };
   if (!raise_limit((const void*)cilqr::cilqr_solve_kernel) || !raise_limit((const void*)corridor::corridor_build_kernel) ||
-      cilqr_internal_dp_set_smem(h->smem_optin) != CILQR_OK) {
+      cilqr_internal_dp_set_smem(h->smem_optin) != CILQR_OK || cilqr_internal_tracker_set_smem(h->smem_optin) != CILQR_OK) {
     fprintf(stderr, "cilqr_b200: %s\n", h->cuda_err.c_str());
     return bail(CILQR_E_CUDA);
   }
@@ -559,7 +559,7 @@ void cilqr_destroy(cilqr_handle* h) {
     if (s->ready_host) cudaFreeHost(s->ready_host);
     if (s->stream) cudaStreamDestroy(s->stream);
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (h->aux_buf[i]) cudaFree(h->aux_buf[i]);
     for (int j = 0; j < 2; ++j)
       if (h->aux_ev[i][j]) cudaEventDestroy(h->aux_ev[i][j]);
@@ -1069,6 +1069,7 @@ int cilqr_corridor_last_kernel_ms(cilqr_handle* h, float* ms) {
 int cilqr_internal_device(const cilqr_handle* h) { return h->device; }
 cudaStream_t cilqr_internal_stream(cilqr_handle* h) { return h->slots[0].stream; }
 int cilqr_internal_num_sms(const cilqr_handle* h) { return h->num_sms; }
+int cilqr_internal_smem_optin(const cilqr_handle* h) { return h->smem_optin; }
 int cilqr_internal_fail(cilqr_handle* h, cudaError_t e, const char* where) { return fail_cuda(h, e, where); }
 int cilqr_internal_scratch(cilqr_handle* h, int slot, size_t bytes, char** out) {
   if (h->aux_bytes[slot] < bytes) {

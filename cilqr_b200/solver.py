@@ -84,6 +84,15 @@ class DpConfig(C.Structure):
         "max_velocity", "width", "wheel_base", "front_hang_length", "rear_hang_length")]
 
 
+class TrackerConfig(C.Structure):
+    """POD mirror of CilqrTrackerConfig (TrackerConfig planner_config.h:18-43 + VehicleParam fields)."""
+    _fields_ = [(n, C.c_double) for n in (
+        "sumulation_dt", "dt", "tolerance", "lat_weight_l", "lat_weight_theta", "lat_weight_delta", "lat_weight_delta_rate",
+        "lat_preview_time", "lon_weight_s", "lon_weight_v", "lon_weight_a", "lon_weight_j", "wheel_base", "delta_min",
+        "delta_max", "min_acceleration", "max_acceleration", "delta_rate_min", "delta_rate_max", "jerk_min", "jerk_max")] + [
+        ("max_num_iteration", C.c_int32)]
+
+
 class DpIn(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "R", "NB", "V", "n_static", "n_dyn", "T")] + [
         (n, C.c_void_p) for n in ("ref", "barrier", "start", "static_poly", "static_nv", "dyn_time", "dyn_samples",
@@ -104,7 +113,8 @@ EXPORTS = ["cilqr_abi_version", "cilqr_default_params", "cilqr_create", "cilqr_d
            "cilqr_corridor_batch_device", "cilqr_lane_constraints", "cilqr_lane_constraints_device",
            "cilqr_corridor_last_kernel_ms", "cilqr_dp_default_config", "cilqr_dp_num_knots",
            "cilqr_dp_plan_batch", "cilqr_dp_plan_batch_device", "cilqr_dp_last_kernel_ms",
-           "cilqr_multi_create", "cilqr_multi_destroy", "cilqr_multi_devices", "cilqr_multi_shard_size",
+           "cilqr_tracker_default_config", "cilqr_tracker_batch", "cilqr_tracker_batch_device",
+           "cilqr_tracker_last_kernel_ms", "cilqr_multi_create", "cilqr_multi_destroy", "cilqr_multi_devices", "cilqr_multi_shard_size",
            "cilqr_multi_last_error", "cilqr_plan_sharded"]
 
 _libs = {}
@@ -165,6 +175,11 @@ def load_library(build_if_missing: bool = True, variant: str = ""):
     L.cilqr_dp_plan_batch_device.argtypes = [C.c_void_p, C.POINTER(DpConfig), C.POINTER(DpIn), C.POINTER(DpOut),
                                              C.c_void_p]
     L.cilqr_dp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cilqr_tracker_default_config.argtypes = [C.POINTER(TrackerConfig)]
+    L.cilqr_tracker_default_config.restype = None
+    L.cilqr_tracker_batch.argtypes = [C.c_void_p, C.POINTER(TrackerConfig), C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.cilqr_tracker_batch_device.argtypes = [C.c_void_p, C.POINTER(TrackerConfig), C.c_int, C.c_int] + [C.c_void_p] * 7
+    L.cilqr_tracker_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.cilqr_multi_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]
     L.cilqr_multi_destroy.argtypes = [C.c_void_p]
@@ -420,6 +435,35 @@ class Solver:
                                                                         dyn_time, dyn_samples, dyn_poly, dyn_nv)])
         do = DpOut(_ptr(trajectory), _ptr(coarse), _ptr(xytheta), _ptr(ok), _ptr(cost), _ptr(waypoints))
         self._check(self._L.cilqr_dp_plan_batch_device(self._h, C.byref(cfg), C.byref(di), C.byref(do), stream))
+
+    # ---- tracker initial guess (Tracker::Plan, algorithm/ilqr/tracker.cc:169-215 + InitGuess) ----------------------
+    def tracker_batch(self, start4, coarse_traj, cfg: "TrackerConfig | None" = None) -> dict:
+        """Host path: start4 [B,4], coarse_traj [B,K,13] (TrajectoryPoint records) -> trajectory [B,K,13],
+        guess_states [B,K,6], guess_controls [B,K-1,2], ok [B]."""
+        if cfg is None:
+            cfg = TrackerConfig()
+            self._L.cilqr_tracker_default_config(C.byref(cfg))
+        st = np.ascontiguousarray(start4, np.float64)
+        co = np.ascontiguousarray(coarse_traj, np.float64)
+        B, K = co.shape[:2]
+        o = {"trajectory": np.zeros((B, K, 13)), "guess_states": np.zeros((B, K, 6)), "guess_controls": np.zeros((B, K - 1, 2)),
+             "ok": np.zeros(B, np.int32)}
+        self._check(self._L.cilqr_tracker_batch(self._h, C.byref(cfg), B, K, _ptr(st), _ptr(co), _ptr(o["trajectory"]),
+                                                _ptr(o["guess_states"]), _ptr(o["guess_controls"]), _ptr(o["ok"])))
+        return o
+
+    def tracker_batch_device(self, B, K, start4, coarse_traj, ok, traj=None, guess_states=None, guess_controls=None,
+                             cfg: "TrackerConfig | None" = None, stream: int | None = None):
+        if cfg is None:
+            cfg = TrackerConfig()
+            self._L.cilqr_tracker_default_config(C.byref(cfg))
+        self._check(self._L.cilqr_tracker_batch_device(self._h, C.byref(cfg), B, K, _ptr(start4), _ptr(coarse_traj), _ptr(traj),
+                                                       _ptr(guess_states), _ptr(guess_controls), _ptr(ok), stream))
+
+    def tracker_last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.cilqr_tracker_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def dp_last_kernel_ms(self) -> float:
         ms = C.c_float()

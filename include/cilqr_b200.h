@@ -343,6 +343,42 @@ int cilqr_dp_plan_batch_device(cilqr_handle* h, const CilqrDpConfig* cfg, const 
 int cilqr_dp_plan_batch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const CilqrDpOut* out);
 int cilqr_dp_last_kernel_ms(cilqr_handle* h, float* ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tracker initial guess: the alternative to iqr that README.md:61 recommends.
+ * Replaces Tracker::Plan (algorithm/ilqr/tracker.h:48-51, tracker.cc:11-17,169-215) -- a 10 ms closed-loop simulation
+ * along the coarse trajectory with lateral and longitudinal discrete LQR controllers whose gains come from a DARE
+ * fixed-point iteration at every step (math::SolveLQRProblem, algorithm/math/linear_quadratic_regulator.cc:30-70) --
+ * and the copy IlqrOptimizer::InitGuess (ilqr_optimizer.cc:107-139) makes of its result, for B scenarios at once.
+ *
+ *   start          [B][4]            x, y, theta, v of start_state (trajectory_planner.cpp:73-75)
+ *   coarse_traj    [B][K][13]        TrajectoryPoint records of the coarse trajectory (time, s, x, y, theta, kappa,
+ *                                    velocity, ...): exactly cilqr_dp_plan_batch's `trajectory` output
+ *   traj           [B][K][13]  out (opt.) the tracker's trajectory (opt_trajectory of Tracker::Plan)
+ *   guess_states   [B][K][6]   out (opt.) x, y, theta, velocity, a, delta      = CilqrBatchIn::init_states
+ *   guess_controls [B][K-1][2] out (opt.) jerk, delta_rate                     = CilqrBatchIn::init_controls
+ *   ok             [B] int32   out        Tracker::Plan's return value (the simulation reached every knot)
+ * With init_mode = CILQR_INIT_GUESS the solve starts from (guess_states, guess_controls): DP -> tracker -> solve chain
+ * on the device.
+ */
+typedef struct CilqrTrackerConfig { /* TrackerConfig, planner_config.h:18-43 + the VehicleParam fields the tracker reads */
+  double sumulation_dt, dt, tolerance;
+  double lat_weight_l, lat_weight_theta, lat_weight_delta, lat_weight_delta_rate, lat_preview_time;
+  double lon_weight_s, lon_weight_v, lon_weight_a, lon_weight_j;
+  double wheel_base, delta_min, delta_max, min_acceleration, max_acceleration, delta_rate_min, delta_rate_max, jerk_min,
+      jerk_max;
+  int32_t max_num_iteration;
+} CilqrTrackerConfig;
+void cilqr_tracker_default_config(CilqrTrackerConfig* c);
+/* DEVICE pointers; enqueues on `cuda_stream` (NULL = the handle's stream) and returns. */
+int cilqr_tracker_batch_device(cilqr_handle* h, const CilqrTrackerConfig* cfg, int B, int K, const double* start,
+                               const double* coarse_traj, double* traj, double* guess_states, double* guess_controls,
+                               int32_t* ok, void* cuda_stream);
+/* HOST pointers; blocks until the outputs are in host memory. */
+int cilqr_tracker_batch(cilqr_handle* h, const CilqrTrackerConfig* cfg, int B, int K, const double* start,
+                        const double* coarse_traj, double* traj, double* guess_states, double* guess_controls,
+                        int32_t* ok);
+int cilqr_tracker_last_kernel_ms(cilqr_handle* h, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

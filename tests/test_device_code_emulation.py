@@ -68,3 +68,36 @@ def test_dp_device_code_equals_the_oracle(tmp_path):
         assert bool(ok[b]) == o_ok and cost[b] == o_cost and np.array_equal(wp[b], o_wp)
         assert np.array_equal(traj[b], o_traj, equal_nan=True)
         assert np.array_equal(coarse[b][:, :3], o_traj[:, 2:5], equal_nan=True)
+
+
+def test_tracker_device_code_equals_the_oracle(tmp_path):
+    """tracker_kernel (cilqr_b200/csrc/tracker_kernel.cuh) compiled for the host against oracle/tracker_oracle.c, which is
+    itself bit-identical to the reference's own Tracker (tests/test_reference_pins.py): trajectory, InitGuess copy, ok."""
+    from oracle import dp_binding as dp
+    from oracle import tracker_binding as tb
+    L = _build(tmp_path, "tracker_host_emul")
+    db = scenarios.generate_dp(5, 4, n_obs=6)
+    barrier = dp.build_barrier(db.ref)
+    cfg = tb.default_config()
+    names = ["sumulation_dt", "dt", "tolerance", "lat_weight_l", "lat_weight_theta", "lat_weight_delta", "lat_weight_delta_rate",
+             "lat_preview_time", "lon_weight_s", "lon_weight_v", "lon_weight_a", "lon_weight_j", "wheel_base", "delta_min",
+             "delta_max", "min_acceleration", "max_acceleration", "delta_rate_min", "delta_rate_max", "jerk_min", "jerk_max"]
+    cf = np.array([getattr(cfg, n) for n in names])
+    coarse, starts = [], []
+    for b in range(db.B):
+        sc = dp.Scene(db.ref, barrier, db.static_poly[b], db.static_nv[b], db.dyn_time[b], db.dyn_samples[b], db.dyn_poly[b],
+                      db.dyn_nv[b])
+        ok, traj, _, _ = dp.plan(sc, *db.start[b])
+        if ok and not np.isnan(traj).any():
+            coarse.append(traj)
+            starts.append([db.start[b][0] + 0.2, db.start[b][1] - 0.1, db.start[b][2] + 0.03, 9.0])
+    coarse, starts = np.ascontiguousarray(coarse), np.ascontiguousarray(starts)
+    B, K = coarse.shape[:2]
+    assert B >= 2
+    traj, gx, gu, ok = np.zeros((B, K, 13)), np.zeros((B, K, 6)), np.zeros((B, K - 1, 2)), np.zeros(B, np.int32)
+    L.emul_tracker(_p(cf), cfg.max_num_iteration, B, K, _p(starts), _p(coarse), _p(traj), _p(gx), _p(gu), _p(ok))
+    for b in range(B):
+        oko, to, _ = tb.plan(tb.start_record(starts[b]), coarse[b])
+        X, U = tb.init_guess(to)
+        assert ok[b] == int(oko) == 1
+        assert np.array_equal(traj[b], to) and np.array_equal(gx[b], X) and np.array_equal(gu[b], U)

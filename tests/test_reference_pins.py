@@ -374,3 +374,37 @@ def test_gradient_norm_exit_equals_the_reference(oracle):
             assert len(o["cost_hist"]) == o["accepted"] + 1
             seen += 1
     assert seen == 8
+
+
+# ---- the reference's own Tracker (tracker.cc + linear_quadratic_regulator.cc compiled unmodified) -----------------
+def test_tracker_equals_the_reference_bit_for_bit():
+    """Tracker::Plan (algorithm/ilqr/tracker.cc:169-215: 800 simulation steps, two DARE fixed-point solves each, RK4)
+    of the reference itself against oracle/tracker_oracle.c on DP-planned coarse trajectories: every field of every
+    trajectory point bit-identical (about 50 000 DARE iterations per plan)."""
+    from oracle import dp_binding as dpo
+    from oracle import tracker_binding as tb
+    dpo.build()
+    assert tb.ref_lib() is not None, "oracle/_ref/libcilqr_ref_tracker.so missing: run `make -C oracle _ref`"
+    n = 0
+    for seed, B in ((3, 6), (4, 6)):
+        db = scenarios.generate_dp(seed, B, n_obs=6)
+        barrier = dpo.build_barrier(db.ref)
+        for b in range(B):
+            sc = dpo.Scene(db.ref, barrier, db.static_poly[b], db.static_nv[b], db.dyn_time[b], db.dyn_samples[b],
+                           db.dyn_poly[b], db.dyn_nv[b])
+            ok, traj, _, _ = dpo.plan(sc, *db.start[b])
+            if not ok or np.isnan(traj).any():
+                continue
+            for v0 in (10.0, 4.0):
+                s13 = tb.start_record([db.start[b][0] + 0.3, db.start[b][1] - 0.2, db.start[b][2] + 0.05, v0])
+                oko, to, its = tb.plan(s13, traj)
+                rc, tr = tb.ref_plan(s13, traj)
+                assert rc == int(oko) == 1 and its > 10000
+                assert np.array_equal(to, tr)
+                n += 1
+    assert n >= 12
+    # a follow trajectory whose time stamps the simulation clock cannot reach: both report failure
+    bad = traj.copy()
+    bad[:, 0] *= 0.999
+    s13 = tb.start_record([*db.start[b], 10.0])
+    assert tb.ref_plan(s13, bad)[0] in (0, -1) and not tb.plan(s13, bad)[0]
