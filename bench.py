@@ -317,14 +317,50 @@ def dp_measurement(solver, a, dev, stream, peak=None):
     tin = [tile(x) for x in (db.start, db.static_poly, db.static_nv, db.dyn_time, db.dyn_samples, db.dyn_poly, db.dyn_nv)]
     ok = torch.zeros(B, dtype=torch.int32, device=dev)
     coarse = torch.zeros(B, K, 6, dtype=torch.float64, device=dev)
+    traj = torch.zeros(B, K, 13, dtype=torch.float64, device=dev)
     ms = []
     for _ in range(3):
         torch.cuda.synchronize()
         solver.dp_plan_batch_device(B, len(db.ref), len(barrier), 4, db.static_poly.shape[1], db.dyn_poly.shape[1],
-                                    db.dyn_poly.shape[2], ref, bar, *tin, ok, coarse=coarse, stream=stream.cuda_stream)
+                                    db.dyn_poly.shape[2], ref, bar, *tin, ok, coarse=coarse, trajectory=traj,
+                                    stream=stream.cuda_stream)
         torch.cuda.synchronize()
         ms.append(solver.dp_last_kernel_ms())
     kms = float(np.mean(ms[1:]))
+    # the Tracker initial guess on the planner's own output, chained on the device
+    tracker = None
+    try:
+        from oracle import tracker_binding as tb
+        good = torch.nonzero(ok.bool() & torch.isfinite(traj).all(dim=2).all(dim=1)).flatten()
+        tg = traj[good].contiguous()
+        st4 = torch.cat([tin[0][good], torch.full((len(good), 1), 10.0, dtype=torch.float64, device=dev)], dim=1).contiguous()
+        gx = torch.zeros(len(good), K, 6, dtype=torch.float64, device=dev)
+        gu = torch.zeros(len(good), K - 1, 2, dtype=torch.float64, device=dev)
+        tok = torch.zeros(len(good), dtype=torch.int32, device=dev)
+        tms = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            solver.tracker_batch_device(len(good), K, st4, tg, tok, guess_states=gx, guess_controls=gu, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            tms.append(solver.tracker_last_kernel_ms())
+        n_t = 8
+        th, sh = tg[:n_t].cpu().numpy(), st4[:n_t].cpu().numpy()
+        t0 = time.perf_counter()
+        ref_t = [tb.plan(tb.start_record(sh[b]), th[b]) for b in range(n_t)]
+        cpu_t = (time.perf_counter() - t0) / n_t
+        gx_h = gx[:n_t].cpu().numpy()
+        err = max(float(np.abs(gx_h[b] - tb.init_guess(ref_t[b][1])[0]).max()) for b in range(n_t))
+        tk = float(np.mean(tms[1:]))
+        tracker = {"kernel": "tracker_kernel", "scenes_per_launch": int(len(good)), "kernel_ms": tk,
+                   "traj_per_s": len(good) / tk * 1e3, "ok_fraction": float(tok.double().mean().item()),
+                   "cpu_baseline": {"value": 1.0 / cpu_t, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"first {n_t} scenes, oracle/tracker_oracle.c (bit-identical to the reference's own "
+                                              f"tracker.cc), 1 thread, {cpu_t * 1e3:.1f} ms per plan; max abs difference of the guess "
+                                              f"states GPU vs CPU: {err:.1e}"},
+                   "note": "800 sequential 10 ms simulation steps per scene, ~50 000 DARE iterations; one thread per scene "
+                           "(latency bound by construction); HBM traffic negligible"}
+    except Exception as ex:  # side measurement only
+        tracker = {"error": str(ex)[:200]}
     n_cpu = 6
     # CPU side: the reference's OWN DpPlanner (oracle/_ref/libcilqr_ref_dp.so, compiled from the reference sources in
     # the build container; it travels with the repo) when present, else the C restatement -- bit-identical anyway
@@ -361,7 +397,7 @@ def dp_measurement(solver, a, dev, stream, peak=None):
                 "note": "compute / latency bound (19 670 transitions x ~10 collision-checked points per scene); the HBM "
                         "fraction is reported as defined, not as the limiter"}
     return {"kernel": "dp_plan_kernel", "scenes_per_launch": B, "kernel_ms": kms, "traj_per_s": B / kms * 1e3,
-            "planned_ok_fraction": float(ok.double().mean().item()), "roofline": roof,
+            "planned_ok_fraction": float(ok.double().mean().item()), "roofline": roof, "tracker": tracker,
             "cpu_baseline": {"value": n_cpu / cpu_s, "unit": UNIT, "cores": 1, "kind": kind,
                              "sample": f"first {n_cpu} scenes, {impl}, 1 thread, {cpu_s:.2f} s; "
                                        f"ok flags equal to the GPU's: {same}"},
@@ -426,6 +462,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL sizes its channel count from the topology it detects; on this pool's boxes it picks few channels and the
+        # all-gather of the result blocks runs at ~140 GB/s per GPU.  32 channels: 444 GB/s at 2 GPUs
+        # (profiles/r02_k_nccl_channels.txt).  A user's own setting wins.
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     B, N = a.batch_per_gpu, a.horizon
@@ -659,6 +699,7 @@ def main():
             res["config"]["allgather"] = {"ms_per_step": ag_ms, "bytes_received_per_gpu": int(ag_bytes),
                                           "achieved_gbs_per_gpu": ag_bytes / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None,
                                           "nvlink_peak_gbs_per_direction": 900.0,
+                                          "nccl_min_nchannels": os.environ.get("NCCL_MIN_NCHANNELS"),
                                           "note": "exposed time of the all-gather with one batch in flight (step time "
                                                   "minus solve-kernel time); with batches in flight it overlaps the next solve"}
         if e2e:

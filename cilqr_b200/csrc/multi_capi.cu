@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -206,6 +207,9 @@ int cilqr_plan_sharded(cilqr_multi* m, const CilqrBatchIn* in, const CilqrBatchO
       m->err = "libnccl.so.2 could not be loaded";
       return CILQR_E_NCCL;
     }
+    // (NCCL picks few channels on some boxes: ~140 GB/s per GPU for this all-gather against 444 GB/s with 32 channels,
+    // profiles/r02_k_nccl_channels.txt; a setting the user made wins)
+    setenv("NCCL_MIN_NCHANNELS", "32", 0);
     std::vector<int> devs(G);
     for (int r = 0; r < G; ++r) devs[r] = m->sh[r].device;
     m->comms.assign(G, nullptr);

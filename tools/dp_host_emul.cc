@@ -9,6 +9,8 @@
 #define __device__
 #define __host__
 #define __global__
+#define __grid_constant__
+#define __noinline__
 #define __forceinline__ inline
 #define __launch_bounds__(x)
 #define __align__(x)
