@@ -207,7 +207,7 @@ __device__ __forceinline__ RefPoint interpolate(const double* p0, const double* 
 // EvaluateStation, :110-121 with QueryLowerBoundStationPoint :34-46.  std::lower_bound's answer (the first
 // index whose s is not less than the station) is unique for the sorted line, so it is found from a guess
 // (uniform spacing) corrected by stepping -- the same index in 2-3 loads instead of 12.
-__device__ __noinline__ RefPoint evaluate_station(const Args& a, double station) {
+__device__ __forceinline__ RefPoint evaluate_station(const Args& a, double station) {
   const double* ref = a.ref;
   const int R = a.R;
   int it;
@@ -266,7 +266,7 @@ __device__ __forceinline__ bool aabb_disjoint(const double* o, double cx, double
 }
 
 // Polygon2d::HasOverlap(const Box2d&), polygon2d.cpp:150-165, after its bounding-box rejection
-__device__ __noinline__ bool polygon_overlaps_box(const double* p, int nv, const double* bb, double cx, double cy, double half) {
+__device__ bool polygon_overlaps_box(const double* p, int nv, const double* bb, double cx, double cy, double half) {
   if (aabb_disjoint(bb, cx, cy, half)) return false;
   for (int i = 0; i < nv; ++i)
     if (box_is_point_in(p[2 * i], p[2 * i + 1], cx, cy, half)) return true;
@@ -291,7 +291,7 @@ __device__ __forceinline__ int barrier_upper_bound(const double* bar, int NB, do
 // obb: per scenario, in shared memory: the bounds of every static polygon, then for every dynamic obstacle the
 // bounds of ALL its samples (a box that misses those misses every sample's own bounding box, which is the
 // reference's first test)
-__device__ __noinline__ bool check_static(const Args& a, int b, const double* obb, bool any_near, double cx, double cy, double half) {
+__device__ bool check_static(const Args& a, int b, const double* obb, bool any_near, double cx, double cy, double half) {
   const double* polys = a.static_poly + (size_t)b * a.n_static * a.V * 2;
   const int* nv = a.static_nv + (size_t)b * a.n_static;
   for (int o = 0; any_near && o < a.n_static; ++o) {
@@ -345,7 +345,7 @@ __device__ __forceinline__ int dynamic_sample(const Args& a, size_t ob, double t
   }
   return lo >= ns ? ns - 1 : lo;
 }
-__device__ __noinline__ bool check_dynamic(const Args& a, int b, const double* obb, const double* sbb, const int* sidx, int point,
+__device__ bool check_dynamic(const Args& a, int b, const double* obb, const double* sbb, const int* sidx, int point,
                               double time, double cx, double cy, double half) {
   for (int o = 0; o < a.n_dyn; ++o) {
     if (aabb_disjoint(obb + 4 * (a.n_static + o), cx, cy, half)) continue;
