@@ -153,3 +153,17 @@ def test_strict_initial_guess_modes_are_bit_identical(strict, oracle_pm):
         assert same.all()
         if mode == 2:  # iter_trajs[0] is the caller's guess
             assert np.array_equal(out["init_states"], Xg) and np.array_equal(out["init_controls"], Ug)
+
+
+def test_strict_16k_slice_of_the_bench_workload_is_bit_identical(strict, oracle_pm):
+    """16 384 scenarios of BASELINE configs[2] (the workload bench.py times, seed 20260103): the size at which the
+    persistent scheduler really runs full (128 contexts per CTA, type epochs, hot contexts, help board, drain) --
+    still every bit of every scenario.  (tools/strict_full.py does all 65 536: profiles/r02_strict_full_65536.log.)"""
+    batch = scenarios.generate(20260103, 0, 16384, N=100, workers=16)
+    out = strict.plan_batch(batch)
+    Xo, Uo, So, _ = oracle_pm.solve_batch(batch, nthreads=os.cpu_count() or 1)
+    same = np.array([np.array_equal(out["states"][b], Xo[b], equal_nan=True) and np.array_equal(out["controls"][b], Uo[b], equal_nan=True)
+                     and np.array_equal(out["status"][b], So[b], equal_nan=True) for b in range(batch.B)])
+    print(f"\n[strict, bench workload] bit-identical {int(same.sum())}/{batch.B}; strict kernel {strict.last_kernel_ms():.0f} ms; "
+          f"exits {np.bincount(So[:, 0].astype(int), minlength=5).tolist()}, max iterations {int(So[:, 1].max())}")
+    assert same.all()
