@@ -59,6 +59,12 @@
 
 namespace cilqr {
 
+// The CTA's dynamic shared memory: one stage per warp.  Declared at namespace scope and addressed as
+// smem_cta + offset inside every phase function, so that the compiler KNOWS the accesses are to shared memory and
+// emits LDS / STS with 32-bit addresses; a stage pointer handed through structs and __noinline__ calls is a generic
+// pointer and costs a 64-bit address computation plus a generic LD / ST per access (profiles/r02_sass_summary.txt).
+extern __shared__ __align__(16) double smem_cta[];
+
 constexpr int kNX = 6;
 constexpr int kNU = 2;
 constexpr int kDisc = 5;
@@ -433,15 +439,16 @@ __device__ __forceinline__ void cp_async_wait() {
 // What one warp needs to run one phase of one context.
 struct Ctx {
   const KernelArgs& a;
-  double* sm;   // this warp's shared-memory stage
+  int sm_off;   // this warp's shared-memory stage: smem_cta + sm_off (doubles)
   double* cx;   // this context in the global workspace
   CtxHdr* h;
   int lane;
   bool seg_staged;      // this warp's stage already holds the context's lane segments (chained EVALs)
   const double* goals;  // global [K][6] (row 0 is replaced by h->g0)
   const int32_t* cnt;   // global [K]
-  __device__ Ctx(const KernelArgs& a_, double* s, double* c, int l)
-      : a(a_), sm(s), cx(c), h(reinterpret_cast<CtxHdr*>(c + a_.cl.hdr)), lane(l), seg_staged(false), goals(nullptr), cnt(nullptr) {}
+  __device__ __forceinline__ double* smp() const { return smem_cta + sm_off; }
+  __device__ Ctx(const KernelArgs& a_, int s, double* c, int l)
+      : a(a_), sm_off(s), cx(c), h(reinterpret_cast<CtxHdr*>(c + a_.cl.hdr)), lane(l), seg_staged(false), goals(nullptr), cnt(nullptr) {}
   __device__ __forceinline__ void bind(unsigned b) {
     goals = a.coarse + (size_t)b * (a.N + 1) * 6;
     cnt = a.corridor_cnt + (size_t)b * (a.N + 1);
@@ -557,8 +564,8 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
-  const double* seg = c.sm + a.sm.seg;
-  double* trig = c.sm + a.sm.trig;  // [K][2] sin, cos
+  const double* seg = c.smp() + a.sm.seg;
+  double* trig = c.smp() + a.sm.trig;  // [K][2] sin, cos
   double sum_j = 0.0, sum_d = 0.0, sum_c = 0.0, sum_l = 0.0;
 #pragma unroll 1
   for (int k = c.lane; k < K; k += 32) {
@@ -590,9 +597,9 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   __syncwarp();
   const int items = K * kDisc;
   const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
-  const double* grp = c.sm + a.sm.grp;
+  const double* grp = c.smp() + a.sm.grp;
   const double* cert = grp + (ngl + ngr) * 3;  // [S_left + S_right] certificate radii, behind the group circles
-  double* pbuf = c.sm + a.sm.pl_e;
+  double* pbuf = c.smp() + a.sm.pl_e;
   const int pstride = a.M_max * kPlaneTile;
   // tile of chunk j0: knots j0/5 .. (j0+31)/5 (at most kPlaneKnots), planes below the chunk's largest count
   auto chunk_M = [&](int j0) {
@@ -768,7 +775,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const double* seg = c.gseg();  // only (a, b, c) of ten segments per knot: read from the context
-  double* pbuf = c.sm + a.sm.pl_b;
+  double* pbuf = c.smp() + a.sm.pl_b;
   const int pstride = a.M_max * kPlaneTile;
   const int d = c.lane / kKnotsPerPass, kl = c.lane - d * kKnotsPerPass;
   auto pass_M = [&](int g0) { return (d < kDisc && g0 + kl < nk) ? c.cnt[k0 + g0 + kl] : 0; };
@@ -839,7 +846,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     }
     // sum over the five disc lanes of each knot through shared memory, in the fixed order
     // ((d0 + d3) + (d1 + d4)) + d2
-    double* rb = c.sm + a.sm.red;  // [9][32]
+    double* rb = c.smp() + a.sm.red;  // [9][32]
     rb[0 * 32 + c.lane] = J0;
     rb[1 * 32 + c.lane] = J1;
     rb[2 * 32 + c.lane] = J2;
@@ -920,7 +927,7 @@ __device__ __noinline__ void linearize_window(const Ctx& c, int k0, const double
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
-  double* lin = c.sm + a.sm.lin;
+  double* lin = c.smp() + a.sm.lin;
   double* R = c.linrec();
   const int k = k0 + lane;
   const int nk = K - k0 < kWin ? K - k0 : kWin;
@@ -959,8 +966,8 @@ __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double d
   const KernelArgs& a = c.a;
   const int N = a.N;
   const int lane = c.lane;
-  double* scr = c.sm + a.sm.scr;
-  double* ring = c.sm + a.sm.bring;  // two stages of kBackChunk records
+  double* scr = c.smp() + a.sm.scr;
+  double* ring = c.smp() + a.sm.bring;  // two stages of kBackChunk records
   const double* R = c.linrec();
   double* gains = c.gains();  // global: K, k of every knot are consumed by the next ROLL phase
   double* M = scr + SM_;
@@ -1218,12 +1225,12 @@ __device__ __noinline__ void stage_segments(Ctx& c) {
   c.seg_staged = true;
   const int n16 = ((a.S_left + a.S_right) * kSegStride + 1) / 2;
   const double* src = c.gseg();
-  double* dst = c.sm + a.sm.seg;
+  double* dst = c.smp() + a.sm.seg;
   for (int i = c.lane; i < n16; i += 32) cp_async16(dst + i * 2, src + i * 2);
   const int ng = (a.S_left + kGroup - 1) / kGroup + (a.S_right + kGroup - 1) / kGroup;
   const int g16 = (ng * 3 + a.S_left + a.S_right + 1) / 2;  // group circles + certificate radii
   const double* gs = c.ggrp();
-  double* gd = c.sm + a.sm.grp;
+  double* gd = c.smp() + a.sm.grp;
   for (int i = c.lane; i < g16; i += 32) cp_async16(gd + i * 2, gs + i * 2);
   cp_async_commit();
   cp_async_wait<0>();
@@ -1419,7 +1426,7 @@ __device__ __noinline__ int phase_init(Ctx& c) {
       }
     }
     const int ST_ = a.S_left + a.S_right;
-    double* seg = c.sm + a.sm.seg;
+    double* seg = c.smp() + a.sm.seg;
     double* gsg = c.gseg();
 #pragma unroll 1
     for (int s = lane; s < ST_; s += 32) {
@@ -1577,7 +1584,8 @@ constexpr int kRollGroups = 8;
 __device__ __forceinline__ double* ctx_base(const KernelArgs& a, const int* gidx, int id) {
   return a.ws + (size_t)gidx[id] * a.cl.stride;  // gidx: the CTA's slot -> global context index table (shared memory)
 }
-__device__ __noinline__ void roll_multi(const KernelArgs& a, double* sm, const int* gidx, int my_id, int lane) {
+__device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const int* gidx, int my_id, int lane) {
+  double* sm = smem_cta + sm_off;
   const DevParams& P = a.P;
   const int g = lane >> 2, ai = lane & 3;
   const bool valid = my_id >= 0;
@@ -2131,7 +2139,7 @@ __device__ __noinline__ int gang_lin(Ctx& c, HelpBoard* hb, int mine) {
 }
 
 // An idle warp looks at the board; returns true if it evaluated a candidate for somebody.
-__device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, const int* gidx, HelpBoard* hb, int lane) {
+__device__ __noinline__ bool help_once(const KernelArgs& a, int smem, const int* gidx, HelpBoard* hb, int lane) {
   const int owner = *(volatile int*)&hb->owner;
   const int nx = *(volatile int*)&hb->next;
   if (owner < 0 || nx >= *(volatile int*)&hb->n || nx >= kHelpClosed) return false;
@@ -2177,7 +2185,6 @@ __device__ __noinline__ bool help_once(const KernelArgs& a, double* smem, const 
 // for each other; they only nap when every live context is being run by another warp.
 constexpr int ST_BUSY = 6;
 __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) double smem_cta[];
   __shared__ int s_state[kMaxCtx];
   __shared__ int s_iter[kMaxCtx];  // iterations run so far by the scenario in each context (claim priority)
   __shared__ HelpBoard s_help;
@@ -2188,7 +2195,7 @@ __global__ void __launch_bounds__(32 * kCtaWarps, 1) cilqr_solve_kernel(const __
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int C = a.ctx_per_cta;
-  double* smem = smem_cta + (size_t)warp * (a.sm.total_bytes / 8);
+  const int smem = warp * (a.sm.total_bytes / 8);  // this warp's stage, as an offset into smem_cta
   if (a.resume) {
     // a later launch of the drain relay: adopt up to resume_per_cta contexts that the previous launch left
     // unfinished, wherever in the workspace they live; they resume at the phase they were waiting for

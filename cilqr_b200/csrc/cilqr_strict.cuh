@@ -69,9 +69,9 @@ __device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const uns
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N, lane = c.lane;
-  const double* seg = c.sm + a.sm.seg;
-  double* trig = c.sm + a.sm.trig;  // [K][2] sin, cos
-  double* buf = c.sm + a.sm.pl_e;
+  const double* seg = c.smp() + a.sm.seg;
+  double* trig = c.smp() + a.sm.trig;  // [K][2] sin, cos
+  double* buf = c.smp() + a.sm.pl_e;
   const int bw = strict_row_width(a.M_max);
   // ---- JCost (:497-516) state terms and the state half of DynamicsCost (:518-538); sin / cos of the heading
   double acc_j = 0.0, acc_x = 0.0;
@@ -299,7 +299,7 @@ __device__ __noinline__ void linearize_window(const Ctx& c, int k0, const double
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
-  double* lin = c.sm + a.sm.lin;
+  double* lin = c.smp() + a.sm.lin;
   double* R = c.linrec();
   const int k = k0 + lane;
   const int nk = K - k0 < kWin ? K - k0 : kWin;
@@ -365,7 +365,7 @@ __device__ __forceinline__ void s_expand(const double* rec, double* A, double* B
 __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double dV[2]) {
   const KernelArgs& a = c.a;
   const int N = a.N, lane = c.lane;
-  double* w = c.sm + a.sm.scr;
+  double* w = c.smp() + a.sm.scr;
   const double* R = c.linrec();
   double* gains = c.gains();
   double *A = w, *B = A + 36, *Jx = B + 12, *Ju = Jx + 6, *Hx = Ju + 2, *Hu = Hx + 36;             // 96
@@ -456,7 +456,7 @@ __device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double d
 __device__ __noinline__ void s_iqr_sweep(const Ctx& c) {
   const KernelArgs& a = c.a;
   const int N = a.N, lane = c.lane;
-  double* w = c.sm + a.sm.scr;
+  double* w = c.smp() + a.sm.scr;
   const double* R = c.linrec();
   double* gains = c.gains();
   double *A = w, *B = A + 36, *Jx = B + 12, *Ju = Jx + 6, *Hx = Ju + 2, *Hu = Hx + 36;
