@@ -559,8 +559,9 @@ __device__ __forceinline__ int nearest_segment(const double* sg0, const double* 
 // fills 505 of 512 lane slots at K = 101 instead of 101 of 128).  Also records the nearest lane
 // segment of every (knot, disc, side) in nidx for the linearisation that follows an accepted step.
 // The lane segments / group circles must have been staged in shared memory (stage_segments).
-__device__ __noinline__ void eval_cost(const Ctx& c, const double* Xs, const unsigned char* guess,
+__device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const unsigned char* guess,
                                        unsigned char* nidx, double cost5[5]) {
+  const Ctx c = c_ref;  // a private copy (registers): the caller's Ctx lives in local memory and every char store below could alias it
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
   const int K = a.N + 1, N = a.N;
@@ -922,8 +923,9 @@ static_assert(SKH + 14 <= kScratch, "scratch overflow");
 // memory), and flush the records to the context, where the Riccati sweep of the BACK phase streams
 // them from.  (One phase for both was 57 KB of code -- more than the ~32 KB an SM's instruction cache
 // feeds to unaligned warps -- and spilled at 128 registers.)
-__device__ __noinline__ void linearize_window(const Ctx& c, int k0, const double* Xs, const unsigned char* nidx,
+__device__ __noinline__ void linearize_window(const Ctx& c_ref, int k0, const double* Xs, const unsigned char* nidx,
                                               const DebugPtrs* dbg, int b) {
+  const Ctx c = c_ref;  // a private copy (registers): the caller's Ctx lives in local memory and every char store below could alias it
   const KernelArgs& a = c.a;
   const int N = a.N, K = N + 1;
   const int lane = c.lane;
@@ -962,7 +964,8 @@ __device__ __forceinline__ void linearize_all(const Ctx& c, const double* Xs, co
   for (int k0 = 0; k0 <= c.a.N; k0 += kWin) linearize_window(c, k0, Xs, nidx, dbg, b);
 }
 
-__device__ __noinline__ void backward_pass(const Ctx& c, double lambda, double dV[2]) {
+__device__ __noinline__ void backward_pass(const Ctx& c_ref, double lambda, double dV[2]) {
+  const Ctx c = c_ref;  // a private copy (registers): the caller's Ctx lives in local memory and every char store below could alias it
   const KernelArgs& a = c.a;
   const int N = a.N;
   const int lane = c.lane;
@@ -1203,7 +1206,8 @@ __device__ void iqr_records(const Ctx& c, double* Xs) {
 __device__ __forceinline__ unsigned fnv1a(unsigned h, unsigned byte) { return (h ^ (byte & 0xffu)) * 16777619u; }
 
 // trajectory slot ([8][Kc], component-major) -> states [K][6] and controls [N][2] (knot-major)
-__device__ __noinline__ void copy_traj(const Ctx& c, const double* Xs, double* states, double* controls) {
+__device__ __noinline__ void copy_traj(const Ctx& c_ref, const double* Xs, double* states, double* controls) {
+  const Ctx c = c_ref;  // a private copy (registers): the caller's Ctx lives in local memory and every char store below could alias it
   const int N = c.a.N, Kc = c.a.Kc;
 #pragma unroll 1
   for (int k = c.lane; k <= N; k += 32) {

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum \
+    --clock-control none --import-source on -k regex:cilqr_solve -c 1 -f -o gpurun_out/r2p_prof \
+    python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-corridor --no-dp --no-latency > gpurun_out/r2p_bench_ncu_full.json 2> gpurun_out/r2p_err.log
+tail -2 gpurun_out/r2p_err.log; ls -la gpurun_out/r2p_prof.ncu-rep
