@@ -52,9 +52,13 @@
 #include "pm_math.h"
 #define CILQR_FMA(a, b, c) ((a) * (b) + (c))
 #define CILQR_DIVL(P, x) ((x) / (P).L)
+#define CILQR_LQ(P) ((P).L)          // the wheel-base operand as a value ...
+#define CILQR_DIVQ(q, x) ((x) / (q))  // ... and the division by it
 #else
 #define CILQR_FMA(a, b, c) fma((a), (b), (c))
 #define CILQR_DIVL(P, x) ((x) * (P).inv_L)
+#define CILQR_LQ(P) ((P).inv_L)
+#define CILQR_DIVQ(q, x) ((x) * (q))
 #endif
 
 namespace cilqr {
@@ -312,24 +316,25 @@ __device__ __forceinline__ double normalize_angle(double angle) {
 // Division by the wheel base is a multiplication by its reciprocal (bit-identical for the
 // reference's L_w = 1.0, vehicle_param.h:30; <= 1 ulp otherwise).
 // (theta enters k1 only through k1x, k1y, which the midpoint step never uses.)
-__device__ __forceinline__ void rollout_step(const DevParams& P, double* x, double u0, double u1, bool allow_general,
+// dt and lq = CILQR_LQ(P) are values the caller loaded once (see bar_add).
+__device__ __forceinline__ void rollout_step(double dt, double lq, double* x, double u0, double u1, bool allow_general,
                                              bool& slow) {
-  const double h = 0.5 * P.dt;
+  const double h = 0.5 * dt;
   const double m5 = x[5] + h * u1;
   const double de = wrap_angle(x[5], allow_general, slow);
   const double dem = wrap_angle(m5, allow_general, slow);
   const double2 tt = nt_tan2(de, dem);
-  const double k1t = CILQR_DIVL(P, x[3] * tt.x);
+  const double k1t = CILQR_DIVQ(lq, x[3] * tt.x);
   const double m2 = x[2] + h * k1t, m3 = x[3] + h * x[4], m4 = x[4] + h * u0;
   const double thm = wrap_angle(m2, allow_general, slow);
   const double2 sc = nt_sincos(thm);
-  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = CILQR_DIVL(P, m3 * tt.y);
-  x[0] = x[0] + P.dt * k2x;
-  x[1] = x[1] + P.dt * k2y;
-  x[2] = wrap_angle(x[2] + P.dt * k2t, allow_general, slow);
-  x[3] = x[3] + P.dt * m4;
-  x[4] = x[4] + P.dt * u0;
-  x[5] = wrap_angle(x[5] + P.dt * u1, allow_general, slow);
+  const double k2x = m3 * sc.y, k2y = m3 * sc.x, k2t = CILQR_DIVQ(lq, m3 * tt.y);
+  x[0] = x[0] + dt * k2x;
+  x[1] = x[1] + dt * k2y;
+  x[2] = wrap_angle(x[2] + dt * k2t, allow_general, slow);
+  x[3] = x[3] + dt * m4;
+  x[4] = x[4] + dt * u0;
+  x[5] = wrap_angle(x[5] + dt * u1, allow_general, slow);
 }
 
 // vehicle_model.cc:21-86.  Writes the 11 state-dependent entries of A and B(2,1).
@@ -371,12 +376,15 @@ __device__ __noinline__ double bar_quad(double g, const DevParams& P) {
   const double q = (-g - 2.0 * P.eps) * P.inv_eps;
   return fma(0.5 * P.rt * q, q, P.relax_c);
 }
-__device__ __forceinline__ void bar_add(BarAcc& a, double g, const DevParams& P) {
-  if (g < -P.eps) a.prod *= -g;
+// eps / rt are passed as VALUES the caller loaded once: a member of `const DevParams&` is re-read from the parameter block
+// (a generic load, two R2UR and a long-scoreboard wait) after every store or call the compiler cannot disambiguate
+// from it -- once per half-plane in the loops below (profiles/r02_q_ncu_summary.txt, line 375 of that revision).
+__device__ __forceinline__ void bar_add(BarAcc& a, double g, double eps, const DevParams& P) {
+  if (g < -eps) a.prod *= -g;
   else a.quad += bar_quad(g, P);
 }
-__device__ __forceinline__ double bar_value(const BarAcc& a, const DevParams& P) {
-  return a.quad - P.rt * nt_log(a.prod);
+__device__ __forceinline__ double bar_value(const BarAcc& a, double rt) {
+  return a.quad - rt * nt_log(a.prod);
 }
 // 1 / g for a normal, non-zero g (here g < -eps): hardware seed + three Newton steps.  Not correctly
 // rounded like the IEEE division (<= 1 ulp off), a third of its instructions, no slow-path call.
@@ -392,16 +400,16 @@ __device__ __forceinline__ double fast_rcp(double g) {
   return r;
 }
 // barrier_function.h:115-140: coefficient of dx in the Jacobian (cj), of dx dx^T (co) and of ddx (cd)
-__device__ __forceinline__ void bar_coef(double g, const DevParams& P, double& cj, double& co,
+__device__ __forceinline__ void bar_coef(double g, double eps, double rt, const DevParams& P, double& cj, double& co,
                                          double& cd) {
-  if (g < -P.eps) {
+  if (g < -eps) {
     const double inv = fast_rcp(g);
-    const double q = P.rt * inv;
+    const double q = rt * inv;
     cj = -q;
     co = q * inv;
     cd = q;
   } else {
-    cj = P.rt * (g + 2.0 * P.eps) * P.inv_eps2;
+    cj = rt * (g + 2.0 * eps) * P.inv_eps2;
     co = cj;
     cd = 0.0;
   }
@@ -474,14 +482,15 @@ __device__ __forceinline__ int cand_slot(int cur, int ai) {
 // shared tile buf[(m * 3 + comp) * kPlaneKnots + knot - k_lo] by cp.async, one commit group.  The
 // consumer overlaps the copy of the next tile with the arithmetic of the current one, so the inner
 // loops never wait on L2 / HBM.
-__device__ __forceinline__ void stage_planes(const Ctx& c, double* buf, int k_lo, int nk, int Mrows) {
+// (planes = c.planes() and Kc as values: the callers load them once, not once per tile)
+__device__ __forceinline__ void stage_planes(const double* planes, int Kc, int lane, double* buf, int k_lo, int nk, int Mrows) {
   static_assert(32 % kPlaneKnots == 0, "a lane keeps its knot column");
   constexpr int kRowsPerIter = 32 / kPlaneKnots;
-  const int kk = c.lane % kPlaneKnots, r0 = c.lane / kPlaneKnots;
+  const int kk = lane % kPlaneKnots, r0 = lane / kPlaneKnots;
   if (kk < nk) {
-    const double* src = c.planes() + k_lo + kk + (size_t)r0 * c.a.Kc;
-    unsigned dst = (unsigned)__cvta_generic_to_shared(buf + c.lane);
-    const size_t sstep = (size_t)kRowsPerIter * c.a.Kc;
+    const double* src = planes + k_lo + kk + (size_t)r0 * Kc;
+    unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
+    const size_t sstep = (size_t)kRowsPerIter * Kc;
     for (int row = r0; row < Mrows * 3; row += kRowsPerIter) {
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
       src += sstep;
@@ -564,54 +573,57 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
   const Ctx c = c_ref;  // a private copy (registers): the caller's Ctx lives in local memory and every char store below could alias it
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
-  const int K = a.N + 1, N = a.N;
+  const int K = a.N + 1, N = a.N, Kc = a.Kc, S_left = a.S_left, S_right = a.S_right;
+  const double eps = P.eps, rt = P.rt;  // loaded once (see bar_add)
   const double* seg = c.smp() + a.sm.seg;
   double* trig = c.smp() + a.sm.trig;  // [K][2] sin, cos
   double sum_j = 0.0, sum_d = 0.0, sum_c = 0.0, sum_l = 0.0;
 #pragma unroll 1
   for (int k = c.lane; k < K; k += 32) {
     const double* xc = Xs + k;
-    const double px = xc[0], py = xc[a.Kc], th = xc[2 * a.Kc], v = xc[3 * a.Kc], ac = xc[4 * a.Kc], de = xc[5 * a.Kc];
+    const double px = xc[0], py = xc[Kc], th = xc[2 * Kc], v = xc[3 * Kc], ac = xc[4 * Kc], de = xc[5 * Kc];
     const double dx = px - c.goal(k, 0), dy = py - c.goal(k, 1), dth = th - c.goal(k, 2);
     double tj = P.wx * (dx * dx) + P.wy * (dy * dy) + P.wth * (dth * dth);
     BarAcc bd = {1.0, 0.0};
-    bar_add(bd, -v, P);
-    bar_add(bd, v - P.vmax, P);
-    bar_add(bd, ac - P.amax, P);
-    bar_add(bd, P.amin - ac, P);
-    bar_add(bd, de - P.dmax, P);
-    bar_add(bd, P.dmin - de, P);
+    bar_add(bd, -v, eps, P);
+    bar_add(bd, v - P.vmax, eps, P);
+    bar_add(bd, ac - P.amax, eps, P);
+    bar_add(bd, P.amin - ac, eps, P);
+    bar_add(bd, de - P.dmax, eps, P);
+    bar_add(bd, P.dmin - de, eps, P);
     if (k < N) {
-      const double u0 = Xs[6 * a.Kc + k], u1 = Xs[7 * a.Kc + k];
+      const double u0 = Xs[6 * Kc + k], u1 = Xs[7 * Kc + k];
       tj += P.wj * (u0 * u0) + P.wdr * (u1 * u1);
-      bar_add(bd, u0 - P.jmax, P);
-      bar_add(bd, P.jmin - u0, P);
-      bar_add(bd, u1 - P.drmax, P);
-      bar_add(bd, P.drmin - u1, P);
+      bar_add(bd, u0 - P.jmax, eps, P);
+      bar_add(bd, P.jmin - u0, eps, P);
+      bar_add(bd, u1 - P.drmax, eps, P);
+      bar_add(bd, P.drmin - u1, eps, P);
     }
     sum_j += tj;
-    sum_d += bar_value(bd, P);
+    sum_d += bar_value(bd, rt);
     const double2 scth = nt_sincos(th);
     trig[k * 2] = scth.x;
     trig[k * 2 + 1] = scth.y;
   }
   __syncwarp();
   const int items = K * kDisc;
-  const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
+  const int ngl = (S_left + kGroup - 1) / kGroup, ngr = (S_right + kGroup - 1) / kGroup;
   const double* grp = c.smp() + a.sm.grp;
   const double* cert = grp + (ngl + ngr) * 3;  // [S_left + S_right] certificate radii, behind the group circles
   double* pbuf = c.smp() + a.sm.pl_e;
   const int pstride = a.M_max * kPlaneTile;
+  const double* planes_g = c.planes();
+  const int32_t* cnt = c.cnt;
   // tile of chunk j0: knots j0/5 .. (j0+31)/5 (at most kPlaneKnots), planes below the chunk's largest count
   auto chunk_M = [&](int j0) {
     const int j = j0 + c.lane;
-    return j < items ? c.cnt[j / kDisc] : 0;
+    return j < items ? cnt[j / kDisc] : 0;
   };
   auto chunk_stage = [&](int j0, int Mw, int s) {
     const int k_lo = j0 / kDisc;
     int k_hi = (j0 + 31) / kDisc;
     k_hi = k_hi < K ? k_hi : K - 1;
-    stage_planes(c, pbuf + s * pstride, k_lo, k_hi - k_lo + 1, Mw);
+    stage_planes(planes_g, Kc, c.lane, pbuf + s * pstride, k_lo, k_hi - k_lo + 1, Mw);
   };
   int M = chunk_M(0);
   int Mw = __reduce_max_sync(kFull, M);
@@ -622,7 +634,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
     const int j = j0 + c.lane;
     return (j < items ? j : items - 1) / kDisc;
   };
-  double px_n = Xs[item_knot(0)], py_n = Xs[a.Kc + item_knot(0)];
+  double px_n = Xs[item_knot(0)], py_n = Xs[Kc + item_knot(0)];
 #pragma unroll 1
   for (int j0 = 0; j0 < items; j0 += 32, stage ^= 1) {
     int M_next = 0, Mw_next = 0;
@@ -648,7 +660,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
     if (j0 + 32 < items) {
       const int kn = item_knot(j0 + 32);
       px_n = Xs[kn];
-      py_n = Xs[a.Kc + kn];
+      py_n = Xs[Kc + kn];
     }
     // corridor half-planes of this knot
     BarAcc bc = {1.0, 0.0}, bc2 = {1.0, 0.0};  // two running products: two independent multiply chains
@@ -657,12 +669,12 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
     for (int m = 0; m < Mw; m += 2) {
       if (m < M) {
         const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
-        bar_add(bc, fma(pb, yd, pa * xd) - pc, P);
+        bar_add(bc, fma(pb, yd, pa * xd) - pc, eps, P);
       }
       if (m + 1 < M) {
         const double* w1 = w + kPlaneTile;
         const double pa = w1[m * kPlaneTile], pb = w1[m * kPlaneTile + kPlaneKnots], pc = w1[m * kPlaneTile + 2 * kPlaneKnots];
-        bar_add(bc2, fma(pb, yd, pa * xd) - pc, P);
+        bar_add(bc2, fma(pb, yd, pa * xd) - pc, eps, P);
       }
     }
     bc.prod *= bc2.prod;
@@ -677,15 +689,15 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
     BarAcc bl = {1.0, 0.0};
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
-      const int S = side == 0 ? a.S_left : a.S_right;
-      const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
-      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, cert + (side == 0 ? 0 : a.S_left), S,
+      const int S = side == 0 ? S_left : S_right;
+      const double* sg0 = seg + (side == 0 ? 0 : S_left) * kSegStride;
+      const int bi = nearest_segment(sg0, grp + (side == 0 ? 0 : ngl) * 3, cert + (side == 0 ? 0 : S_left), S,
                                      side == 0 ? (g2 & 0xff) : (g2 >> 8), xd, yd);
       const double* sg = sg0 + bi * kSegStride;
-      bar_add(bl, fma(sg[8], yd, sg[7] * xd) - sg[9], P);
+      bar_add(bl, fma(sg[8], yd, sg[7] * xd) - sg[9], eps, P);
       if (act) nidx[jj * 2 + side] = (unsigned char)bi;
     }
-    const double tc = bar_value(bc, P), tl = bar_value(bl, P);
+    const double tc = bar_value(bc, rt), tl = bar_value(bl, rt);
     if (act) {
       sum_c += tc;
       sum_l += tl;
@@ -712,11 +724,11 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
 __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, double* rec) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
-  const int N = a.N;
+  const int N = a.N, Kc = a.Kc;
   double x[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k];
-  const double u0 = k < N ? Xs[6 * a.Kc + k] : 0.0, u1 = k < N ? Xs[7 * a.Kc + k] : 0.0;
+  for (int i = 0; i < 6; ++i) x[i] = Xs[i * Kc + k];
+  const double u0 = k < N ? Xs[6 * Kc + k] : 0.0, u1 = k < N ? Xs[7 * Kc + k] : 0.0;
   if (k < N) {
     double A11[11], b21;
     dynamics_jacobian(P, x, u1, A11, &b21);
@@ -724,46 +736,54 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, double* re
     for (int i = 0; i < 11; ++i) rec[LA + i] = A11[i];
     rec[LB21] = b21;
   }
+  // every parameter and goal is loaded HERE, in one batch (one load latency): below, each would be a generic load
+  // serialised behind the record stores that precede it
+  const double eps = P.eps, rt = P.rt, dt = P.dt;
+  const double vmax = P.vmax, amin = P.amin, amax = P.amax, dmin = P.dmin, dmax = P.dmax;
+  const double jmin = P.jmin, jmax = P.jmax, drmin = P.drmin, drmax = P.drmax;
+  const double wx2 = 2.0 * P.wx, wy2 = 2.0 * P.wy, wth2 = 2.0 * P.wth, wv2 = 2.0 * P.wv, wa2 = 2.0 * P.wa, wd2 = 2.0 * P.wd;
+  const double wj2 = 2.0 * P.wj, wdr2 = 2.0 * P.wdr;
+  const double gx = c.goal(k, 0), gy = c.goal(k, 1), gth = c.goal(k, 2);
   // DynamicsConsJacbian / Hessian: each state (control) component carries a pair of bounds
   auto bound_pair = [&](double lo_g, double hi_g, double& dj, double& dh) {
     double cj0, cj1, co0, co1, cd;
-    bar_coef(lo_g, P, cj0, co0, cd);
-    bar_coef(hi_g, P, cj1, co1, cd);
+    bar_coef(lo_g, eps, rt, P, cj0, co0, cd);
+    bar_coef(hi_g, eps, rt, P, cj1, co1, cd);
     dj = cj1 - cj0;
     dh = co0 + co1;
   };
   double dj, dh;
-  bound_pair(0.0 - x[3], x[3] - P.vmax, dj, dh);
+  bound_pair(0.0 - x[3], x[3] - vmax, dj, dh);
   rec[LJX + 3] = dj;
-  rec[LHX + 6] = 2.0 * P.wv + dh;
-  bound_pair(P.amin - x[4], x[4] - P.amax, dj, dh);
+  rec[LHX + 6] = wv2 + dh;
+  bound_pair(amin - x[4], x[4] - amax, dj, dh);
   rec[LJX + 4] = dj;
-  rec[LHX + 7] = 2.0 * P.wa + dh;
-  bound_pair(P.dmin - x[5], x[5] - P.dmax, dj, dh);
+  rec[LHX + 7] = wa2 + dh;
+  bound_pair(dmin - x[5], x[5] - dmax, dj, dh);
   rec[LJX + 5] = dj;
-  rec[LHX + 8] = 2.0 * P.wd + dh;
-  bound_pair(P.jmin - u0, u0 - P.jmax, dj, dh);
-  rec[LJU + 0] = 2.0 * P.wj * u0 + dj;
-  rec[LHU + 0] = 2.0 * P.wj + dh;
-  bound_pair(P.drmin - u1, u1 - P.drmax, dj, dh);
-  rec[LJU + 1] = 2.0 * P.wdr * u1 + dj;
-  rec[LHU + 1] = 2.0 * P.wdr + dh;
+  rec[LHX + 8] = wd2 + dh;
+  bound_pair(jmin - u0, u0 - jmax, dj, dh);
+  rec[LJU + 0] = wj2 * u0 + dj;
+  rec[LHU + 0] = wj2 + dh;
+  bound_pair(drmin - u1, u1 - drmax, dj, dh);
+  rec[LJU + 1] = wdr2 * u1 + dj;
+  rec[LHU + 1] = wdr2 + dh;
   const double2 scth = nt_sincos(x[2]);
   rec[LSN] = scth.x;
   rec[LCS] = scth.y;
   rec[LZ] = 0.0;
   rec[LO] = 1.0;
-  rec[LDT] = P.dt;
-  rec[LB30] = 0.5 * P.dt * P.dt;
-  rec[LJX + 0] = 2.0 * P.wx * (x[0] - c.goal(k, 0));
-  rec[LJX + 1] = 2.0 * P.wy * (x[1] - c.goal(k, 1));
-  rec[LJX + 2] = 2.0 * P.wth * (x[2] - c.goal(k, 2));
-  rec[LHX + 0] = 2.0 * P.wx;
+  rec[LDT] = dt;
+  rec[LB30] = 0.5 * dt * dt;
+  rec[LJX + 0] = wx2 * (x[0] - gx);
+  rec[LJX + 1] = wy2 * (x[1] - gy);
+  rec[LJX + 2] = wth2 * (x[2] - gth);
+  rec[LHX + 0] = wx2;
   rec[LHX + 1] = 0.0;
   rec[LHX + 2] = 0.0;
-  rec[LHX + 3] = 2.0 * P.wy;
+  rec[LHX + 3] = wy2;
   rec[LHX + 4] = 0.0;
-  rec[LHX + 5] = 2.0 * P.wth;
+  rec[LHX + 5] = wth2;
 }
 
 constexpr int kKnotsPerPass = 6;  // 6 knots x 5 discs = 30 lanes per pass of linearize_discs
@@ -777,12 +797,19 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
   const DevParams& P = a.P;
   const double* seg = c.gseg();  // only (a, b, c) of ten segments per knot: read from the context
   double* pbuf = c.smp() + a.sm.pl_b;
+  double* rb = c.smp() + a.sm.red;  // [9][32]
   const int pstride = a.M_max * kPlaneTile;
   const int d = c.lane / kKnotsPerPass, kl = c.lane - d * kKnotsPerPass;
-  auto pass_M = [&](int g0) { return (d < kDisc && g0 + kl < nk) ? c.cnt[k0 + g0 + kl] : 0; };
+  // launch constants as values, loaded once (see bar_add)
+  const int Kc = a.Kc, S_left = a.S_left;
+  const double eps = P.eps, rt = P.rt;
+  const double o = P.off[d < kDisc ? d : 0];
+  const double* planes_g = c.planes();
+  const int32_t* cnt = c.cnt;
+  auto pass_M = [&](int g0) { return (d < kDisc && g0 + kl < nk) ? cnt[k0 + g0 + kl] : 0; };
   auto pass_stage = [&](int g0, int Mw, int s) {
     const int n = nk - g0 < kKnotsPerPass ? nk - g0 : kKnotsPerPass;
-    stage_planes(c, pbuf + s * pstride, k0 + g0, n, Mw);
+    stage_planes(planes_g, Kc, c.lane, pbuf + s * pstride, k0 + g0, n, Mw);
   };
   int M = pass_M(0);
   int Mw = __reduce_max_sync(kFull, M);
@@ -806,13 +833,12 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     const int k = k0 + ko;
     double* rec = lin + ko * kLinStride;
     const double sn = rec[LSN], cs = rec[LCS];
-    const double o = P.off[act ? d : 0];
-    const double xd = fma(o, cs, Xs[k]), yd = fma(o, sn, Xs[a.Kc + k]);
+    const double xd = fma(o, cs, Xs[k]), yd = fma(o, sn, Xs[Kc + k]);
     double J0 = 0.0, J1 = 0.0, J2 = 0.0, H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
     auto plane = [&](double pa, double pb, double pc) {
       const double g = fma(pb, yd, pa * xd) - pc;
       double cj, co, cdd;
-      bar_coef(g, P, cj, co, cdd);
+      bar_coef(g, eps, rt, P, cj, co, cdd);
       const double to = (pb * cs - pa * sn) * o;
       const double wo = (pa * cs + pb * sn) * o;
       const double ca = pa * co, cb = pb * co;
@@ -841,13 +867,12 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     if (act) {
 #pragma unroll 1
       for (int side = 0; side < 2; ++side) {
-        const double* sg = seg + ((side == 0 ? 0 : a.S_left) + nidx[(k * kDisc + d) * 2 + side]) * kSegStride;
+        const double* sg = seg + ((side == 0 ? 0 : S_left) + nidx[(k * kDisc + d) * 2 + side]) * kSegStride;
         plane(sg[7], sg[8], sg[9]);
       }
     }
     // sum over the five disc lanes of each knot through shared memory, in the fixed order
     // ((d0 + d3) + (d1 + d4)) + d2
-    double* rb = c.smp() + a.sm.red;  // [9][32]
     rb[0 * 32 + c.lane] = J0;
     rb[1 * 32 + c.lane] = J1;
     rb[2 * 32 + c.lane] = J2;
@@ -1610,9 +1635,12 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
   const bool owner = valid && wanted;
   const int ca = wanted ? ai : 31 - __clz(want);
   const double alpha = kAlphaList[gb + ca];
-  const double* Xs = cx + a.cl.slots + cur * 8 * a.Kc;
+  // launch constants as values, loaded once (see bar_add): below they would be re-read after every store to `out`
+  const int N = a.N, Kc = a.Kc;
+  const double dt = P.dt, lq = CILQR_LQ(P), jmin = P.jmin, jmax = P.jmax, drmin = P.drmin, drmax = P.drmax;
+  const double* Xs = cx + a.cl.slots + cur * 8 * Kc;
   const double* gains = cx + a.cl.gains;
-  double* out = cx + a.cl.slots + cand_slot(cur, ca) * 8 * a.Kc;
+  double* out = cx + a.cl.slots + cand_slot(cur, ca) * 8 * Kc;
   double* ring = sm + g * kRingDoubles;
   constexpr int kStage = 8 * kRollChunk + kGainStride * kRollChunk;  // doubles per ring stage
   double x[6];
@@ -1620,7 +1648,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
   for (int i = 0; i < 6; ++i) x[i] = h->g0[i];
   if (owner) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) out[i * a.Kc] = x[i];
+    for (int i = 0; i < 6; ++i) out[i * Kc] = x[i];
   }
   // stage s of a group's ring: [8][kRollChunk] nominal x0..x5,u0,u1 then [kRollChunk][16] gain records;
   // 16 + 32 sixteen-byte pieces per chunk, twelve per lane of the group
@@ -1630,7 +1658,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
     for (int p = ai; p < 4 * kRollChunk + kGainStride * kRollChunk / 2; p += 4) {
       if (p < 4 * kRollChunk) {
         const int comp = p / (kRollChunk / 2), part = p - comp * (kRollChunk / 2);
-        cp_async16(st + comp * kRollChunk + part * 2, Xs + comp * a.Kc + k0 + part * 2);
+        cp_async16(st + comp * kRollChunk + part * 2, Xs + comp * Kc + k0 + part * 2);
       } else {
         const int q = p - 4 * kRollChunk;
         cp_async16(st + 8 * kRollChunk + q * 2, gains + (size_t)k0 * kGainStride + q * 2);
@@ -1641,8 +1669,8 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
   bool dead = false, defer = false, slow = false;
   prefetch(0, 0);
   int stage = 0;
-  for (int k0 = 0; k0 < a.N; k0 += kRollChunk, stage ^= 1) {
-    if (k0 + kRollChunk < a.N) {
+  for (int k0 = 0; k0 < N; k0 += kRollChunk, stage ^= 1) {
+    if (k0 + kRollChunk < N) {
       prefetch(k0 + kRollChunk, stage ^ 1);
       cp_async_wait<1>();
     } else {
@@ -1650,7 +1678,7 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
     }
     __syncwarp();
     const double* st = ring + stage * kStage;
-    const int kn = a.N - k0 < kRollChunk ? a.N - k0 : kRollChunk;
+    const int kn = N - k0 < kRollChunk ? N - k0 : kRollChunk;
     for (int kk = 0; kk < kn; ++kk) {
       const int k = k0 + kk;
       const double* Kk = st + 8 * kRollChunk + kk * kGainStride;
@@ -1666,14 +1694,14 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
       double u0 = st[6 * kRollChunk + kk] + s0 + alpha * Kk[12];
       double u1 = st[7 * kRollChunk + kk] + s1 + alpha * Kk[13];
       if (clamp_u) {
-        u0 = fmin(P.jmax, fmax(u0, P.jmin));     // clamp, ilqr_optimizer.cc:826-836
-        u1 = fmin(P.drmax, fmax(u1, P.drmin));
+        u0 = fmin(jmax, fmax(u0, jmin));     // clamp, ilqr_optimizer.cc:826-836
+        u1 = fmin(drmax, fmax(u1, drmin));
       } else if (iqr) {
         // open loop: the caller's controls as they are
       } else {
         u1 = wrap_angle(u1, allow_general, slow);  // ilqr_optimizer.cc:408
       }
-      rollout_step(P, x, u0, u1, allow_general, slow);
+      rollout_step(dt, lq, x, u0, u1, allow_general, slow);
       if (!iqr && !dead && !defer) {
         const double chk = ((x[0] + x[1]) + (x[2] + x[3])) + (x[4] + x[5]);
         if (slow) defer = true;  // this step was not computed faithfully: the whole rollout is repeated later
@@ -1682,13 +1710,13 @@ __device__ __noinline__ void roll_multi(const KernelArgs& a, int sm_off, const i
       if (dead || defer) {
         // park the lane on the nominal trajectory: benign operands for the remaining steps
 #pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = Xs[i * a.Kc + k + 1];
+        for (int i = 0; i < 6; ++i) x[i] = Xs[i * Kc + k + 1];
         slow = false;
       } else if (owner) {
-        out[6 * a.Kc + k] = u0;
-        out[7 * a.Kc + k] = u1;
+        out[6 * Kc + k] = u0;
+        out[7 * Kc + k] = u1;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) out[i * a.Kc + k + 1] = x[i];
+        for (int i = 0; i < 6; ++i) out[i * Kc + k + 1] = x[i];
       }
     }
     __syncwarp();
