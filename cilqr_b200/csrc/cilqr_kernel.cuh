@@ -415,6 +415,23 @@ __device__ __forceinline__ void bar_coef(double g, double eps, double rt, const 
   }
 }
 
+// the same coefficients with the Jacobian's negated (mj = -cj): in the log branch mj = cd = rt / g needs no sign flip (an
+// FP64 negation is a DADD), and the accumulation uses the free operand negation of the multiply-add
+__device__ __forceinline__ void bar_coef_neg(double g, double eps, double rt, const DevParams& P, double& mj, double& co,
+                                             double& cd) {
+  if (g < -eps) {
+    const double inv = fast_rcp(g);
+    const double q = rt * inv;
+    mj = q;
+    co = q * inv;
+    cd = q;
+  } else {
+    co = rt * (g + 2.0 * eps) * P.inv_eps2;
+    mj = -co;
+    cd = 0.0;
+  }
+}
+
 // squared distance point -> segment with the case split of line_segment2d.cpp:61-75
 __device__ __forceinline__ double seg_dist2(const double* sg, double px, double py) {
   const double x0 = px - sg[0], y0 = py - sg[1];
@@ -834,24 +851,26 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     double* rec = lin + ko * kLinStride;
     const double sn = rec[LSN], cs = rec[LCS];
     const double xd = fma(o, cs, Xs[k]), yd = fma(o, sn, Xs[Kc + k]);
-    double J0 = 0.0, J1 = 0.0, J2 = 0.0, H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
+    // Per half-plane only the sums over its normal (a, b) are accumulated; the heading components follow once per
+    // disc, after the loops.  With t = off (b cos - a sin) and w = off (a cos + b sin), tc = off cos, ts = off sin:
+    //   J2  = sum cj t   = tc J1 - ts J0
+    //   H02 = sum co a t = tc H01 - ts H00        H12 = sum co b t = tc H11 - ts H01
+    //   H22 = sum co t^2 + sum cd w = (tc H12 - ts H02) + (tc D0 + ts D1),   D = sum cd (a, b)
+    // -- the sums of CorridorConsJacbian / Hessian (:690-727) re-associated: 9 multiply-adds per half-plane instead of 21
+    // (the LIN epoch of a CTA is bound by the FP64 pipe: all sixteen warps run this loop at the same time).
+    double J0 = 0.0, J1 = 0.0, H00 = 0.0, H01 = 0.0, H11 = 0.0, D0 = 0.0, D1 = 0.0;
     auto plane = [&](double pa, double pb, double pc) {
       const double g = fma(pb, yd, pa * xd) - pc;
-      double cj, co, cdd;
-      bar_coef(g, eps, rt, P, cj, co, cdd);
-      const double to = (pb * cs - pa * sn) * o;
-      const double wo = (pa * cs + pb * sn) * o;
+      double mj, co, cdd;
+      bar_coef_neg(g, eps, rt, P, mj, co, cdd);
       const double ca = pa * co, cb = pb * co;
-      J0 = fma(pa, cj, J0);
-      J1 = fma(pb, cj, J1);
-      J2 = fma(to, cj, J2);
+      J0 = fma(-pa, mj, J0);
+      J1 = fma(-pb, mj, J1);
       H00 = fma(pa, ca, H00);
       H01 = fma(pa, cb, H01);
       H11 = fma(pb, cb, H11);
-      H02 = fma(to, ca, H02);
-      H12 = fma(to, cb, H12);
-      H22 = fma(to, to * co, H22);
-      H22 = fma(wo, cdd, H22);
+      D0 = fma(pa, cdd, D0);
+      D1 = fma(pb, cdd, D1);
     };
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (act ? kl : 0);
 #pragma unroll 2
@@ -871,6 +890,10 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
         plane(sg[7], sg[8], sg[9]);
       }
     }
+    const double tc = o * cs, ts = o * sn;
+    const double J2 = tc * J1 - ts * J0;
+    const double H02 = tc * H01 - ts * H00, H12 = tc * H11 - ts * H01;
+    const double H22 = (tc * H12 - ts * H02) + (tc * D0 + ts * D1);
     // sum over the five disc lanes of each knot through shared memory, in the fixed order
     // ((d0 + d3) + (d1 + d4)) + d2
     rb[0 * 32 + c.lane] = J0;
@@ -1180,15 +1203,16 @@ __device__ __noinline__ void backward_pass(const Ctx& c_ref, double lambda, doub
 __device__ void iqr_records(const Ctx& c, double* Xs) {
   const KernelArgs& a = c.a;
   const DevParams& P = a.P;
-  const int N = a.N, lane = c.lane;
+  const int N = a.N, Kc = a.Kc, lane = c.lane;
+  const double dt = P.dt;
   double* R = c.linrec();
   const double Qd[6] = {0.001, 0.001, 0.001, 0.001, 0.01, 0.005};
   for (int k = lane; k <= N; k += 32) {
     double* rec = R + (size_t)k * kRecStride;
-    if (k < N) {
-      double g[6];
+    double g[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) g[i] = c.goal(k, i);
+    for (int i = 0; i < 6; ++i) g[i] = c.goal(k, i);
+    if (k < N) {
       double A11[11], b21;
       dynamics_jacobian(P, g, 0.0, A11, &b21);
 #pragma unroll
@@ -1217,13 +1241,13 @@ __device__ void iqr_records(const Ctx& c, double* Xs) {
 #endif
     rec[LZ] = 0.0;
     rec[LO] = 1.0;
-    rec[LDT] = P.dt;
-    rec[LB30] = 0.5 * P.dt * P.dt;
+    rec[LDT] = dt;
+    rec[LB30] = 0.5 * dt * dt;
     // (xbar, ubar) = (goals, 0)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) Xs[i * a.Kc + k] = c.goal(k, i);
-    Xs[6 * a.Kc + k] = 0.0;
-    Xs[7 * a.Kc + k] = 0.0;
+    for (int i = 0; i < 6; ++i) Xs[i * Kc + k] = g[i];
+    Xs[6 * Kc + k] = 0.0;
+    Xs[7 * Kc + k] = 0.0;
   }
   __syncwarp();
 }
@@ -1432,38 +1456,45 @@ __device__ __noinline__ int phase_init(Ctx& c) {
   }
   __syncwarp();
   {
-    const double* raw = a.corridor + (size_t)b * K * a.M_max * 3;
+    // launch constants as values, loaded once (see bar_add)
+    const int M_max = a.M_max, Kc = a.Kc, S_left = a.S_left, S_right = a.S_right;
+    const double shrink_corr = P.shrink_corr, shrink_lane = P.shrink_lane;
+    const int32_t* cnt = c.cnt;
+    double* dbg_corridor = dbg ? dbg->corridor : nullptr;
+    double* dbg_lanes = dbg ? dbg->lanes : nullptr;
+    const double* raw = a.corridor + (size_t)b * K * M_max * 3;
     double* planes = c.planes();
-    const int total = K * a.M_max;
+    const int total = K * M_max;
 #pragma unroll 1
     for (int idx = lane; idx < total; idx += 32) {
-      const int k = idx / a.M_max, m = idx - k * a.M_max;
-      if (m < c.cnt[k]) {
+      const int k = idx / M_max, m = idx - k * M_max;
+      if (m < cnt[k]) {
         const double e0 = raw[idx * 3], e1 = raw[idx * 3 + 1];
         double e2 = raw[idx * 3 + 2];
-        e2 = e2 - P.shrink_corr * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+        e2 = e2 - shrink_corr * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
         const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
-        planes[(m * 3 + 0) * a.Kc + k] = e0 / nrm;
-        planes[(m * 3 + 1) * a.Kc + k] = e1 / nrm;
-        planes[(m * 3 + 2) * a.Kc + k] = e2 / nrm;
-        if (dbg && dbg->corridor) {
-          double* o = dbg->corridor + ((size_t)b * total + idx) * 3;
+        planes[(m * 3 + 0) * Kc + k] = e0 / nrm;
+        planes[(m * 3 + 1) * Kc + k] = e1 / nrm;
+        planes[(m * 3 + 2) * Kc + k] = e2 / nrm;
+        if (dbg_corridor) {
+          double* o = dbg_corridor + ((size_t)b * total + idx) * 3;
           o[0] = e0 / nrm;
           o[1] = e1 / nrm;
           o[2] = e2 / nrm;
         }
       }
     }
-    const int ST_ = a.S_left + a.S_right;
+    const int ST_ = S_left + S_right;
     double* seg = c.smp() + a.sm.seg;
     double* gsg = c.gseg();
+    const double* lane_left = a.lane_left + (size_t)b * S_left * 7;
+    const double* lane_right = a.lane_right + (size_t)b * S_right * 7;
 #pragma unroll 1
     for (int s = lane; s < ST_; s += 32) {
-      const double* ln = s < a.S_left ? a.lane_left + ((size_t)b * a.S_left + s) * 7
-                                      : a.lane_right + ((size_t)b * a.S_right + (s - a.S_left)) * 7;
+      const double* ln = s < S_left ? lane_left + s * 7 : lane_right + (s - S_left) * 7;
       const double e0 = ln[0], e1 = ln[1];
       double e2 = ln[2];
-      e2 = e2 - P.shrink_lane * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
+      e2 = e2 - shrink_lane * (e0 * e0 + e1 * e1) / nt_hypot(e0, e1);
       const double nrm = nt_hypot(nt_hypot(e0, e1), e2);
       const double dx = ln[5] - ln[3], dy = ln[6] - ln[4];
       const double len = nt_hypot(dx, dy);
@@ -1483,8 +1514,8 @@ __device__ __noinline__ int phase_init(Ctx& c) {
         seg[s * kSegStride + q] = r[q];
         gsg[s * kSegStride + q] = r[q];
       }
-      if (dbg && dbg->lanes) {
-        double* o = dbg->lanes + ((size_t)b * ST_ + s) * 3;
+      if (dbg_lanes) {
+        double* o = dbg_lanes + ((size_t)b * ST_ + s) * 3;
         o[0] = r[7];
         o[1] = r[8];
         o[2] = r[9];
@@ -1492,15 +1523,15 @@ __device__ __noinline__ int phase_init(Ctx& c) {
     }
     __syncwarp();
     // bounding circles of the segment groups (see nearest_segment)
-    const int ngl = (a.S_left + kGroup - 1) / kGroup, ngr = (a.S_right + kGroup - 1) / kGroup;
+    const int ngl = (S_left + kGroup - 1) / kGroup, ngr = (S_right + kGroup - 1) / kGroup;
     double* grp = c.ggrp();
 #pragma unroll 1
     for (int g = lane; g < ngl + ngr; g += 32) {
       const int side = g < ngl ? 0 : 1;
-      const int S = side == 0 ? a.S_left : a.S_right;
+      const int S = side == 0 ? S_left : S_right;
       const int s_lo = (side == 0 ? g : g - ngl) * kGroup;
       const int s_hi = s_lo + kGroup < S ? s_lo + kGroup : S;
-      const double* sg0 = seg + (side == 0 ? 0 : a.S_left) * kSegStride;
+      const double* sg0 = seg + (side == 0 ? 0 : S_left) * kSegStride;
       double xmin = 1.7976931348623157e308, xmax = -xmin, ymin = xmin, ymax = -xmin;
 #pragma unroll 1
       for (int s2 = s_lo; s2 < s_hi; ++s2) {
@@ -1529,8 +1560,8 @@ __device__ __noinline__ int phase_init(Ctx& c) {
     double* cert = grp + (ngl + ngr) * 3;
 #pragma unroll 1
     for (int s = lane; s < ST_; s += 32) {
-      const int side = s < a.S_left ? 0 : 1;
-      const int s0 = side == 0 ? 0 : a.S_left, S = side == 0 ? a.S_left : a.S_right;
+      const int side = s < S_left ? 0 : 1;
+      const int s0 = side == 0 ? 0 : S_left, S = side == 0 ? S_left : S_right;
       const double* me = seg + s * kSegStride;
       const double mx = 0.5 * (me[0] + me[2]), my = 0.5 * (me[1] + me[3]);
       double D = 1.7976931348623157e308;
