@@ -81,6 +81,7 @@ constexpr int kLinStride = 40;    // strict: the lower triangle of Hx's 3x3 bloc
 constexpr int kLinStride = 37;    // doubles per knot in the linearisation window
 #endif
 constexpr int kSegStride = 10;    // sx sy ex ey ux uy len a b c
+static_assert(kSegStride % 2 == 0, "seg_dist2 reads a record with 16-byte loads");
 constexpr int kGainStride = 16;   // K (2x6), k (2), pad (2): one 128-byte record per knot
 constexpr int kRollChunk = 4;     // knots per cp.async stage of the rollout ring
 constexpr int kRecStride = 40;    // doubles per knot of the linearisation records in the context (16-byte pieces)
@@ -386,14 +387,13 @@ __device__ __forceinline__ void bar_add(BarAcc& a, double g, double eps, const D
 __device__ __forceinline__ double bar_value(const BarAcc& a, double rt) {
   return a.quad - rt * nt_log(a.prod);
 }
-// 1 / g for a normal, non-zero g (here g < -eps): hardware seed + three Newton steps.  Not correctly
-// rounded like the IEEE division (<= 1 ulp off), a third of its instructions, no slow-path call.
+// 1 / g for a normal, non-zero g (here g < -eps): hardware seed (relative error < 1e-6) + two Newton steps.  Measured on
+// B200 over 6.2e8 log-uniform operands of both signs: 0 ulp from the IEEE division, with two steps as with three
+// (tools/microbench/rcp_steps.cu, profiles/r02_s_rcp_steps.json) -- a fifth of the division's instructions, no slow-path call.
 __device__ __forceinline__ double fast_rcp(double g) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(g));
   double e = fma(-g, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-g, r, 1.0);
   r = fma(r, e, r);
   e = fma(-g, r, 1.0);
   r = fma(r, e, r);
@@ -433,11 +433,14 @@ __device__ __forceinline__ void bar_coef_neg(double g, double eps, double rt, co
 }
 
 // squared distance point -> segment with the case split of line_segment2d.cpp:61-75
+// sg: a segment record in the shared-memory stage (80-byte records from a 16-byte aligned base: three 16-byte loads)
 __device__ __forceinline__ double seg_dist2(const double* sg, double px, double py) {
-  const double x0 = px - sg[0], y0 = py - sg[1];
-  const double x1 = px - sg[2], y1 = py - sg[3];
-  const double proj = x0 * sg[4] + y0 * sg[5];
-  const double cr = x0 * sg[5] - y0 * sg[4];
+  const double2 s = *reinterpret_cast<const double2*>(sg), e = *reinterpret_cast<const double2*>(sg + 2);
+  const double2 u = *reinterpret_cast<const double2*>(sg + 4);
+  const double x0 = px - s.x, y0 = py - s.y;
+  const double x1 = px - e.x, y1 = py - e.y;
+  const double proj = x0 * u.x + y0 * u.y;
+  const double cr = x0 * u.y - y0 * u.x;
   const double d0 = fma(x0, x0, y0 * y0);
   const double d1 = fma(x1, x1, y1 * y1);
   double d = cr * cr;
@@ -543,7 +546,7 @@ __device__ __forceinline__ int nearest_segment(const double* sg0, const double* 
     const int hi = gi + kNearWin < S - 1 ? gi + kNearWin : S - 1;
     double best = 1.7976931348623157e308;
     int bi = gi;
-#pragma unroll 1
+#pragma unroll 1  // (unroll 2: -4.5 %, profiles/r02_t_ab_rcp_lds128_unroll.log -- eval_cost is at the edge of the instruction cache)
     for (int s = lo; s <= hi; ++s) {
       const double dd = s == gi ? ddg : seg_dist2(sg0 + s * kSegStride, xd, yd);
       if (dd < best) {
