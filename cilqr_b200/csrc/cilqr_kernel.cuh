@@ -400,7 +400,7 @@ __device__ __forceinline__ double fast_rcp(double g) {
   return r;
 }
 // barrier_function.h:115-140: coefficient of dx in the Jacobian (cj), of dx dx^T (co) and of ddx (cd)
-__device__ __forceinline__ void bar_coef(double g, double eps, double rt, const DevParams& P, double& cj, double& co,
+__device__ __forceinline__ void bar_coef(double g, double eps, double rt, double inv_eps2, double& cj, double& co,
                                          double& cd) {
   if (g < -eps) {
     const double inv = fast_rcp(g);
@@ -409,7 +409,7 @@ __device__ __forceinline__ void bar_coef(double g, double eps, double rt, const 
     co = q * inv;
     cd = q;
   } else {
-    cj = rt * (g + 2.0 * eps) * P.inv_eps2;
+    cj = rt * (g + 2.0 * eps) * inv_eps2;
     co = cj;
     cd = 0.0;
   }
@@ -417,7 +417,7 @@ __device__ __forceinline__ void bar_coef(double g, double eps, double rt, const 
 
 // the same coefficients with the Jacobian's negated (mj = -cj): in the log branch mj = cd = rt / g needs no sign flip (an
 // FP64 negation is a DADD), and the accumulation uses the free operand negation of the multiply-add
-__device__ __forceinline__ void bar_coef_neg(double g, double eps, double rt, const DevParams& P, double& mj, double& co,
+__device__ __forceinline__ void bar_coef_neg(double g, double eps, double rt, double inv_eps2, double& mj, double& co,
                                              double& cd) {
   if (g < -eps) {
     const double inv = fast_rcp(g);
@@ -426,7 +426,7 @@ __device__ __forceinline__ void bar_coef_neg(double g, double eps, double rt, co
     co = q * inv;
     cd = q;
   } else {
-    co = rt * (g + 2.0 * eps) * P.inv_eps2;
+    co = rt * (g + 2.0 * eps) * inv_eps2;
     mj = -co;
     cd = 0.0;
   }
@@ -511,6 +511,7 @@ __device__ __forceinline__ void stage_planes(const double* planes, int Kc, int l
     const double* src = planes + k_lo + kk + (size_t)r0 * Kc;
     unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
     const size_t sstep = (size_t)kRowsPerIter * Kc;
+#pragma unroll 1  // (asynchronous copies: nothing to overlap by unrolling, and this body is inlined four times)
     for (int row = r0; row < Mrows * 3; row += kRowsPerIter) {
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
       src += sstep;
@@ -566,7 +567,7 @@ __device__ __forceinline__ int nearest_segment(const double* sg0, const double* 
     const double thr = ub + gp[g * 3 + 2];
     if (fma(dcx, dcx, dcy * dcy) > thr * thr) continue;  // (NaN compares false: never pruned)
     const int s_hi = (g + 1) * kGroup < S ? (g + 1) * kGroup : S;
-#pragma unroll 2
+#pragma unroll 1  // (code size before ILP: profiles/r02_u_ab_unroll_reduction.log)
     for (int s = g * kGroup; s < s_hi; ++s) {
       const double dd = seg_dist2(sg0 + s * kSegStride, xd, yd);
       if (dd < best) {
@@ -685,7 +686,7 @@ __device__ __noinline__ void eval_cost(const Ctx& c_ref, const double* Xs, const
     // corridor half-planes of this knot
     BarAcc bc = {1.0, 0.0}, bc2 = {1.0, 0.0};  // two running products: two independent multiply chains
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (k - j0 / kDisc);
-#pragma unroll 2
+#pragma unroll 1  // (code size before ILP: profiles/r02_u_ab_unroll_reduction.log)
     for (int m = 0; m < Mw; m += 2) {
       if (m < M) {
         const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
@@ -758,7 +759,7 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, double* re
   }
   // every parameter and goal is loaded HERE, in one batch (one load latency): below, each would be a generic load
   // serialised behind the record stores that precede it
-  const double eps = P.eps, rt = P.rt, dt = P.dt;
+  const double eps = P.eps, rt = P.rt, inv_eps2 = P.inv_eps2, dt = P.dt;
   const double vmax = P.vmax, amin = P.amin, amax = P.amax, dmin = P.dmin, dmax = P.dmax;
   const double jmin = P.jmin, jmax = P.jmax, drmin = P.drmin, drmax = P.drmax;
   const double wx2 = 2.0 * P.wx, wy2 = 2.0 * P.wy, wth2 = 2.0 * P.wth, wv2 = 2.0 * P.wv, wa2 = 2.0 * P.wa, wd2 = 2.0 * P.wd;
@@ -767,8 +768,8 @@ __device__ void linearize_knot(const Ctx& c, int k, const double* Xs, double* re
   // DynamicsConsJacbian / Hessian: each state (control) component carries a pair of bounds
   auto bound_pair = [&](double lo_g, double hi_g, double& dj, double& dh) {
     double cj0, cj1, co0, co1, cd;
-    bar_coef(lo_g, eps, rt, P, cj0, co0, cd);
-    bar_coef(hi_g, eps, rt, P, cj1, co1, cd);
+    bar_coef(lo_g, eps, rt, inv_eps2, cj0, co0, cd);
+    bar_coef(hi_g, eps, rt, inv_eps2, cj1, co1, cd);
     dj = cj1 - cj0;
     dh = co0 + co1;
   };
@@ -822,7 +823,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
   const int d = c.lane / kKnotsPerPass, kl = c.lane - d * kKnotsPerPass;
   // launch constants as values, loaded once (see bar_add)
   const int Kc = a.Kc, S_left = a.S_left;
-  const double eps = P.eps, rt = P.rt;
+  const double eps = P.eps, rt = P.rt, inv_eps2 = P.inv_eps2;
   const double o = P.off[d < kDisc ? d : 0];
   const double* planes_g = c.planes();
   const int32_t* cnt = c.cnt;
@@ -865,7 +866,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     auto plane = [&](double pa, double pb, double pc) {
       const double g = fma(pb, yd, pa * xd) - pc;
       double mj, co, cdd;
-      bar_coef_neg(g, eps, rt, P, mj, co, cdd);
+      bar_coef_neg(g, eps, rt, inv_eps2, mj, co, cdd);
       const double ca = pa * co, cb = pb * co;
       J0 = fma(-pa, mj, J0);
       J1 = fma(-pb, mj, J1);
@@ -876,7 +877,7 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
       D1 = fma(pb, cdd, D1);
     };
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (act ? kl : 0);
-#pragma unroll 2
+#pragma unroll 1  // (code size before ILP: profiles/r02_u_ab_unroll_reduction.log)
     for (int m = 0; m < Mw; ++m) {
       if (m < M) plane(w[m * kPlaneTile], w[m * kPlaneTile + kPlaneKnots], w[m * kPlaneTile + 2 * kPlaneKnots]);
     }
@@ -1088,6 +1089,7 @@ __device__ __noinline__ void backward_pass(const Ctx& c_ref, double lambda, doub
   auto prefetch = [&](int q, int s) {  // records of knots [4q, 4q+4) -> stage s (the context pads to whole chunks)
     const double* src = R + (size_t)q * kStageD;
     double* dst = ring + s * kStageD;
+#pragma unroll 1
     for (int i = lane; i < kStageD / 2; i += 32) cp_async16(dst + i * 2, src + i * 2);
     cp_async_commit();
   };
