@@ -879,7 +879,9 @@ __device__ void linearize_discs(const Ctx& c, int k0, int nk, const double* Xs, 
     const double* w = pbuf + (kTileBufs == 2 ? stage * pstride : 0) + (act ? kl : 0);
 #pragma unroll 1  // (code size before ILP: profiles/r02_u_ab_unroll_reduction.log)
     for (int m = 0; m < Mw; ++m) {
-      if (m < M) plane(w[m * kPlaneTile], w[m * kPlaneTile + kPlaneKnots], w[m * kPlaneTile + 2 * kPlaneKnots]);
+      // (loaded ahead of the validity branch: rows below Mw are staged for every knot of the tile)
+      const double pa = w[m * kPlaneTile], pb = w[m * kPlaneTile + kPlaneKnots], pc = w[m * kPlaneTile + 2 * kPlaneKnots];
+      if (m < M) plane(pa, pb, pc);
     }
     if (kTileBufs == 1 && g0 + kKnotsPerPass < nk) {
       __syncwarp();  // every lane is done with the tile

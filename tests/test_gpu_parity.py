@@ -334,7 +334,11 @@ def test_size_independent_properties_at_full_size(solver):
         nx = X[:, k] + dt * k2
         nx[:, 2], nx[:, 5] = wrap(nx[:, 2]), wrap(nx[:, 5])
         worst = max(worst, float(((nx - X[:, k + 1]).abs() / (X[:, k + 1].abs() + 1)).max()))
-    assert worst < 1e-12, worst
+    # (the production build contracts x + dt * k into one fused multiply-add; a diverging trial step of a scenario that ends
+    # in the lambda-overflow exit has |dt * k| ~ 1e4 in the heading, where half an ulp is 1e-12 -- and the wrap into
+    # [-pi, pi) turns that into an absolute error of the O(1) result.  The CPU restatement, unfused, checks to 1.5e-16.)
+    print(f"\n[properties] B={batch.B} N={batch.N}: worst one-step dynamics residual {worst:.2e}")
+    assert worst < 1e-10, worst
     assert (X[:, :, 2] >= -np.pi).all() and (X[:, :, 2] < np.pi).all()
     assert (U[:, :, 1] >= -np.pi).all() and (U[:, :, 1] < np.pi).all()
     assert set(S[:, 0].long().unique().tolist()) <= {0, 1, 2, 3, 4}
