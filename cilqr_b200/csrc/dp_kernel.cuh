@@ -155,11 +155,14 @@ struct RefPoint {
 // fmod(x, y) for y > 0, bit-exact: fmod is an exact operation, and for |x| < 2y its result is x itself or
 // x -/+ y, a difference that is exactly representable (Sterbenz) -- the general (slow, iterative) routine is only
 // needed for larger arguments, which headings never are
+// (out of line: libdevice's fmod is ~100 instructions, and normalize_angle is inlined at a dozen sites -- the kernel is
+// bound by instruction fetch, profiles/r02_dp_ncu_summary.txt: stall_no_instruction 7 of 15 cycles per issue)
+__device__ __noinline__ double fmod_general(double x, double y) { return fmod(x, y); }
 __device__ __forceinline__ double fmod_small(double x, double y) {
   const double ax = fabs(x);
   if (ax < y) return x;
   if (ax < 2.0 * y) return copysign(ax - y, x);
-  return fmod(x, y);
+  return fmod_general(x, y);
 }
 
 // math_utils.cpp:53-59
@@ -230,6 +233,7 @@ __device__ __forceinline__ bool polygon_is_point_in(const double* p, int nv, dou
                                                     double maxy, double x, double y) {
   if (x < minx || x > maxx || y < miny || y > maxy) return false;
   int j = nv - 1, c = 0;
+#pragma unroll 1
   for (int i = 0; i < nv; ++i) {
     const double xi = p[2 * i], yi = p[2 * i + 1], xj = p[2 * j], yj = p[2 * j + 1];
     if ((yi > y) != (yj > y)) {
@@ -249,8 +253,9 @@ __device__ __forceinline__ bool box_is_point_in(double px, double py, double cx,
 }
 
 // a polygon's axis-aligned bounds as Polygon2d::BuildFromPoints computes them (polygon2d.cpp:246-256)
-__device__ __forceinline__ void polygon_aabb(const double* p, int nv, double* o) {
+__device__ __noinline__ void polygon_aabb(const double* p, int nv, double* o) {
   double minx = p[0], maxx = p[0], miny = p[1], maxy = p[1];
+#pragma unroll 1
   for (int i = 1; i < nv; ++i) {
     minx = fmin(minx, p[2 * i]);
     maxx = fmax(maxx, p[2 * i]);
@@ -266,8 +271,10 @@ __device__ __forceinline__ bool aabb_disjoint(const double* o, double cx, double
 }
 
 // Polygon2d::HasOverlap(const Box2d&), polygon2d.cpp:150-165, after its bounding-box rejection
-__device__ bool polygon_overlaps_box(const double* p, int nv, const double* bb, double cx, double cy, double half) {
+// (out of line: reached only when the bounding boxes overlap)
+__device__ __noinline__ bool polygon_overlaps_box(const double* p, int nv, const double* bb, double cx, double cy, double half) {
   if (aabb_disjoint(bb, cx, cy, half)) return false;
+#pragma unroll 1
   for (int i = 0; i < nv; ++i)
     if (box_is_point_in(p[2 * i], p[2 * i + 1], cx, cy, half)) return true;
   if (polygon_is_point_in(p, nv, bb[0], bb[1], bb[2], bb[3], cx + half, cy - half)) return true;  // aabox2d.cpp:63-71

@@ -51,6 +51,8 @@ if __name__ == "__main__":
                       db.dyn_poly[b], db.dyn_nv[b])
         okc.append(dp.plan(sc, *db.start[b], cfg)[0])
     cpu_s = (time.perf_counter() - t0) / max(n, 1)
-    print(json.dumps({"B": B, "K": K, "obstacles": a.obstacles, "ms": ms, "traj_per_s": B / min(ms) * 1e3,
+    import hashlib
+    checksum = hashlib.sha1(coarse.cpu().numpy().tobytes() + ok.cpu().numpy().tobytes()).hexdigest()[:16]
+    print(json.dumps({"B": B, "K": K, "obstacles": a.obstacles, "ms": ms, "traj_per_s": B / min(ms) * 1e3, "checksum": checksum,
                       "planned_ok": int(ok.sum().item()), "cpu_s_per_scene_1_thread": cpu_s,
                       "cpu_ok_equal": bool(np.array_equal(np.array(okc, bool), ok[:n].cpu().numpy().astype(bool)))}))
