@@ -390,10 +390,16 @@ __device__ bool check_optimization_collision(const Args& a, int b, const double*
   if (nobs > 32) near = 0xffffffffu;
   const unsigned near_static = a.n_static >= 32 ? near : (near & ((1u << a.n_static) - 1u));
   const unsigned near_dyn = nobs > 32 ? 1u : (a.n_static >= 32 ? 0u : near >> a.n_static);
-  return check_static(a, b, obb, near_static != 0 || a.n_static > 32, fx, fy, half) ||
-         check_static(a, b, obb, near_static != 0 || a.n_static > 32, rx, ry, half) ||
-         (near_dyn != 0 && (check_dynamic(a, b, obb, sbb, sidx, point, time, fx, fy, half) ||
-                            check_dynamic(a, b, obb, sbb, sidx, point, time, rx, ry, half)));
+  // front disc, then rear disc, static before dynamic (the reference's order); one copy of each check in the code
+  const bool any_static = near_static != 0 || a.n_static > 32;
+#pragma unroll 1
+  for (int w = 0; w < 2; ++w)
+    if (check_static(a, b, obb, any_static, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
+  if (near_dyn == 0) return false;
+#pragma unroll 1
+  for (int w = 0; w < 2; ++w)
+    if (check_dynamic(a, b, obb, sbb, sidx, point, time, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
+  return false;
 }
 
 struct Start {
@@ -431,20 +437,31 @@ __device__ __forceinline__ Segment make_segment(const Args& a, const Start& st, 
   return g;
 }
 
-// GetCollisionCost, dp_planner.cpp:40-85; pt < 0: the parent is the start state
+// the same segment from end points the caller already holds (GetCost evaluates the lateral offsets of the grandparent,
+// the parent and the child itself -- the same function of the same stations, so the values are the same bits)
+__device__ __forceinline__ Segment segment_of(double p_s, double p_l, double cur_l, double station, int nseg) {
+  Segment g;
+  g.nseg = nseg;
+  g.p_s = p_s;
+  g.p_l = p_l;
+  g.s_step = station / nseg;
+  g.l_step = (cur_l - p_l) / nseg;
+  return g;
+}
+
+// GetCollisionCost, dp_planner.cpp:40-85; pt < 0: the parent is the start state.  (grandparent_s, grandparent_l),
+// (parent_s, parent_l), cur_l: the end points GetCost computed (start state where there is no such ancestor) -- seven
+// reference-line evaluations per transition become three, and four inlined copies of evaluate_station go away.
 __device__ double collision_cost(const Args& a, int b, const double* obb, const double* sbb, const int* sidx,
-                                 const Start& st, const Cell* cells, int pt, int psi, int pli, int ct, int csi, int cli) {
-  double parent_s = st.s, grandparent_s = st.s;
+                                 const Start& st, int pt, int psi, int ct, int csi, double grandparent_s,
+                                 double grandparent_l, double parent_s, double parent_l, double cur_l) {
   double last_l = st.l, last_s = st.s;
   if (pt >= 0) {
-    const Cell cell = cells[pt * NP + psi * NL + pli];
-    parent_s = cell.current_s;
-    if (pt > 0) grandparent_s = cells[(pt - 1) * NP + cell.ps * NL + cell.pl].current_s;
-    const Segment prev = make_segment(a, st, grandparent_s, cell.pl, pt, psi, pli);
+    const Segment prev = segment_of(grandparent_s, grandparent_l, parent_l, a.lat.station_[psi], a.lat.nseg[pt]);
     last_l = prev.p_l + (prev.nseg - 1) * prev.l_step;
     last_s = prev.p_s + (prev.nseg - 1) * prev.s_step;
   }
-  const Segment g = make_segment(a, st, parent_s, pli, ct, csi, cli);
+  const Segment g = segment_of(parent_s, parent_l, cur_l, a.lat.station_[csi], a.lat.nseg[ct]);
   const double parent_time = pt < 0 ? 0.0 : a.lat.time_[pt];
   for (int i = 0; i < g.nseg; ++i) {
     const double ps = g.p_s + i * g.s_step, pl = g.p_l + i * g.l_step;
@@ -486,7 +503,8 @@ __device__ double get_cost(const Args& a, int b, const double* obb, const double
   const double ds0 = parent_s - grandparent_s;
   const double dl0 = parent_l - grandparent_l;
   *cur_s_out = cur_s;
-  const double cost_obstacle = collision_cost(a, b, obb, sbb, sidx, st, cells, pt, psi, pli, ct, csi, cli);
+  const double cost_obstacle = collision_cost(a, b, obb, sbb, sidx, st, pt, psi, ct, csi, grandparent_s, grandparent_l,
+                                              parent_s, parent_l, cur_l);
   if (cost_obstacle >= a.w_obstacle) return a.w_obstacle;
   const double cost_lateral = fabs(cur_l);
   const double cost_lateral_change = fabs(parent_l - cur_l) / (a.lat.station_[csi] + kDpEps);
