@@ -298,12 +298,29 @@ __device__ __forceinline__ int barrier_upper_bound(const double* bar, int NB, do
 // obb: per scenario, in shared memory: the bounds of every static polygon, then for every dynamic obstacle the
 // bounds of ALL its samples (a box that misses those misses every sample's own bounding box, which is the
 // reference's first test)
-__device__ bool check_static(const Args& a, int b, const double* obb, bool any_near, double cx, double cy, double half) {
+__device__ __forceinline__ int lowest_bit(unsigned m) {
+#ifdef __CUDA_ARCH__
+  return __ffs(m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+// near: bit o set = static obstacle o's bounds reach the union of the two disc boxes (an obstacle whose bit is clear is
+// disjoint from either disc box, i.e. the loop below would skip it); all = true: every obstacle is visited (> 32 obstacles)
+__device__ bool check_static(const Args& a, int b, const double* obb, unsigned near, bool all, double cx, double cy, double half) {
   const double* polys = a.static_poly + (size_t)b * a.n_static * a.V * 2;
   const int* nv = a.static_nv + (size_t)b * a.n_static;
-  for (int o = 0; any_near && o < a.n_static; ++o) {
-    if (aabb_disjoint(obb + 4 * o, cx, cy, half)) continue;
-    if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], obb + 4 * o, cx, cy, half)) return true;
+  if (all) {
+    for (int o = 0; o < a.n_static; ++o) {
+      if (aabb_disjoint(obb + 4 * o, cx, cy, half)) continue;
+      if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], obb + 4 * o, cx, cy, half)) return true;
+    }
+  } else {
+    for (unsigned m = near; m != 0; m &= m - 1) {
+      const int o = lowest_bit(m);
+      if (aabb_disjoint(obb + 4 * o, cx, cy, half)) continue;
+      if (polygon_overlaps_box(polys + (size_t)o * a.V * 2, nv[o], obb + 4 * o, cx, cy, half)) return true;
+    }
   }
   if (a.NB == 0) return false;
   const double minx = cx - half, maxx = cx + half;
@@ -352,9 +369,12 @@ __device__ __forceinline__ int dynamic_sample(const Args& a, size_t ob, double t
   }
   return lo >= ns ? ns - 1 : lo;
 }
+// near / all: as in check_static, bit o = dynamic obstacle o
 __device__ bool check_dynamic(const Args& a, int b, const double* obb, const double* sbb, const int* sidx, int point,
-                              double time, double cx, double cy, double half) {
-  for (int o = 0; o < a.n_dyn; ++o) {
+                              double time, unsigned near, bool all, double cx, double cy, double half) {
+  unsigned m = near;
+  for (int oi = 0; all ? oi < a.n_dyn : m != 0; ++oi, m &= m - 1) {
+    const int o = all ? oi : lowest_bit(m);
     if (aabb_disjoint(obb + 4 * (a.n_static + o), cx, cy, half)) continue;
     const size_t ob = (size_t)b * a.n_dyn + o;
     const int lo = sidx ? sidx[o * kMaxSeg + point] : dynamic_sample(a, ob, time);
@@ -391,14 +411,15 @@ __device__ bool check_optimization_collision(const Args& a, int b, const double*
   const unsigned near_static = a.n_static >= 32 ? near : (near & ((1u << a.n_static) - 1u));
   const unsigned near_dyn = nobs > 32 ? 1u : (a.n_static >= 32 ? 0u : near >> a.n_static);
   // front disc, then rear disc, static before dynamic (the reference's order); one copy of each check in the code
-  const bool any_static = near_static != 0 || a.n_static > 32;
+  // (only the obstacles that passed the pre-screen are visited: the others are disjoint from either disc box)
+  const bool all = nobs > 32;
 #pragma unroll 1
   for (int w = 0; w < 2; ++w)
-    if (check_static(a, b, obb, any_static, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
+    if (check_static(a, b, obb, near_static, all, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
   if (near_dyn == 0) return false;
 #pragma unroll 1
   for (int w = 0; w < 2; ++w)
-    if (check_dynamic(a, b, obb, sbb, sidx, point, time, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
+    if (check_dynamic(a, b, obb, sbb, sidx, point, time, near_dyn, all, w == 0 ? fx : rx, w == 0 ? fy : ry, half)) return true;
   return false;
 }
 
