@@ -55,17 +55,21 @@ int launch(cilqr_handle* h, const CilqrDpConfig* cfg, const CilqrDpIn* in, const
   a.waypoints = out->waypoints;
   // the barrier grid: built on the host, uploaded to the handle's scratch (slot 0)
   std::vector<int> gs, gi;
-  dp::build_grid(host_barrier, in->NB, a.lat.radius, &a, &gs, &gi);
+  std::vector<double> gxy;
+  dp::build_grid(host_barrier, in->NB, a.lat.radius, &a, &gs, &gi, &gxy);
   {
     char* g = nullptr;
-    const size_t b0 = (gs.size() * sizeof(int) + 255) & ~(size_t)255, b1 = gi.size() * sizeof(int);
-    int rcg = cilqr_internal_scratch(h, 0, b0 + b1, &g);
+    const size_t b0 = (gs.size() * sizeof(int) + 255) & ~(size_t)255, b1 = (gi.size() * sizeof(int) + 255) & ~(size_t)255;
+    const size_t b2 = gxy.size() * sizeof(double);
+    int rcg = cilqr_internal_scratch(h, 0, b0 + b1 + b2, &g);
     if (rcg != CILQR_OK) return rcg;
     CKH(cudaMemcpyAsync(g, gs.data(), gs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CKH(cudaMemcpyAsync(g + b0, gi.data(), b1, cudaMemcpyHostToDevice, st));
-    CKH(cudaStreamSynchronize(st));  // gs / gi are locals
+    CKH(cudaMemcpyAsync(g + b0, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKH(cudaMemcpyAsync(g + b0 + b1, gxy.data(), b2, cudaMemcpyHostToDevice, st));
+    CKH(cudaStreamSynchronize(st));  // gs / gi / gxy are locals
     a.grid_start = (const int*)g;
     a.grid_idx = (const int*)(g + b0);
+    a.grid_xy = (const double*)(g + b0 + b1);
   }
   // the per-sample bounds of the dynamic obstacles go to shared memory while two CTAs per SM still fit (~110 KB each)
   a.use_sample_bounds = dp::smem_bytes(a.lat.K, in->n_static + in->n_dyn, in->n_dyn, in->T, true) <= 110 * 1024 ? 1 : 0;

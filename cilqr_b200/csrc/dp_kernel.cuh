@@ -94,6 +94,7 @@ struct Args {
   int gnx, gny;
   const int* grid_start;
   const int* grid_idx;
+  const double* grid_xy;  // [NB][2]: the points in grid order (grid_xy[k] = barrier[grid_idx[k]]), one load level less per point
   const double* start;    // [B][3]
   const double* static_poly;
   const int* static_nv;
@@ -114,7 +115,7 @@ struct Args {
 // at most 5 x 5 cells; a row of cells is one contiguous range of the CSR list).  cell(p) = floor((p - origin) * ginv) is monotone in p, and the kernel computes the
 // cells of a query with the same expression, so every point the box test can accept lies in a scanned cell.
 inline void build_grid(const double* barrier, int NB, double half, Args* a, std::vector<int>* start,
-                       std::vector<int>* idx) {
+                       std::vector<int>* idx, std::vector<double>* xy) {
   const double cs = (2.0 * half + 1e-6) / 4.0;
   double minx = 0, maxx = 0, miny = 0, maxy = 0;
   for (int i = 0; i < NB; ++i) {
@@ -141,6 +142,11 @@ inline void build_grid(const double* barrier, int NB, double half, Args* a, std:
   for (size_t c = 0; c < cells; ++c) (*start)[c + 1] += (*start)[c];
   std::vector<int> fill(start->begin(), start->end() - 1);
   for (int i = 0; i < NB; ++i) (*idx)[fill[cell[i]]++] = i;
+  xy->assign(2 * (size_t)(NB > 0 ? NB : 1), 0.0);
+  for (int k = 0; k < NB; ++k) {
+    (*xy)[2 * (size_t)k] = barrier[2 * (size_t)(*idx)[k]];
+    (*xy)[2 * (size_t)k + 1] = barrier[2 * (size_t)(*idx)[k] + 1];
+  }
 }
 
 struct Cell {
@@ -340,12 +346,11 @@ __device__ bool check_static(const Args& a, int b, const double* obb, unsigned n
   for (int iy = iy0; iy <= iy1; ++iy) {
     const int k1 = a.grid_start[iy * a.gnx + ix1 + 1];
     for (int k = a.grid_start[iy * a.gnx + ix0]; k < k1; ++k) {
-      const int i = a.grid_idx[k];
-      const double px = a.barrier[(size_t)i * 2], py = a.barrier[(size_t)i * 2 + 1];
+      const double px = a.grid_xy[(size_t)k * 2], py = a.grid_xy[(size_t)k * 2 + 1];
       if (!box_is_point_in(px, py, cx, cy, half)) continue;
       if (!(px <= maxx)) continue;  // index >= upper_bound(maxx)
       if (px > minx) return true;
-      if (i == barrier_upper_bound(a.barrier, a.NB, minx) - 1) return true;
+      if (a.grid_idx[k] == barrier_upper_bound(a.barrier, a.NB, minx) - 1) return true;
     }
   }
   return false;

@@ -40,9 +40,11 @@ extern "C" int emul_dp(const double* cfg, const int* dims, const double* ref, co
   a.dyn_time = dyn_time; a.dyn_samples = dyn_samples; a.dyn_poly = dyn_poly; a.dyn_nv = dyn_nv;
   a.trajectory = trajectory; a.coarse = coarse; a.xytheta = xytheta; a.ok = ok; a.cost = cost; a.waypoints = waypoints;
   std::vector<int> gs, gi;
-  dp::build_grid(barrier, a.NB, a.lat.radius, &a, &gs, &gi);
+  std::vector<double> gxy;
+  dp::build_grid(barrier, a.NB, a.lat.radius, &a, &gs, &gi, &gxy);
   a.grid_start = gs.data();
   a.grid_idx = gi.data();
+  a.grid_xy = gxy.data();
   a.use_sample_bounds = dp::smem_bytes(a.lat.K, a.n_static + a.n_dyn, a.n_dyn, a.T, true) <= sizeof(dp::dp_smem) ? 1 : 0;
   gridDim.x = 1;
   dp::dp_plan_kernel(a);
