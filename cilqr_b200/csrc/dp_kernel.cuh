@@ -543,7 +543,10 @@ __device__ double get_cost(const Args& a, int b, const double* obb, const double
          a.w_longitudinal_velocity_change * cost_longitudinal_velocity_change;
 }
 
-constexpr int kMaxThreads = 256;
+// 512 threads x 2 CTAs per SM = 32 warps per SM at 64 registers per thread: the walk is latency bound (dependent FP64 chains, L1/L2
+// loads, half the lanes of a warp active), and doubling the resident warps pays more than the registers cost
+// (profiles/r02_dp_ab_5_occupancy.log: 256 x 2 at 128 registers 32.7k plans/s, 384 x 2 38.0k, 512 x 2 38.6k)
+constexpr int kMaxThreads = 512;
 constexpr int kMaxKnots = 512;
 
 // shared-memory layout (bytes); K <= kMaxKnots
@@ -553,7 +556,7 @@ __host__ __device__ inline size_t smem_bytes(int K, int n_obstacles, int n_dyn, 
          sizeof(int) * kMaxSeg * (size_t)n_dyn + 16 + (sample_bounds ? sizeof(double) * 4 * (size_t)n_dyn * T : 0);
 }
 
-__global__ void __launch_bounds__(kMaxThreads) dp_plan_kernel(const __grid_constant__ Args a) {
+__global__ void __launch_bounds__(kMaxThreads, 2) dp_plan_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(16) unsigned char dp_smem[];
   Cell* cells = reinterpret_cast<Cell*>(dp_smem);                        // [NT][NP]
   double* delta = reinterpret_cast<double*>(cells + NT * NP);             // [NP parents][NP children]

@@ -10,7 +10,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __align__(x)
 #define __shared__
 struct emul_dim3 { int x; };

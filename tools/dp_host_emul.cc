@@ -12,7 +12,7 @@
 #define __grid_constant__
 #define __noinline__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __align__(x)
 #define __shared__
 static inline void __syncthreads() {}
