@@ -601,7 +601,7 @@ def main():
         torch.cuda.synchronize()
         # F host threads, one handle each, every call blocking (ctypes releases the GIL): the H2D stream of one
         # batch and the drain of another overlap, exactly as two planner threads sharing a GPU would
-        per_thread = 2
+        per_thread = max(2, -(-a.steps // F))  # about as many steps as the device-resident leg (K = --steps)
         n_e2e = per_thread * F
 
         def worker(f):
